@@ -1,0 +1,183 @@
+/*
+ * include/sddmm_b200.h -- the drop-in boundary of the B200-native SDDMM engine.
+ *
+ * A plain C ABI (no C++/torch types) over libsddmm_b200.so.  Each entry point names the
+ * interface of CX9898/sddmm-gpu (paths relative to the reference root) that it replaces; the
+ * reference-side binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - uint32_t indices everywhere (the reference's UIN, include/TensorCoreConfig.cuh:10);
+ *     SDDMM_NULL_VALUE = 0xFFFFFFFF (TensorCoreConfig.cuh:11-12); row panel = 16 rows, column
+ *     block = 16 columns (include/BSMR.hpp:8-10).
+ *   - A is row-major M x K; B is COLUMN-major K x N (N contiguous rows of K floats);
+ *     P has one float per stored (row, col) of S, in the CSR order of colIdx
+ *     (layout contract of include/Matrix.hpp + src/sddmmKernel.cu:2518-2537).
+ *   - P[i] = sum_k A[row,k] * B[k,col].  The values of S are NOT read (src/host.cpp:62-73).
+ *   - Pointers named d_* are device pointers on the current CUDA device, h_* are host pointers.
+ *   - Every function returning int returns 0 on success and a non-zero SDDMM_E_* code on error;
+ *     sddmm_last_error() returns a thread-local human-readable message.  (The reference returns
+ *     void and prints; the C++ shim in sddmm-gpu_b200/csrc/host keeps those signatures.)
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     SDDMM_E_CUDA.
+ */
+#ifndef SDDMM_B200_H
+#define SDDMM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDDMM_NULL_VALUE 0xFFFFFFFFu
+#define SDDMM_ROW_PANEL 16u
+#define SDDMM_BLOCK_COLS 16u
+
+enum {
+  SDDMM_OK = 0,
+  SDDMM_E_ARG = 1,      /* bad argument (null pointer, K % 4 != 0, capacity too small ...) */
+  SDDMM_E_CUDA = 2,     /* CUDA runtime error / no device */
+  SDDMM_E_NOMEM = 3,    /* device allocation failed */
+  SDDMM_E_UNSUPPORTED = 4
+};
+
+/* ---- library ------------------------------------------------------------------------------ */
+int sddmm_b200_abi_version(void);            /* bumps when this header changes incompatibly */
+const char* sddmm_last_error(void);
+/* number of kernels this library has launched on this thread since the last reset (bench.py's
+ * gpu_launches) */
+uint64_t sddmm_launch_count(void);
+void sddmm_launch_count_reset(void);
+
+/* ---- a2: histogram block width --------------------------------------------------------------
+ * replaces calculateBlockSize(const CSR&)          src/rowReordering.cu:1009-1025
+ * free_mem_bytes == 0 -> query cudaMemGetInfo like the reference does (result then depends on
+ * the device's free memory); pass an explicit value for reproducibility. */
+uint32_t bsmr_calc_block_size(uint32_t M, uint32_t N, uint64_t free_mem_bytes);
+
+/* ---- a3-a6: row-similarity reordering ---------------------------------------------------------
+ * replaces bsa_rowReordering_gpu(matrix, alpha, block_size, num_clusters, time)
+ *                                                  src/rowReordering.cu:1027-1095
+ *          (calculateDispersion :49-93/:478-501, host sorts :1060-1062/:990,
+ *           get_permutation_gpu :893-1007, bsa_clustering :325-432, zero-row strip :1081-1090)
+ * and, through it, BSMR::rowReordering             src/BSMR.cpp:27-50.
+ * block_size == 0 -> bsmr_calc_block_size(M, N, 0).
+ * d_reorderedRows: capacity M; *numRows receives the number of non-empty rows written.
+ * numClusters (optional) receives the reference's value (incl. its :996 quirk).
+ * ms (optional) receives device time in milliseconds. */
+int bsmr_row_reorder_dev(const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N,
+                         uint32_t nnz, float alpha, uint32_t block_size, uint32_t* d_reorderedRows,
+                         uint32_t* numRows, int32_t* numClusters, float* ms, void* stream);
+/* host-buffer form (what BSMR::rowReordering consumes/produces: host CSR in, host vector out) */
+int bsmr_row_reorder(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, uint32_t N,
+                     uint32_t nnz, float alpha, uint32_t block_size, uint32_t* h_reorderedRows,
+                     uint32_t* numRows, int32_t* numClusters, float* ms);
+
+/* optional introspection used by the parity tests (K1 encode / dispersion, a3):
+ * d_dispersion[M]; returns nbpr in *numBlocksPerRow. */
+int bsmr_dispersion_dev(const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N,
+                        uint32_t nnz, uint32_t block_size, uint32_t* d_dispersion,
+                        uint32_t* numBlocksPerRow, void* stream);
+
+/* ---- a7 + a8: column reordering, dense/sparse split and the RPHM device layout ---------------
+ * replaces colReordering_cpu(...)                   src/colReordering.cu:274-404
+ *          BSMR::colReordering                      src/BSMR.cpp:52-81
+ *          RPHM::RPHM(matrix, bsmr)                 src/BSMR.cpp:83-265
+ * The layout object owns device copies of every array named in include/BSMR.hpp:39-49, 85-104.
+ * panelBegin/panelEnd select a contiguous range of row panels of the reordered matrix (multi-GPU
+ * row-panel shards); pass 0 / UINT32_MAX for all panels.  Offsets inside a shard
+ * are relative to the shard; sparseValues / blockValues still hold GLOBAL CSR indices. */
+typedef struct bsmr_layout bsmr_layout;
+
+int bsmr_layout_build_dev(const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N,
+                          uint32_t nnz, const uint32_t* d_reorderedRows, uint32_t numRows, float delta,
+                          uint32_t panelBegin, uint32_t panelEnd, bsmr_layout** out, float* msColReorder,
+                          float* msRphm, void* stream);
+int bsmr_layout_build(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, uint32_t N,
+                      uint32_t nnz, const uint32_t* h_reorderedRows, uint32_t numRows, float delta,
+                      bsmr_layout** out, float* msColReorder, float* msRphm);
+void bsmr_layout_destroy(bsmr_layout*);
+
+typedef enum {
+  BSMR_REORDERED_ROWS = 0,      /* [numRows]      BSMR::reorderedRows()      */
+  BSMR_DENSE_COLS = 1,          /* [denseColOffsets[P]]                       */
+  BSMR_DENSE_COL_OFFSETS = 2,   /* [P+1]                                      */
+  BSMR_SPARSE_COLS = 3,         /* [sparseColOffsets[P]] (sentinel N included)*/
+  BSMR_SPARSE_COL_OFFSETS = 4,  /* [P+1]                                      */
+  BSMR_SPARSE_VALUE_OFFSETS = 5,/* [P+1]                                      */
+  RPHM_BLOCK_OFFSETS = 6,       /* [P+1]                                      */
+  RPHM_BLOCK_VALUES = 7,        /* [numBlocks*256] CSR index or NULL_VALUE    */
+  RPHM_SPARSE_VALUES = 8,       /* [numSparse] CSR index                      */
+  RPHM_SPARSE_RELATIVE_ROWS = 9,/* [numSparse] 0..15                          */
+  RPHM_SPARSE_COL_INDICES = 10, /* [numSparse]                                */
+  RPHM_DENSE_ROW_PANEL_IDS = 11,
+  RPHM_DENSE_COL_BLOCK_ITERS = 12,
+  RPHM_SPARSE_ROW_PANEL_IDS = 13,
+  RPHM_SPARSE_COL_BLOCK_ITERS = 14,
+  BSMR_ARRAY_COUNT = 15
+} bsmr_array_id;
+
+typedef struct {
+  uint32_t M, N, nnz;
+  uint32_t numRows;        /* non-empty rows (|reorderedRows|) covered by this layout */
+  uint32_t numRowPanels;   /* BSMR::numRowPanels()                                    */
+  uint32_t panelBegin;     /* first global panel of this shard                        */
+  uint32_t numDenseBlocks; /* RPHM::getNumDenseBlocks()                               */
+  uint32_t numSparseValues;
+  uint32_t numDenseValues; /* stored entries that fall in dense blocks                */
+  uint32_t maxNumDenseColBlocksInRowPanel;
+  uint32_t maxNumSparseColBlocksInRowPanel;
+  uint32_t numDenseThreadBlocks;
+  uint32_t numSparseThreadBlocks;
+} bsmr_layout_info;
+
+int bsmr_layout_get_info(const bsmr_layout*, bsmr_layout_info* out);
+size_t bsmr_layout_array_len(const bsmr_layout*, bsmr_array_id which);
+const uint32_t* bsmr_layout_array_dev(const bsmr_layout*, bsmr_array_id which);
+int bsmr_layout_array_to_host(const bsmr_layout*, bsmr_array_id which, uint32_t* h_dst, size_t capacity);
+
+/* ---- a9-a11: the SDDMM itself ---------------------------------------------------------------
+ * replaces sddmm_gpu(M, N, K, dA, dB, rphm, dP, logger)   src/sddmmKernel.cu:2539-2663
+ *          sddmm_gpu_k32(...)                             src/sddmmKernel.cu:2665-2762
+ *          and the kernels they launch (:213-351, :355-488, :1994-2104, :2109-2199).
+ * One call = one pass: dense-block tcgen05 kernel and residual CUDA-core kernel, concurrently.
+ * K must be a positive multiple of 4 (16-byte rows); the reference asks for K % 32 == 0.
+ * Entries of d_P not covered by this layout (other shards) are left untouched. */
+int sddmm_run_dev(const bsmr_layout*, uint32_t K, const float* d_A, const float* d_B, float* d_P,
+                  void* stream);
+/* `iters` timed passes after `warmup` untimed ones; ms_* are per-pass means (CUDA events on the
+ * launching streams).  Any of the three outputs may be NULL. */
+int sddmm_run_timed_dev(const bsmr_layout*, uint32_t K, const float* d_A, const float* d_B, float* d_P,
+                        int warmup, int iters, float* msDense, float* msSparse, float* msTotal);
+/* replaces sddmm_gpu(const Matrix&, const Matrix&, const RPHM&, CSR&, Logger&)
+ *                                                         src/sddmmKernel.cu:2518-2537
+ * host A, B in; host P out; H2D and D2H inside the call. msTotal (optional) = whole call. */
+int sddmm_run_host(const bsmr_layout*, uint32_t K, const float* h_A, const float* h_B, float* h_P,
+                   float* msTotal);
+
+/* ---- whole path on host buffers ----------------------------------------------------------------
+ * replaces sddmm(options, A, B, P, logger)                src/sddmm.cu:10-39
+ * = row reorder -> layout -> one SDDMM pass.  `layoutOut` (optional) receives the layout so the
+ * caller can read the BSMR/RPHM arrays or re-run; otherwise it is destroyed before returning. */
+typedef struct {
+  float rowReorderMs, colReorderMs, rphmMs, sddmmMs;
+  int32_t numClusters;
+  uint32_t blockSize;
+} sddmm_stats;
+int sddmm_host(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, uint32_t N, uint32_t nnz,
+               uint32_t K, const float* h_A, const float* h_B, float alpha, float delta,
+               uint32_t block_size, float* h_P, sddmm_stats* stats, bsmr_layout** layoutOut);
+
+/* ---- e: multi-GPU row-panel sharding ----------------------------------------------------------
+ * (no reference counterpart: the reference is single-GPU.)  Cuts the P row panels of the
+ * reordered matrix into `numShards` contiguous ranges with equal non-zero counts; cuts[s] ..
+ * cuts[s+1] is shard s (numShards+1 entries).  Host arrays in, host array out. */
+int bsmr_shard_plan(const uint32_t* h_rowOff, const uint32_t* h_reorderedRows, uint32_t numRows,
+                    uint32_t numShards, uint32_t* h_cuts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDDMM_B200_H */

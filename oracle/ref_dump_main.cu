@@ -67,13 +67,9 @@ int main(int argc, char** argv) {
   // src/sddmm.cu:10-39, spelled out so the intermediates can be dumped
   BSMR bsmr(alpha, delta, S, 1);
   RPHM rphm(S, bsmr);
-  Logger logger;
-  logger.numITER_ = numIter;
-  sparseMatrix::CSR<float> P(S);
-  sddmm_gpu(mA, mB, rphm, P, logger);
-  cudaDeviceSynchronize();
-  const cudaError_t err = cudaGetLastError();
-
+  // layout arrays first: a faulting SDDMM kernel poisons the context (on sm_100 the reference's
+  // K>32 residual kernel dies with cudaErrorIllegalInstruction: its __shfl_xor_sync mask
+  // `(1 << tId) | (1 << (tId ^ 1))` (src/sddmmKernel.cu:2096) is 0 for threadIdx.x >= 32)
   dump(out, "reorderedRows.u32", bsmr.reorderedRows());
   dump(out, "denseCols.u32", bsmr.denseCols());
   dump(out, "denseColOffsets.u32", bsmr.denseColOffsets());
@@ -89,6 +85,14 @@ int main(int argc, char** argv) {
   dump(out, "denseColBlockIters.u32", d2h(rphm.denseColBlockIters()));
   dump(out, "sparseRowPanelIds.u32", d2h(rphm.sparseRowPanelIds()));
   dump(out, "sparseColBlockIters.u32", d2h(rphm.sparseColBlockIters()));
+  const UIN numDenseBlocks = rphm.getNumDenseBlocks();
+
+  Logger logger;
+  logger.numITER_ = numIter;
+  sparseMatrix::CSR<float> P(S);
+  sddmm_gpu(mA, mB, rphm, P, logger);
+  cudaDeviceSynchronize();
+  const cudaError_t err = cudaGetLastError();
   dump(out, "P.f32", P.values());
 
   // the reference's own oracle + tolerance (src/sddmm.cu:41-59)
@@ -107,7 +111,7 @@ int main(int argc, char** argv) {
   fprintf(m, "row_reorder_ms %.6f\ncol_reorder_ms %.6f\nsddmm_ms %.6f\n", bsmr.rowReorderingTime(),
           bsmr.colReorderingTime(), logger.sddmmTime_);
   fprintf(m, "gflops %.6f\n", 2.0 * nnz * K / (logger.sddmmTime_ * 1e6));
-  fprintf(m, "num_dense_blocks %u\nnum_sparse_values %u\n", rphm.getNumDenseBlocks(),
+  fprintf(m, "num_dense_blocks %u\nnum_sparse_values %u\n", numDenseBlocks,
           bsmr.sparseValueOffsets().empty() ? 0u : bsmr.sparseValueOffsets().back());
   fprintf(m, "max_dense_blocks %u\nnum_dense_tb %u\nnum_sparse_tb %u\nmax_sparse_tb %u\n",
           rphm.maxNumDenseColBlocksInRowPanel(), rphm.numDenseThreadBlocks(),

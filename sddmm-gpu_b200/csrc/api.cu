@@ -1,0 +1,320 @@
+// api.cu -- the C ABI of include/sddmm_b200.h.  Thin: argument checks, H2D/D2H for the host-buffer
+// forms, exception -> error code translation.  No CPU compute path exists behind any entry point.
+#include <mutex>
+#include <vector>
+
+#include "layout.cuh"
+#include "reorder_rows.cuh"
+#include "sddmm_kernels.cuh"
+
+namespace sb {
+thread_local u64 g_launches = 0;
+static thread_local std::string g_err;
+void set_last_error(const std::string& m) { g_err = m; }
+int device_sm_count() {
+  int dev = 0, n = 0;
+  SB_CUDA(cudaGetDevice(&dev));
+  SB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  return n;
+}
+}  // namespace sb
+
+using namespace sb;
+
+#define API_BEGIN try {
+#define API_END                                   \
+  }                                               \
+  catch (const sb::Error& e) {                    \
+    sb::set_last_error(e.what());                 \
+    return e.code;                                \
+  }                                               \
+  catch (const std::exception& e) {               \
+    sb::set_last_error(e.what());                 \
+    return SDDMM_E_CUDA;                          \
+  }                                               \
+  return SDDMM_OK;
+
+static void require(bool ok, const char* what) {
+  if (!ok) fail(SDDMM_E_ARG, "invalid argument: %s", what);
+}
+static void require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    fail(SDDMM_E_CUDA, "no CUDA device available (%s): libsddmm_b200 has no CPU fallback",
+         e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+}
+
+extern "C" {
+
+int sddmm_b200_abi_version(void) { return 1; }
+const char* sddmm_last_error(void) { return sb::g_err.c_str(); }
+uint64_t sddmm_launch_count(void) { return sb::g_launches; }
+void sddmm_launch_count_reset(void) { sb::g_launches = 0; }
+
+uint32_t bsmr_calc_block_size(uint32_t M, uint32_t N, uint64_t free_mem_bytes) {
+  if (free_mem_bytes == 0) {
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess || fr == 0) {
+      sb::set_last_error("bsmr_calc_block_size: cudaMemGetInfo failed (no device?)");
+      return 0;
+    }
+    free_mem_bytes = fr;
+  }
+  return calc_block_size(M, N, free_mem_bytes);
+}
+
+int bsmr_row_reorder_dev(const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N, uint32_t nnz,
+                         float alpha, uint32_t block_size, uint32_t* d_reorderedRows, uint32_t* numRows,
+                         int32_t* numClusters, float* ms, void* stream) {
+  API_BEGIN
+  require_device();
+  require(d_rowOff && d_colIdx && d_reorderedRows && numRows, "null pointer");
+  if (block_size == 0) block_size = bsmr_calc_block_size(M, N, 0);
+  require(block_size > 0, "block_size");
+  cudaStream_t s = (cudaStream_t)stream;
+  Timer t(s);
+  t.start();
+  row_reorder_dev(d_rowOff, d_colIdx, M, N, nnz, alpha, block_size, d_reorderedRows, numRows, numClusters, nullptr, s);
+  const float el = t.stop();
+  if (ms) *ms = el;
+  API_END
+}
+
+int bsmr_row_reorder(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, uint32_t N, uint32_t nnz,
+                     float alpha, uint32_t block_size, uint32_t* h_reorderedRows, uint32_t* numRows,
+                     int32_t* numClusters, float* ms) {
+  API_BEGIN
+  require_device();
+  require(h_rowOff && h_colIdx && h_reorderedRows && numRows, "null pointer");
+  DevBuf<u32> ro((size_t)M + 1), ci(nnz ? nnz : 1), out(M ? M : 1);
+  SB_CUDA(cudaMemcpy(ro.get(), h_rowOff, ((size_t)M + 1) * 4, cudaMemcpyHostToDevice));
+  SB_CUDA(cudaMemcpy(ci.get(), h_colIdx, (size_t)nnz * 4, cudaMemcpyHostToDevice));
+  const int rc = bsmr_row_reorder_dev(ro.get(), ci.get(), M, N, nnz, alpha, block_size, out.get(), numRows, numClusters,
+                                      ms, nullptr);
+  if (rc) return rc;
+  SB_CUDA(cudaMemcpy(h_reorderedRows, out.get(), (size_t)(*numRows) * 4, cudaMemcpyDeviceToHost));
+  API_END
+}
+
+int bsmr_dispersion_dev(const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N, uint32_t nnz,
+                        uint32_t block_size, uint32_t* d_dispersion, uint32_t* numBlocksPerRow, void* stream) {
+  API_BEGIN
+  require_device();
+  require(d_rowOff && d_colIdx && d_dispersion, "null pointer");
+  if (block_size == 0) block_size = bsmr_calc_block_size(M, N, 0);
+  dispersion_dev(d_rowOff, d_colIdx, M, N, nnz, block_size, d_dispersion, numBlocksPerRow, (cudaStream_t)stream);
+  API_END
+}
+
+int bsmr_layout_build_dev(const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N, uint32_t nnz,
+                          const uint32_t* d_reorderedRows, uint32_t numRows, float delta, uint32_t panelBegin,
+                          uint32_t panelEnd, bsmr_layout** out, float* msColReorder, float* msRphm, void* stream) {
+  API_BEGIN
+  require_device();
+  require(d_rowOff && d_colIdx && out && (d_reorderedRows || numRows == 0), "null pointer");
+  *out = layout_build_dev(d_rowOff, d_colIdx, M, N, nnz, d_reorderedRows, numRows, delta, panelBegin, panelEnd,
+                          msColReorder, msRphm, (cudaStream_t)stream);
+  API_END
+}
+
+int bsmr_layout_build(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, uint32_t N, uint32_t nnz,
+                      const uint32_t* h_reorderedRows, uint32_t numRows, float delta, bsmr_layout** out,
+                      float* msColReorder, float* msRphm) {
+  API_BEGIN
+  require_device();
+  require(h_rowOff && h_colIdx && out && (h_reorderedRows || numRows == 0), "null pointer");
+  DevBuf<u32> ro((size_t)M + 1), ci(nnz ? nnz : 1), rr(numRows ? numRows : 1);
+  SB_CUDA(cudaMemcpy(ro.get(), h_rowOff, ((size_t)M + 1) * 4, cudaMemcpyHostToDevice));
+  SB_CUDA(cudaMemcpy(ci.get(), h_colIdx, (size_t)nnz * 4, cudaMemcpyHostToDevice));
+  SB_CUDA(cudaMemcpy(rr.get(), h_reorderedRows, (size_t)numRows * 4, cudaMemcpyHostToDevice));
+  *out = layout_build_dev(ro.get(), ci.get(), M, N, nnz, rr.get(), numRows, delta, 0, 0xFFFFFFFFu, msColReorder,
+                          msRphm, nullptr);
+  API_END
+}
+
+void bsmr_layout_destroy(bsmr_layout* L) { delete L; }
+
+int bsmr_layout_get_info(const bsmr_layout* L, bsmr_layout_info* out) {
+  API_BEGIN
+  require(L && out, "null pointer");
+  *out = L->info;
+  API_END
+}
+size_t bsmr_layout_array_len(const bsmr_layout* L, bsmr_array_id which) {
+  if (!L || which < 0 || which >= BSMR_ARRAY_COUNT) return 0;
+  return L->arr[which].size();
+}
+const uint32_t* bsmr_layout_array_dev(const bsmr_layout* L, bsmr_array_id which) {
+  if (!L || which < 0 || which >= BSMR_ARRAY_COUNT) return nullptr;
+  return L->arr[which].get();
+}
+int bsmr_layout_array_to_host(const bsmr_layout* L, bsmr_array_id which, uint32_t* h_dst, size_t capacity) {
+  API_BEGIN
+  require(L && which >= 0 && which < BSMR_ARRAY_COUNT, "layout / array id");
+  const size_t n = L->arr[which].size();
+  require(capacity >= n && (h_dst || n == 0), "capacity too small");
+  if (n) SB_CUDA(cudaMemcpy(h_dst, L->arr[which].get(), n * 4, cudaMemcpyDeviceToHost));
+  API_END
+}
+
+// ---- SDDMM ------------------------------------------------------------------------------------
+namespace {
+struct Streams {
+  cudaStream_t dense = nullptr, sparse = nullptr;
+  cudaEvent_t fork = nullptr, joinD = nullptr, joinS = nullptr;
+  Streams() {
+    SB_CUDA(cudaStreamCreateWithFlags(&dense, cudaStreamNonBlocking));
+    SB_CUDA(cudaStreamCreateWithFlags(&sparse, cudaStreamNonBlocking));
+    SB_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    SB_CUDA(cudaEventCreateWithFlags(&joinD, cudaEventDisableTiming));
+    SB_CUDA(cudaEventCreateWithFlags(&joinS, cudaEventDisableTiming));
+  }
+};
+Streams& streams() {
+  static thread_local Streams* s = nullptr;  // per host thread, per process; leaked at exit on purpose
+  if (!s) s = new Streams();
+  return *s;
+}
+// dense || residual, forked from and joined back into `s`
+void run_once(const bsmr_layout* L, u32 K, const float* dA, const float* dB, float* dP, cudaStream_t s) {
+  Streams& st = streams();
+  if (L->numDenseWork && L->numSparseWork) {
+    SB_CUDA(cudaEventRecord(st.fork, s));
+    SB_CUDA(cudaStreamWaitEvent(st.dense, st.fork, 0));
+    SB_CUDA(cudaStreamWaitEvent(st.sparse, st.fork, 0));
+    sddmm_launch(L, K, dA, dB, dP, st.dense, st.sparse);
+    SB_CUDA(cudaEventRecord(st.joinD, st.dense));
+    SB_CUDA(cudaEventRecord(st.joinS, st.sparse));
+    SB_CUDA(cudaStreamWaitEvent(s, st.joinD, 0));
+    SB_CUDA(cudaStreamWaitEvent(s, st.joinS, 0));
+  } else {
+    sddmm_launch(L, K, dA, dB, dP, s, s);
+  }
+}
+}  // namespace
+
+int sddmm_run_dev(const bsmr_layout* L, uint32_t K, const float* d_A, const float* d_B, float* d_P, void* stream) {
+  API_BEGIN
+  require_device();
+  require(L && d_A && d_B && d_P, "null pointer");
+  run_once(L, K, d_A, d_B, d_P, (cudaStream_t)stream);
+  API_END
+}
+
+int sddmm_run_timed_dev(const bsmr_layout* L, uint32_t K, const float* d_A, const float* d_B, float* d_P, int warmup,
+                        int iters, float* msDense, float* msSparse, float* msTotal) {
+  API_BEGIN
+  require_device();
+  require(L && d_A && d_B && d_P && iters > 0 && warmup >= 0, "arguments");
+  Streams& st = streams();
+  cudaStream_t s = st.dense;  // the launching stream of the combined pass
+  for (int i = 0; i < warmup; ++i) run_once(L, K, d_A, d_B, d_P, s);
+  SB_CUDA(cudaStreamSynchronize(s));
+  Timer t(s);
+  t.start();
+  for (int i = 0; i < iters; ++i) run_once(L, K, d_A, d_B, d_P, s);
+  const float tot = t.stop() / iters;
+  if (msTotal) *msTotal = tot;
+  // each kernel alone (its own stream, nothing else running): the per-kernel roofline figures
+  if (msDense) {
+    *msDense = 0.f;
+    if (L->numDenseWork) {
+      Timer td(st.dense);
+      td.start();
+      for (int i = 0; i < iters; ++i) sddmm_launch(L, K, d_A, d_B, d_P, st.dense, st.dense, kLaunchDense);
+      *msDense = td.stop() / iters;
+    }
+  }
+  if (msSparse) {
+    *msSparse = 0.f;
+    if (L->numSparseWork) {
+      Timer ts(st.sparse);
+      ts.start();
+      for (int i = 0; i < iters; ++i) sddmm_launch(L, K, d_A, d_B, d_P, st.sparse, st.sparse, kLaunchSparse);
+      *msSparse = ts.stop() / iters;
+    }
+  }
+  API_END
+}
+
+int sddmm_run_host(const bsmr_layout* L, uint32_t K, const float* h_A, const float* h_B, float* h_P, float* msTotal) {
+  API_BEGIN
+  require_device();
+  require(L && h_A && h_B && h_P, "null pointer");
+  const bsmr_layout_info& I = L->info;
+  cudaStream_t s = streams().dense;
+  Timer t(s);
+  t.start();
+  DevBuf<float> dA((size_t)I.M * K), dB((size_t)I.N * K), dP(I.nnz ? I.nnz : 1);
+  SB_CUDA(cudaMemcpyAsync(dA.get(), h_A, (size_t)I.M * K * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(dB.get(), h_B, (size_t)I.N * K * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemsetAsync(dP.get(), 0, (size_t)I.nnz * 4, s));  // dev::vector<float> P(nnz, 0)  sddmmKernel.cu:2525
+  run_once(L, K, dA.get(), dB.get(), dP.get(), s);
+  SB_CUDA(cudaMemcpyAsync(h_P, dP.get(), (size_t)I.nnz * 4, cudaMemcpyDeviceToHost, s));
+  const float el = t.stop();
+  if (msTotal) *msTotal = el;
+  API_END
+}
+
+int sddmm_host(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, uint32_t N, uint32_t nnz, uint32_t K,
+               const float* h_A, const float* h_B, float alpha, float delta, uint32_t block_size, float* h_P,
+               sddmm_stats* stats, bsmr_layout** layoutOut) {
+  API_BEGIN
+  require_device();
+  require(h_rowOff && h_colIdx && h_A && h_B && h_P, "null pointer");
+  if (block_size == 0) block_size = bsmr_calc_block_size(M, N, 0);
+  DevBuf<u32> ro((size_t)M + 1), ci(nnz ? nnz : 1), rr(M ? M : 1);
+  SB_CUDA(cudaMemcpy(ro.get(), h_rowOff, ((size_t)M + 1) * 4, cudaMemcpyHostToDevice));
+  SB_CUDA(cudaMemcpy(ci.get(), h_colIdx, (size_t)nnz * 4, cudaMemcpyHostToDevice));
+  u32 numRows = 0;
+  int32_t ncl = 0;
+  float msRow = 0.f, msCol = 0.f, msRphm = 0.f, msRun = 0.f;
+  int rc = bsmr_row_reorder_dev(ro.get(), ci.get(), M, N, nnz, alpha, block_size, rr.get(), &numRows, &ncl, &msRow,
+                                nullptr);
+  if (rc) return rc;
+  bsmr_layout* L = nullptr;
+  rc = bsmr_layout_build_dev(ro.get(), ci.get(), M, N, nnz, rr.get(), numRows, delta, 0, 0xFFFFFFFFu, &L, &msCol,
+                             &msRphm, nullptr);
+  if (rc) return rc;
+  rc = sddmm_run_host(L, K, h_A, h_B, h_P, &msRun);
+  if (stats) {
+    stats->rowReorderMs = msRow; stats->colReorderMs = msCol; stats->rphmMs = msRphm; stats->sddmmMs = msRun;
+    stats->numClusters = ncl; stats->blockSize = block_size;
+  }
+  if (rc || !layoutOut) bsmr_layout_destroy(L);
+  else *layoutOut = L;
+  if (rc) return rc;
+  API_END
+}
+
+int bsmr_shard_plan(const uint32_t* h_rowOff, const uint32_t* h_reorderedRows, uint32_t numRows, uint32_t numShards,
+                    uint32_t* h_cuts) {
+  API_BEGIN
+  require(h_rowOff && (h_reorderedRows || numRows == 0) && h_cuts && numShards > 0, "arguments");
+  const u32 P = (numRows + kPanel - 1) / kPanel;
+  std::vector<u64> pre((size_t)P + 1, 0);
+  for (u32 p = 0; p < P; ++p) {
+    u64 c = 0;
+    for (u32 i = p * kPanel; i < (p + 1) * kPanel && i < numRows; ++i) {
+      const u32 r = h_reorderedRows[i];
+      c += h_rowOff[r + 1] - h_rowOff[r];
+    }
+    pre[p + 1] = pre[p] + c;
+  }
+  const u64 total = pre[P];
+  h_cuts[0] = 0;
+  u32 p = 0;
+  for (u32 s = 1; s < numShards; ++s) {
+    const u64 target = (total * s + numShards / 2) / numShards;
+    while (p < P && pre[p] < target) ++p;
+    // pick the closer of p-1 / p
+    if (p > 0 && target - pre[p - 1] < pre[p] - target) --p;
+    if (p < h_cuts[s - 1]) p = h_cuts[s - 1];
+    h_cuts[s] = p;
+  }
+  h_cuts[numShards] = P;
+  API_END
+}
+
+}  // extern "C"

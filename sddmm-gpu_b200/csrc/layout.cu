@@ -1,0 +1,434 @@
+// layout.cu -- column reordering, dense/sparse split and RPHM construction ON DEVICE
+// (a7 + a8 of SURVEY.md 8a; the reference does both on the host with OpenMP:
+//  colReordering_cpu src/colReordering.cu:274-404, RPHM::RPHM src/BSMR.cpp:83-265).
+//
+// Formulation (all stages are stable radix sorts, scans and flat scatter kernels, so cost is
+// O(nnz) HBM traffic per pass regardless of how skewed the row panels are):
+//   1. every stored entry of the selected panels gets the key (panel | col | row-in-panel) and its
+//      CSR index as payload; one stable sort groups entries by (panel, col), rows ascending;
+//   2. run heads give the distinct (panel, col) "column groups" with their counts (1..16);
+//   3. a stable sort of the groups by (panel, 16-count) yields, per panel, columns ordered by
+//      count descending / column ascending  == thrust::stable_sort_by_key(greater) in the reference;
+//   4. per panel: pad to x16 with sentinel N, blocks whose count-sum >= ceil(delta*256) are dense;
+//   5. scans give every offset array; one scatter writes denseCols / sparseCols / blockValues and
+//      the residual COO arrays in exactly the reference's order (appendix B of SURVEY.md).
+#include "layout.cuh"
+#include "primitives.cuh"
+
+namespace sb {
+
+namespace {
+
+__global__ void k_scatter_rowpos(const u32* __restrict__ R, u32 r0, u32 n, u32* __restrict__ rowLenOut,
+                                 const u32* __restrict__ rowOff) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const u32 row = R[r0 + i];
+    rowLenOut[i] = rowOff[row + 1] - rowOff[row];
+  }
+}
+
+// one warp per reordered row: emit keys (panelLocal | col | r) + CSR index
+__global__ void __launch_bounds__(256) k_make_entry_keys(const u32* __restrict__ R, u32 r0, u32 n,
+                                                         const u32* __restrict__ rowOff,
+                                                         const u32* __restrict__ colIdx,
+                                                         const u32* __restrict__ eOff, int colBits,
+                                                         u64* __restrict__ keys, u32* __restrict__ vals) {
+  const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const u32 nw = (gridDim.x * blockDim.x) >> 5;
+  for (u32 i = gw; i < n; i += nw) {
+    const u32 row = R[r0 + i];
+    const u32 b = rowOff[row], len = rowOff[row + 1] - b;
+    const u32 o = eOff[i];
+    const u64 hi = ((u64)(i >> 4) << (colBits + 4)) | (i & 15u);
+    for (u32 j = lane; j < len; j += 32) {
+      keys[o + j] = hi | ((u64)colIdx[b + j] << 4);
+      vals[o + j] = b + j;
+    }
+  }
+}
+
+__global__ void k_group_heads(const u64* __restrict__ keys, size_t n, u32* __restrict__ head) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    head[i] = (i == 0 || (keys[i] >> 4) != (keys[i - 1] >> 4)) ? 1u : 0u;
+}
+
+// gid = exclusive scan of head; at heads gidIncl-1... we scan `head` exclusively into gidEx, so the group
+// of element i is gidEx[i] + head[i] - 1.
+__global__ void k_group_starts(const u32* __restrict__ head, const u32* __restrict__ gidEx, size_t n,
+                               u32* __restrict__ gStart) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    if (head[i]) gStart[gidEx[i]] = (u32)i;
+}
+
+__global__ void k_group_keys(const u64* __restrict__ keys, const u32* __restrict__ gStart, u32 numGroups, u32 nSel,
+                             int colBits, u32* __restrict__ sortKey, u32* __restrict__ gCount) {
+  for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < numGroups; g += (size_t)gridDim.x * blockDim.x) {
+    const u32 s = gStart[g];
+    const u32 e = (g + 1 < numGroups) ? gStart[g + 1] : nSel;
+    const u32 cnt = e - s;  // 1..16 (no duplicate (row,col): src/Matrix.cpp:447-461)
+    const u32 panel = (u32)(keys[s] >> (colBits + 4));
+    sortKey[g] = (panel << 5) | (16u - (cnt > 16u ? 16u : cnt));
+    gCount[g] = cnt;
+  }
+}
+
+// sorted group j -> panel boundaries, inverse permutation
+__global__ void k_sorted_group_info(const u32* __restrict__ sortedKey, const u32* __restrict__ order, u32 numGroups,
+                                    u32* __restrict__ pStart, u32* __restrict__ rank, u32 P) {
+  for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < numGroups; j += (size_t)gridDim.x * blockDim.x) {
+    rank[order[j]] = (u32)j;
+    const u32 p = sortedKey[j] >> 5;
+    if (j == 0 || (sortedKey[j - 1] >> 5) != p) pStart[p] = (u32)j;
+    if (j + 1 == numGroups) pStart[P] = numGroups;
+  }
+}
+
+// per panel: nd (dense columns), padded column count, residual / dense entry counts.  One warp per
+// panel, two 16-column blocks per step (half-warps).
+__global__ void __launch_bounds__(256) k_panel_split(const u32* __restrict__ sortedKey, const u32* __restrict__ pStart,
+                                                     u32 P, u32 T, u32* __restrict__ nd, u32* __restrict__ nsCols,
+                                                     u32* __restrict__ nnzSparse, u32* __restrict__ nBlk,
+                                                     u32* __restrict__ denseTB, u32* __restrict__ sparseTB,
+                                                     u32* __restrict__ myDenseWork, u32* __restrict__ mySparseWork,
+                                                     u32* __restrict__ maxima /* [0]=maxDenseBlk [1]=maxSparseTB [2]=denseNnz */) {
+  const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const u32 nw = (gridDim.x * blockDim.x) >> 5;
+  for (u32 p = gw; p < P; p += nw) {
+    const u32 s = pStart[p], nCols = pStart[p + 1] - s;
+    const u32 padded = (nCols + 15u) & ~15u;
+    u32 denseBlocks = 0, total = 0, denseNnz = 0;
+    for (u32 base = 0; base < padded; base += 32) {
+      const u32 slot = base + lane;
+      const u32 cnt = slot < nCols ? 16u - (sortedKey[s + slot] & 31u) : 0u;
+      u32 sum = cnt;
+#pragma unroll
+      for (int w = 1; w < 16; w <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, w);
+      // sum = count-sum of this lane's 16-column block
+      const bool blockExists = (base + (lane & 16u)) < padded;
+      const bool dense = blockExists && sum >= T;
+      const unsigned dm = __ballot_sync(0xffffffffu, dense && (lane & 15u) == 0);
+      denseBlocks += __popc(dm);
+      u32 t = cnt, dn = dense ? cnt : 0u;
+#pragma unroll
+      for (int w = 1; w < 32; w <<= 1) {
+        t += __shfl_xor_sync(0xffffffffu, t, w);
+        dn += __shfl_xor_sync(0xffffffffu, dn, w);
+      }
+      total += t;
+      denseNnz += dn;
+    }
+    if (lane == 0) {
+      // colReordering.cu:250-261 counts EVERY block whose sum reaches T; counts are non-increasing so
+      // they form a prefix, and the first nd columns are taken as dense (:380-400)
+      const u32 ndp = denseBlocks * 16u;
+      // entries in the first ndp slots (prefix), which equals denseNnz because dense blocks are a prefix
+      nd[p] = ndp;
+      nsCols[p] = padded - ndp;
+      nnzSparse[p] = total - denseNnz;
+      nBlk[p] = denseBlocks;
+      const u32 dtb = (denseBlocks + 3u) / 4u, stb = (total - denseNnz + 127u) / 128u;
+      denseTB[p] = dtb;
+      sparseTB[p] = stb;
+      myDenseWork[p] = (denseBlocks + kDenseGroupBlocks - 1) / kDenseGroupBlocks;
+      mySparseWork[p] = (total - denseNnz + kSparseChunk - 1) / kSparseChunk;
+      atomicMax(maxima + 0, denseBlocks);
+      atomicMax(maxima + 1, stb);
+      atomicAdd(maxima + 2, denseNnz);
+    }
+  }
+}
+
+__global__ void k_sparse_group_counts(const u32* __restrict__ sortedKey, const u32* __restrict__ pStart,
+                                      const u32* __restrict__ nd, u32 numGroups, u32* __restrict__ out) {
+  for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < numGroups; j += (size_t)gridDim.x * blockDim.x) {
+    const u32 p = sortedKey[j] >> 5;
+    const u32 slot = (u32)j - pStart[p];
+    out[j] = slot >= nd[p] ? 16u - (sortedKey[j] & 31u) : 0u;
+  }
+}
+
+// columns: sorted group j -> denseCols / sparseCols
+__global__ void k_write_cols(const u32* __restrict__ sortedKey, const u32* __restrict__ order,
+                             const u64* __restrict__ keys, const u32* __restrict__ gStart,
+                             const u32* __restrict__ pStart, const u32* __restrict__ nd,
+                             const u32* __restrict__ dOff, const u32* __restrict__ sOff, u32 numGroups, int colBits,
+                             u32* __restrict__ denseCols, u32* __restrict__ sparseCols) {
+  const u64 colMask = (((u64)1) << colBits) - 1;
+  for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < numGroups; j += (size_t)gridDim.x * blockDim.x) {
+    const u32 p = sortedKey[j] >> 5;
+    const u32 slot = (u32)j - pStart[p];
+    const u32 col = (u32)((keys[gStart[order[j]]] >> 4) & colMask);
+    const u32 ndp = nd[p];
+    if (slot < ndp) denseCols[dOff[p] + slot] = col;
+    else sparseCols[sOff[p] + (slot - ndp)] = col;
+  }
+}
+
+// padding sentinels (colReordering.cu:338-343): slots [nCols, padded) hold N
+__global__ void k_write_pad(const u32* __restrict__ pStart, const u32* __restrict__ nd, const u32* __restrict__ dOff,
+                            const u32* __restrict__ sOff, u32 P, u32 N, u32* __restrict__ denseCols,
+                            u32* __restrict__ sparseCols) {
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < (size_t)P * 16; t += (size_t)gridDim.x * blockDim.x) {
+    const u32 p = (u32)(t >> 4), k = (u32)(t & 15);
+    const u32 nCols = pStart[p + 1] - pStart[p];
+    const u32 padded = (nCols + 15u) & ~15u;
+    const u32 slot = nCols + k;
+    if (slot >= padded) continue;
+    const u32 ndp = nd[p];
+    if (slot < ndp) denseCols[dOff[p] + slot] = N;
+    else sparseCols[sOff[p] + (slot - ndp)] = N;
+  }
+}
+
+// entries: sorted element i -> blockValues or the residual COO arrays
+__global__ void k_write_entries(const u64* __restrict__ keys, const u32* __restrict__ vals,
+                                const u32* __restrict__ head, const u32* __restrict__ gidEx,
+                                const u32* __restrict__ gStart, const u32* __restrict__ rank,
+                                const u32* __restrict__ pStart, const u32* __restrict__ nd,
+                                const u32* __restrict__ bOff, const u32* __restrict__ gSparseOff, size_t n,
+                                int colBits, u32* __restrict__ blockValues, u32* __restrict__ sparseValues,
+                                u32* __restrict__ sparseRelRows, u32* __restrict__ sparseColIdx) {
+  const u64 colMask = (((u64)1) << colBits) - 1;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const u64 k = keys[i];
+    const u32 g = gidEx[i] + head[i] - 1u;
+    const u32 j = rank[g];
+    const u32 p = (u32)(k >> (colBits + 4));
+    const u32 r = (u32)(k & 15u);
+    const u32 slot = j - pStart[p];
+    const u32 idx = vals[i];
+    if (slot < nd[p]) {
+      blockValues[((size_t)bOff[p] + (slot >> 4)) * 256u + r * 16u + (slot & 15u)] = idx;
+    } else {
+      const u32 pos = gSparseOff[j] + ((u32)i - gStart[g]);
+      sparseValues[pos] = idx;
+      sparseRelRows[pos] = r;
+      sparseColIdx[pos] = (u32)((k >> 4) & colMask);
+    }
+  }
+}
+
+// reference-shaped work lists (BSMR.cpp:99-119, :221-246) and ours
+__global__ void k_write_worklists(const u32* __restrict__ dOff, const u32* __restrict__ nBlk,
+                                  const u32* __restrict__ nnzSparse, const u32* __restrict__ dtbOff,
+                                  const u32* __restrict__ stbOff, const u32* __restrict__ myDOff,
+                                  const u32* __restrict__ mySOff, u32 P, u32* __restrict__ dIds,
+                                  u32* __restrict__ dIters, u32* __restrict__ sIds, u32* __restrict__ sIters,
+                                  uint2* __restrict__ myDense, uint2* __restrict__ mySparse) {
+  const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const u32 nw = (gridDim.x * blockDim.x) >> 5;
+  for (u32 p = gw; p < P; p += nw) {
+    const u32 dtb = (nBlk[p] + 3u) / 4u, stb = (nnzSparse[p] + 127u) / 128u;
+    for (u32 i = lane; i < dtb; i += 32) {
+      dIds[dtbOff[p] + i] = p;
+      dIters[dtbOff[p] + i] = dOff[p] / 16u + i * 4u;
+    }
+    for (u32 i = lane; i < stb; i += 32) {
+      sIds[stbOff[p] + i] = p;
+      sIters[stbOff[p] + i] = i * 128u;
+    }
+    const u32 md = (nBlk[p] + kDenseGroupBlocks - 1) / kDenseGroupBlocks;
+    const u32 ms = (nnzSparse[p] + kSparseChunk - 1) / kSparseChunk;
+    for (u32 i = lane; i < md; i += 32) myDense[myDOff[p] + i] = make_uint2(p, i * kDenseGroupBlocks);
+    for (u32 i = lane; i < ms; i += 32) mySparse[mySOff[p] + i] = make_uint2(p, i * kSparseChunk);
+  }
+}
+
+u32 read_u32(const u32* d, cudaStream_t s) {
+  u32 h = 0;
+  SB_CUDA(cudaMemcpyAsync(&h, d, 4, cudaMemcpyDeviceToHost, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+  return h;
+}
+
+// exclusive scan of a P-array into a (P+1)-array (out[P] = total)
+void scan_counts(const u32* cnt, u32* out, u32 P, cudaStream_t s) {
+  SB_CUDA(cudaMemcpyAsync(out, cnt, (size_t)P * 4, cudaMemcpyDeviceToDevice, s));
+  SB_CUDA(cudaMemsetAsync(out + P, 0, 4, s));
+  exclusive_scan_u32(out, out, (size_t)P + 1, s);
+}
+
+}  // namespace
+
+bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32 nnz, const u32* d_R,
+                              u32 numRows, float delta, u32 panelBegin, u32 panelEnd, float* msCol, float* msRphm,
+                              cudaStream_t s) {
+  const u32 Pall = (numRows + kPanel - 1) / kPanel;  // BSMR.cpp:48
+  if (panelEnd > Pall) panelEnd = Pall;
+  if (panelBegin > panelEnd) panelBegin = panelEnd;
+  const u32 P = panelEnd - panelBegin;
+  const u32 r0 = panelBegin * kPanel;
+  const u32 r1 = (panelEnd * kPanel < numRows) ? panelEnd * kPanel : numRows;
+  const u32 nR = r1 > r0 ? r1 - r0 : 0;
+  // colReordering.cu:246  static_cast<UIN>(std::ceil(delta * BLOCK_SIZE)), float arithmetic
+  const u32 T = (u32)std::ceil(delta * (float)(kPanel * kBlockCols));
+
+  auto* L = new bsmr_layout();
+  try {
+    SB_CUDA(cudaGetDevice(&L->device));
+    bsmr_layout_info& I = L->info;
+    I.M = M; I.N = N; I.nnz = nnz; I.numRows = nR; I.numRowPanels = P; I.panelBegin = panelBegin;
+    auto A = [&](bsmr_array_id id) -> DevBuf<u32>& { return L->arr[id]; };
+    A(BSMR_REORDERED_ROWS).alloc(nR ? nR : 1);
+    if (nR) SB_CUDA(cudaMemcpyAsync(A(BSMR_REORDERED_ROWS).get(), d_R + r0, (size_t)nR * 4, cudaMemcpyDeviceToDevice, s));
+    for (bsmr_array_id id : {BSMR_DENSE_COL_OFFSETS, BSMR_SPARSE_COL_OFFSETS, BSMR_SPARSE_VALUE_OFFSETS, RPHM_BLOCK_OFFSETS}) {
+      A(id).alloc((size_t)P + 1);
+      SB_CUDA(cudaMemsetAsync(A(id).get(), 0, ((size_t)P + 1) * 4, s));
+    }
+    Timer tCol(s);
+    tCol.start();
+    if (P == 0) {
+      for (bsmr_array_id id : {BSMR_DENSE_COLS, BSMR_SPARSE_COLS, RPHM_BLOCK_VALUES, RPHM_SPARSE_VALUES,
+                               RPHM_SPARSE_RELATIVE_ROWS, RPHM_SPARSE_COL_INDICES, RPHM_DENSE_ROW_PANEL_IDS,
+                               RPHM_DENSE_COL_BLOCK_ITERS, RPHM_SPARSE_ROW_PANEL_IDS, RPHM_SPARSE_COL_BLOCK_ITERS})
+        A(id).alloc(1), A(id).n = 0;
+      if (msCol) *msCol = tCol.stop();
+      if (msRphm) *msRphm = 0.f;
+      return L;
+    }
+
+    // ---- 1. keys for every stored entry of the selected rows
+    DevBuf<u32> eOff((size_t)nR + 1);
+    k_scatter_rowpos<<<grid_for(nR), 256, 0, s>>>(d_R, r0, nR, eOff.get(), d_rowOff);
+    SB_LAUNCH_CHECK();
+    SB_CUDA(cudaMemsetAsync(eOff.get() + nR, 0, 4, s));
+    exclusive_scan_u32(eOff.get(), eOff.get(), (size_t)nR + 1, s);
+    const u32 nSel = read_u32(eOff.get() + nR, s);
+    const int colBits = bits_for(N);  // sentinel-free here: real columns are < N
+    const int panelBits = bits_for(P);
+    if (panelBits > 27) fail(SDDMM_E_UNSUPPORTED, "too many row panels (%u)", P);
+    DevBuf<u64> keyA(nSel ? nSel : 1), keyB(nSel ? nSel : 1);
+    DevBuf<u32> valA(nSel ? nSel : 1), valB(nSel ? nSel : 1);
+    k_make_entry_keys<<<grid_for((size_t)nR * 32), 256, 0, s>>>(d_R, r0, nR, d_rowOff, d_colIdx, eOff.get(), colBits,
+                                                              keyA.get(), valA.get());
+    SB_LAUNCH_CHECK();
+    const int w = radix_sort_pairs<u64>(keyA.get(), keyB.get(), valA.get(), valB.get(), nSel, 0,
+                                        4 + colBits + panelBits, s);
+    const u64* keys = w ? keyB.get() : keyA.get();
+    const u32* vals = w ? valB.get() : valA.get();
+    (w ? keyA : keyB).release();
+    (w ? valA : valB).release();
+
+    // ---- 2. (panel, col) groups
+    DevBuf<u32> head(nSel ? nSel : 1), gidEx((size_t)nSel + 1);
+    k_group_heads<<<grid_for(nSel), 256, 0, s>>>(keys, nSel, head.get());
+    SB_LAUNCH_CHECK();
+    SB_CUDA(cudaMemcpyAsync(gidEx.get(), head.get(), (size_t)nSel * 4, cudaMemcpyDeviceToDevice, s));
+    SB_CUDA(cudaMemsetAsync(gidEx.get() + nSel, 0, 4, s));
+    exclusive_scan_u32(gidEx.get(), gidEx.get(), (size_t)nSel + 1, s);
+    const u32 numGroups = read_u32(gidEx.get() + nSel, s);
+    DevBuf<u32> gStart(numGroups ? numGroups : 1), gCount(numGroups ? numGroups : 1);
+    k_group_starts<<<grid_for(nSel), 256, 0, s>>>(head.get(), gidEx.get(), nSel, gStart.get());
+    SB_LAUNCH_CHECK();
+
+    // ---- 3. per panel: columns by (count desc, col asc)
+    DevBuf<u32> skA(numGroups ? numGroups : 1), skB(numGroups ? numGroups : 1), ordA(numGroups ? numGroups : 1),
+        ordB(numGroups ? numGroups : 1);
+    k_group_keys<<<grid_for(numGroups), 256, 0, s>>>(keys, gStart.get(), numGroups, nSel, colBits, skA.get(),
+                                                    gCount.get());
+    SB_LAUNCH_CHECK();
+    iota<u32>(ordA.get(), numGroups, 0u, s);
+    const int w2 = radix_sort_pairs<u32>(skA.get(), skB.get(), ordA.get(), ordB.get(), numGroups, 0, 5 + panelBits, s);
+    const u32* sortedKey = w2 ? skB.get() : skA.get();
+    const u32* order = w2 ? ordB.get() : ordA.get();
+    DevBuf<u32> pStart((size_t)P + 1), rank(numGroups ? numGroups : 1);
+    SB_CUDA(cudaMemsetAsync(pStart.get(), 0, ((size_t)P + 1) * 4, s));
+    k_sorted_group_info<<<grid_for(numGroups), 256, 0, s>>>(sortedKey, order, numGroups, pStart.get(), rank.get(), P);
+    SB_LAUNCH_CHECK();
+
+    // ---- 4. dense prefix per panel
+    DevBuf<u32> nd(P), nsCols(P), nnzSparse(P), nBlk(P), denseTB(P), sparseTB(P), myDW(P), mySW(P), maxima(4);
+    SB_CUDA(cudaMemsetAsync(maxima.get(), 0, 16, s));
+    k_panel_split<<<grid_for((size_t)P * 32), 256, 0, s>>>(sortedKey, pStart.get(), P, T, nd.get(), nsCols.get(),
+                                                          nnzSparse.get(), nBlk.get(), denseTB.get(), sparseTB.get(),
+                                                          myDW.get(), mySW.get(), maxima.get());
+    SB_LAUNCH_CHECK();
+
+    // ---- 5. offsets
+    scan_counts(nd.get(), A(BSMR_DENSE_COL_OFFSETS).get(), P, s);
+    scan_counts(nsCols.get(), A(BSMR_SPARSE_COL_OFFSETS).get(), P, s);
+    scan_counts(nnzSparse.get(), A(BSMR_SPARSE_VALUE_OFFSETS).get(), P, s);
+    const u32 dTot = read_u32(A(BSMR_DENSE_COL_OFFSETS).get() + P, s);
+    const u32 sTot = read_u32(A(BSMR_SPARSE_COL_OFFSETS).get() + P, s);
+    const u32 vTot = read_u32(A(BSMR_SPARSE_VALUE_OFFSETS).get() + P, s);
+    A(BSMR_DENSE_COLS).alloc(dTot ? dTot : 1); A(BSMR_DENSE_COLS).n = dTot;
+    A(BSMR_SPARSE_COLS).alloc(sTot ? sTot : 1); A(BSMR_SPARSE_COLS).n = sTot;
+    k_write_cols<<<grid_for(numGroups), 256, 0, s>>>(sortedKey, order, keys, gStart.get(), pStart.get(), nd.get(),
+                                                    A(BSMR_DENSE_COL_OFFSETS).get(), A(BSMR_SPARSE_COL_OFFSETS).get(),
+                                                    numGroups, colBits, A(BSMR_DENSE_COLS).get(),
+                                                    A(BSMR_SPARSE_COLS).get());
+    SB_LAUNCH_CHECK();
+    k_write_pad<<<grid_for((size_t)P * 16), 256, 0, s>>>(pStart.get(), nd.get(), A(BSMR_DENSE_COL_OFFSETS).get(),
+                                                        A(BSMR_SPARSE_COL_OFFSETS).get(), P, N,
+                                                        A(BSMR_DENSE_COLS).get(), A(BSMR_SPARSE_COLS).get());
+    SB_LAUNCH_CHECK();
+    const float colMs = tCol.stop();
+    if (msCol) *msCol = colMs;
+
+    // ---- RPHM (BSMR.cpp:83-265)
+    Timer tR(s);
+    tR.start();
+    scan_counts(nBlk.get(), A(RPHM_BLOCK_OFFSETS).get(), P, s);
+    const u32 numBlocks = read_u32(A(RPHM_BLOCK_OFFSETS).get() + P, s);
+    const size_t nbv = (size_t)numBlocks * 256u;
+    A(RPHM_BLOCK_VALUES).alloc(nbv ? nbv : 1); A(RPHM_BLOCK_VALUES).n = nbv;
+    fill<u32>(A(RPHM_BLOCK_VALUES).get(), nbv, kNull, s);
+    for (bsmr_array_id id : {RPHM_SPARSE_VALUES, RPHM_SPARSE_RELATIVE_ROWS, RPHM_SPARSE_COL_INDICES}) {
+      A(id).alloc(vTot ? vTot : 1);
+      A(id).n = vTot;
+    }
+    DevBuf<u32> gSparseOff((size_t)numGroups + 1);
+    k_sparse_group_counts<<<grid_for(numGroups), 256, 0, s>>>(sortedKey, pStart.get(), nd.get(), numGroups,
+                                                             gSparseOff.get());
+    SB_LAUNCH_CHECK();
+    SB_CUDA(cudaMemsetAsync(gSparseOff.get() + numGroups, 0, 4, s));
+    exclusive_scan_u32(gSparseOff.get(), gSparseOff.get(), (size_t)numGroups + 1, s);
+    k_write_entries<<<grid_for(nSel), 256, 0, s>>>(keys, vals, head.get(), gidEx.get(), gStart.get(), rank.get(),
+                                                  pStart.get(), nd.get(), A(RPHM_BLOCK_OFFSETS).get(), gSparseOff.get(),
+                                                  nSel, colBits, A(RPHM_BLOCK_VALUES).get(),
+                                                  A(RPHM_SPARSE_VALUES).get(), A(RPHM_SPARSE_RELATIVE_ROWS).get(),
+                                                  A(RPHM_SPARSE_COL_INDICES).get());
+    SB_LAUNCH_CHECK();
+
+    // work lists
+    DevBuf<u32> dtbOff((size_t)P + 1), stbOff((size_t)P + 1), myDOff((size_t)P + 1), mySOff((size_t)P + 1);
+    scan_counts(denseTB.get(), dtbOff.get(), P, s);
+    scan_counts(sparseTB.get(), stbOff.get(), P, s);
+    scan_counts(myDW.get(), myDOff.get(), P, s);
+    scan_counts(mySW.get(), mySOff.get(), P, s);
+    const u32 nDTB = read_u32(dtbOff.get() + P, s), nSTB = read_u32(stbOff.get() + P, s);
+    L->numDenseWork = read_u32(myDOff.get() + P, s);
+    L->numSparseWork = read_u32(mySOff.get() + P, s);
+    A(RPHM_DENSE_ROW_PANEL_IDS).alloc(nDTB ? nDTB : 1); A(RPHM_DENSE_ROW_PANEL_IDS).n = nDTB;
+    A(RPHM_DENSE_COL_BLOCK_ITERS).alloc(nDTB ? nDTB : 1); A(RPHM_DENSE_COL_BLOCK_ITERS).n = nDTB;
+    A(RPHM_SPARSE_ROW_PANEL_IDS).alloc(nSTB ? nSTB : 1); A(RPHM_SPARSE_ROW_PANEL_IDS).n = nSTB;
+    A(RPHM_SPARSE_COL_BLOCK_ITERS).alloc(nSTB ? nSTB : 1); A(RPHM_SPARSE_COL_BLOCK_ITERS).n = nSTB;
+    L->denseWork.alloc(L->numDenseWork ? L->numDenseWork : 1);
+    L->sparseWork.alloc(L->numSparseWork ? L->numSparseWork : 1);
+    k_write_worklists<<<grid_for((size_t)P * 32), 256, 0, s>>>(
+        A(BSMR_DENSE_COL_OFFSETS).get(), nBlk.get(), nnzSparse.get(), dtbOff.get(), stbOff.get(), myDOff.get(),
+        mySOff.get(), P, A(RPHM_DENSE_ROW_PANEL_IDS).get(), A(RPHM_DENSE_COL_BLOCK_ITERS).get(),
+        A(RPHM_SPARSE_ROW_PANEL_IDS).get(), A(RPHM_SPARSE_COL_BLOCK_ITERS).get(), L->denseWork.get(),
+        L->sparseWork.get());
+    SB_LAUNCH_CHECK();
+    u32 hmax[4];
+    SB_CUDA(cudaMemcpyAsync(hmax, maxima.get(), 16, cudaMemcpyDeviceToHost, s));
+    const float rMs = tR.stop();
+    if (msRphm) *msRphm = rMs;
+
+    A(BSMR_REORDERED_ROWS).n = nR;
+    I.numDenseBlocks = numBlocks;
+    I.numSparseValues = vTot;
+    I.numDenseValues = hmax[2];
+    I.maxNumDenseColBlocksInRowPanel = hmax[0];
+    I.maxNumSparseColBlocksInRowPanel = hmax[1];
+    I.numDenseThreadBlocks = nDTB;
+    I.numSparseThreadBlocks = nSTB;
+    return L;
+  } catch (...) {
+    delete L;
+    throw;
+  }
+}
+
+}  // namespace sb

@@ -1,0 +1,24 @@
+// layout.cuh -- the device-resident BSMR + RPHM layout object behind `bsmr_layout` (C ABI).
+#pragma once
+#include "common.cuh"
+
+struct bsmr_layout {
+  bsmr_layout_info info{};
+  sb::DevBuf<sb::u32> arr[BSMR_ARRAY_COUNT];  // indexed by bsmr_array_id
+  // work lists consumed by OUR kernels (the reference-shaped ones above are kept for API parity)
+  sb::DevBuf<uint2> denseWork;   // (local panel, first dense block of the group inside the panel)
+  sb::DevBuf<uint2> sparseWork;  // (local panel, first residual entry of the chunk inside the panel)
+  sb::u32 numDenseWork = 0, numSparseWork = 0;
+  int device = 0;
+};
+
+namespace sb {
+
+constexpr u32 kDenseGroupBlocks = 8;   // 8 x 16 = 128 gathered B columns per tcgen05 tile (MMA M)
+constexpr u32 kSparseChunk = 1024;     // residual entries per CTA work item
+
+bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32 nnz,
+                              const u32* d_reorderedRows, u32 numRows, float delta, u32 panelBegin, u32 panelEnd,
+                              float* msCol, float* msRphm, cudaStream_t s);
+
+}  // namespace sb

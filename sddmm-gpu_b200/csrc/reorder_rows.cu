@@ -1,0 +1,552 @@
+// reorder_rows.cu -- row-similarity reordering (a2-a6 of SURVEY.md 8a) as sm_100a kernels.
+//
+//   K1  encode      : per row, SPARSE histogram over column blocks (block id, count) + dispersion.
+//                     Replaces kernel::calculateDispersion (src/rowReordering.cu:49-93), which
+//                     writes a dense M x nbpr matrix.
+//   K3  radix sorts : (dispersion, row) and (cluster, position), stable (rowReordering.cu:1060-1062,
+//                     :986-990; thrust::host stable sorts in the reference).
+//   K2  clustering  : one persistent cooperative kernel; same sequential semantics as the chain of
+//                     1-CTA bsa_clustering kernels (rowReordering.cu:325-432) and the same fp32
+//                     reduction tree (cudaUtil.cuh:13-45), evaluated on
+//                     sparse histograms.
+//
+// Bit-exactness strategy for `sim > alpha`:
+//   the reference value is  REDUCE(sum min(a_i,b_i)) / REDUCE(sum max(a_i,b_i))  in fp32 with a fixed
+//   tree.  Over the index set the tree keeps, sum max = S_a + S_b - sum min in real arithmetic, so a
+//   cheap fp32 estimate  m / (S_a + S_b - m)  from the intersection only is within a few ulp-sums of
+//   the reference value (all terms are non-negative: relative error <= ~1e-4 worst case).  Pairs whose
+//   estimate is farther than kTolRel from alpha are decided by the estimate; the (rare) others are
+//   re-evaluated with the literal tree, using round-to-nearest intrinsics only.
+#include <cooperative_groups.h>
+
+#include <vector>
+
+#include "primitives.cuh"
+#include "reorder_rows.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace sb {
+
+// ------------------------------------------------------------------------------------------
+// host-side exact restatements of the reference's launch geometry
+// ------------------------------------------------------------------------------------------
+u32 calc_block_size(u32 M, u32 N, u64 freeMem) {  // rowReordering.cu:1009-1025
+  const float g = std::ceil((float)((size_t)M * (size_t)M * sizeof(u32)) / (float)(freeMem / 2));
+  const float sm = std::ceil((float)((size_t)N * sizeof(u32)) / (float)(49152u / 2u));
+  const u32 a = (u32)g, b = (u32)sm;
+  const u32 bs = a > b ? a : b;
+  return bs > 16 ? bs : 16;
+}
+u32 num_blocks_per_row(u32 N, u32 bs) { return (u32)(int)std::ceil((float)N / (float)bs); }  // :1035
+u32 cluster_blockdim(u32 nbpr) {                                                              // :911-920
+  if (nbpr < 32) return 32;
+  int cand = (int)(32 * std::ceil((float)((int)nbpr / 4) / (float)32));
+  cand = cand > 32 ? cand : 32;
+  return (u32)(1024 < cand ? 1024 : cand);
+}
+u32 kept_warp_mask(u32 B) {  // cudaUtil.cuh:37-43: which per-warp partials reach shm[0]
+  const u32 W = B / 32;
+  u32 set[32];
+  for (u32 w = 0; w < W; ++w) set[w] = 1u << w;
+  for (u32 stride = B / 64; stride >= 1; stride >>= 1)
+    for (u32 w = 0; w < stride; ++w) set[w] |= set[w + stride];
+  return set[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: encode.  One warp per row; columns of a row must be ascending (checked, else a sorted
+// copy is made first).  Run-length encodes col / block_size with ballot/popc.
+// ------------------------------------------------------------------------------------------
+static __global__ void k_check_rows_sorted(const u32* __restrict__ rowOff, const u32* __restrict__ colIdx, u32 M,
+                                           u32* __restrict__ unsortedFlag) {
+  const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const u32 nw = (gridDim.x * blockDim.x) >> 5;
+  for (u32 r = gw; r < M; r += nw) {
+    const u32 b = rowOff[r], e = rowOff[r + 1];
+    bool bad = false;
+    for (u32 i = b + 1 + lane; i < e; i += 32) bad |= colIdx[i] <= colIdx[i - 1];
+    if (__any_sync(0xffffffffu, bad)) {
+      if (lane == 0) *unsortedFlag = 1;
+    }
+  }
+}
+
+static __global__ void k_make_row_col_keys(const u32* __restrict__ rowOff, const u32* __restrict__ colIdx, u32 M,
+                                           u64* __restrict__ keys) {
+  const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const u32 nw = (gridDim.x * blockDim.x) >> 5;
+  for (u32 r = gw; r < M; r += nw) {
+    const u32 b = rowOff[r], e = rowOff[r + 1];
+    for (u32 i = b + lane; i < e; i += 32) keys[i] = ((u64)r << 32) | colIdx[i];
+  }
+}
+static __global__ void k_keys_low32(const u64* __restrict__ keys, u32* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = (u32)keys[i];
+}
+
+__device__ __forceinline__ bool blk_kept(u32 blk, u32 B, u32 keptMask) { return (keptMask >> ((blk % B) >> 5)) & 1u; }
+
+// Walks one row's sorted columns and calls emit(blockId, count, ordinal, keptOrdinal, isKept) once per
+// distinct block, in ascending block order (ordinal = rank among all blocks of the row, keptOrdinal =
+// rank among the blocks the reference's reduction tree keeps).  nbAll / nbKept are returned on all lanes.
+template <typename Emit>
+__device__ __forceinline__ void warp_rle_blocks(const u32* __restrict__ cols, u32 len, u32 bs, u32 B, u32 keptMask,
+                                                u32& nbAll, u32& nbKept, Emit emit) {
+  const u32 lane = threadIdx.x & 31;
+  u32 carryBlk = kNull, carryCnt = 0;
+  nbAll = 0;
+  nbKept = 0;
+  for (u32 base = 0; base < len; base += 32) {
+    const u32 i = base + lane;
+    const bool valid = i < len;
+    const u32 blk = valid ? cols[i] / bs : kNull;
+    u32 prev = __shfl_up_sync(0xffffffffu, blk, 1);
+    if (lane == 0) prev = carryBlk;
+    const bool head = valid && blk != prev;
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    const u32 nvalid = __popc(__ballot_sync(0xffffffffu, valid));
+    if (heads == 0) {
+      carryCnt += nvalid;
+      continue;
+    }
+    const u32 firstHead = __ffs(heads) - 1;
+    if (carryBlk != kNull) {  // the carried run closes at the first head of this chunk
+      const bool ck = blk_kept(carryBlk, B, keptMask);
+      if (lane == 0) emit(carryBlk, carryCnt + firstHead, nbAll, nbKept, ck);
+      nbAll += 1;
+      nbKept += ck;
+    }
+    const u32 lastHead = 31 - __clz(heads);
+    const unsigned closedHeads = heads & ~(1u << lastHead);  // every head run but the last closes here
+    const bool isClosed = head && lane != lastHead;
+    const bool kh = isClosed && blk_kept(blk, B, keptMask);
+    const unsigned keptHeads = __ballot_sync(0xffffffffu, kh);
+    if (isClosed) {
+      const unsigned rest = heads >> (lane + 1);  // non-zero: a later head exists
+      const unsigned lt = (1u << lane) - 1u;
+      emit(blk, (u32)__ffs(rest), nbAll + __popc(closedHeads & lt), nbKept + __popc(keptHeads & lt), kh);
+    }
+    nbAll += __popc(closedHeads);
+    nbKept += __popc(keptHeads);
+    carryBlk = __shfl_sync(0xffffffffu, blk, lastHead);
+    carryCnt = nvalid - lastHead;
+  }
+  if (carryBlk != kNull) {
+    const bool ck = blk_kept(carryBlk, B, keptMask);
+    if (lane == 0) emit(carryBlk, carryCnt, nbAll, nbKept, ck);
+    nbAll += 1;
+    nbKept += ck;
+  }
+}
+
+// pass 1: dispersion (rowReordering.cu:78-92, exact uint32 arithmetic) and #kept entries per row
+static __global__ void __launch_bounds__(256) k_encode_count(const u32* __restrict__ rowOff,
+                                                             const u32* __restrict__ cols, u32 M, u32 bs, u32 B,
+                                                             u32 keptMask, u32* __restrict__ disp,
+                                                             u32* __restrict__ keptCnt) {
+  const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const u32 nw = (gridDim.x * blockDim.x) >> 5;
+  for (u32 r = gw; r < M; r += nw) {
+    const u32 b = rowOff[r], len = rowOff[r + 1] - b;
+    u32 nb, kept;
+    warp_rle_blocks(cols + b, len, bs, B, keptMask, nb, kept, [](u32, u32, u32, u32, bool) {});
+    if (lane == 0) {
+      // sum_b (bs - h_b) + nnz * nb  ==  nb*bs - nnz + nnz*nb   (mod 2^32), 0 for empty rows
+      disp[r] = len ? nb * bs - len + len * nb : 0u;
+      if (keptCnt) keptCnt[r] = kept;
+    }
+  }
+}
+
+// pass 2: write the kept (block, count) entries of row asc[pos] at encOff[pos], plus per-position
+// meta {offset, length, sum of squares (uint32 wrap), sum of counts}.
+static __global__ void __launch_bounds__(256) k_encode_fill(const u32* __restrict__ rowOff,
+                                                            const u32* __restrict__ cols, u32 M, u32 bs, u32 B,
+                                                            u32 keptMask, const u32* __restrict__ asc,
+                                                            const u32* __restrict__ encOff, uint2* __restrict__ enc,
+                                                            uint4* __restrict__ meta) {
+  const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const u32 nw = (gridDim.x * blockDim.x) >> 5;
+  for (u32 pos = gw; pos < M; pos += nw) {
+    const u32 r = asc[pos];
+    const u32 b = rowOff[r], len = rowOff[r + 1] - b;
+    const u32 off = encOff[pos];
+    uint2* out = enc + off;
+    u32 ss = 0, s1 = 0, nb, kept;
+    warp_rle_blocks(cols + b, len, bs, B, keptMask, nb, kept, [&](u32 blk, u32 cnt, u32, u32 ordKept, bool isKept) {
+      if (isKept) {
+        out[ordKept] = make_uint2(blk, cnt);
+        ss += cnt * cnt;
+        s1 += cnt;
+      }
+    });
+    ss = __reduce_add_sync(0xffffffffu, ss);
+    s1 = __reduce_add_sync(0xffffffffu, s1);
+    if (lane == 0) meta[pos] = make_uint4(off, kept, ss, s1);
+  }
+}
+
+static __global__ void k_gather_u32(const u32* __restrict__ src, const u32* __restrict__ idx, u32* __restrict__ dst,
+                                    size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[idx[i]];
+}
+static __global__ void k_count_zero(const u32* __restrict__ v, size_t n, u32* __restrict__ cnt) {
+  u32 c = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    c += v[i] == 0;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(cnt, c);
+}
+static __global__ void k_init_cid(u32* cid, size_t n, u32 zeroRows) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    cid[i] = i < zeroRows ? 0u : kNull;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: clustering
+// ------------------------------------------------------------------------------------------
+constexpr int kClThreads = 256;
+constexpr int kClWarps = kClThreads / 32;
+constexpr float kTolRel = 1e-3f;
+constexpr float kTolAbs = 1e-6f;
+
+struct ClusterArgs {
+  u32 M, start0, nbpr, B, keptMask;
+  float alpha;
+  const uint2* enc;
+  const uint4* meta;  // by position: {off, len, ss, s1}
+  u32* cid;           // by position
+  u32* ctrl;          // [0..2] firstJoin slots, [3..5] firstReject slots, [6] exact-eval counter
+  u32* numClustersOut;
+};
+
+__device__ __forceinline__ u32 ld_cg(const u32* p) { return __ldcg(p); }
+
+// binary search of block id i in a sorted entry list; returns its count or 0
+__device__ __forceinline__ u32 lookup_cnt(const uint2* __restrict__ e, u32 L, u32 i) {
+  u32 lo = 0, hi = L;
+  while (lo < hi) {
+    const u32 mid = (lo + hi) >> 1;
+    const u32 b = e[mid].x;
+    if (b < i) lo = mid + 1; else hi = mid;
+  }
+  return (lo < L && e[lo].x == i) ? e[lo].y : 0u;
+}
+
+// Literal restatement of calculate_similarity_norm_weighted_jaccard (rowReordering.cu:235-293) +
+// cuUtil::reduce_sum (cudaUtil.cuh:13-45) for ONE pair, executed by one warp that plays the B
+// reference threads warp by warp.  Round-to-nearest intrinsics only: no contraction, no approx.
+__device__ float exact_similarity_warp(const u32* __restrict__ rep, const uint2* __restrict__ ent, u32 L, u32 nbpr,
+                                       u32 B, u32 keptMask, u32 ssRep, u32 ssCmp) {
+  const u32 lane = threadIdx.x & 31;
+  const float normRep = __fsqrt_rn(__uint2float_rn(ssRep));
+  const float normCmp = __fsqrt_rn(__uint2float_rn(ssCmp));
+  const u32 W = B >> 5;
+  float smin = 0.f, smax = 0.f;  // lane w holds the reduced value of reference warp w
+  for (u32 vw = 0; vw < W; ++vw) {
+    if (!((keptMask >> vw) & 1u)) continue;  // never added into shm[0] by the reference's tree
+    float pmin = 0.f, pmax = 0.f;
+    for (u32 i = (vw << 5) + lane; i < nbpr; i += B) {
+      const u32 r = rep[i];
+      const u32 c = lookup_cnt(ent, L, i);
+      const float a = __fdiv_rn(__uint2float_rn(r), normRep);
+      const float b = __fdiv_rn(__uint2float_rn(c), normCmp);
+      pmin = __fadd_rn(pmin, fminf(a, b));
+      pmax = __fadd_rn(pmax, fmaxf(a, b));
+    }
+#pragma unroll
+    for (int w = 1; w < 32; w <<= 1) {
+      pmin = __fadd_rn(pmin, __shfl_xor_sync(0xffffffffu, pmin, w));
+      pmax = __fadd_rn(pmax, __shfl_xor_sync(0xffffffffu, pmax, w));
+    }
+    if (lane == vw) { smin = pmin; smax = pmax; }
+  }
+  for (u32 stride = B >> 6; stride >= 1; stride >>= 1) {
+    const float omin = __shfl_down_sync(0xffffffffu, smin, stride);
+    const float omax = __shfl_down_sync(0xffffffffu, smax, stride);
+    if (lane < stride) { smin = __fadd_rn(smin, omin); smax = __fadd_rn(smax, omax); }
+  }
+  const float sim = __fdiv_rn(smin, smax);
+  return __shfl_sync(0xffffffffu, sim, 0);
+}
+
+static __global__ void __launch_bounds__(kClThreads) k_cluster(ClusterArgs a) {
+  extern __shared__ u32 rep[];  // dense accumulated histogram of the current cluster (kept blocks)
+  __shared__ u32 sRed[kClWarps];
+  __shared__ u32 sSsRep, sS1Rep;
+  cg::grid_group grid = cg::this_grid();
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u32 totalWarps = gridDim.x * kClWarps;
+  const u32 gw = blockIdx.x * kClWarps + warp;
+  volatile u32* ctrl = a.ctrl;
+
+  u32 cluster = 1, seed = a.start0, iter = 0;
+  while (seed < a.M) {
+    // ---- new cluster: rep = histogram of the seed row
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.cid[seed] = cluster;
+    for (u32 i = threadIdx.x; i < a.nbpr; i += kClThreads) rep[i] = 0;
+    __syncthreads();
+    {
+      const uint4 m = a.meta[seed];
+      for (u32 j = threadIdx.x; j < m.y; j += kClThreads) {
+        const uint2 e = a.enc[m.x + j];
+        rep[e.x] = e.y;
+      }
+      if (threadIdx.x == 0) { sSsRep = m.z; sS1Rep = m.w; }
+    }
+    __syncthreads();
+    u32 p = seed + 1, nextSeed = kNull;
+    u32 chunk = totalWarps;
+    while (p < a.M) {
+      const u32 e = (a.M - p > chunk) ? p + chunk : a.M;
+      const u32 slot = iter % 3;
+      const u32 ssRep = sSsRep;
+      const float nRepInv = ssRep ? 1.0f / sqrtf((float)ssRep) : 0.f;
+      const float Sa = (float)sS1Rep * nRepInv;
+      for (u32 pos = p + gw; pos < e; pos += totalWarps) {
+        if (ld_cg(a.cid + pos) != kNull) continue;
+        const uint4 m = a.meta[pos];
+        const u32 ssCmp = m.z;
+        bool join;
+        if (ssRep == 0 || ssCmp == 0) {
+          // rowReordering.cu:263-268: both zero -> 1.0f, one zero -> 0.0f
+          const float sim = (ssRep == 0 && ssCmp == 0) ? 1.0f : 0.0f;
+          join = sim > a.alpha;
+        } else {
+          const uint2* ent = a.enc + m.x;
+          const float nCmpInv = 1.0f / sqrtf((float)ssCmp);
+          float mn = 0.f;
+          for (u32 j = lane; j < m.y; j += 32) {
+            const uint2 en = ent[j];
+            const u32 r = rep[en.x];
+            mn += fminf((float)r * nRepInv, (float)en.y * nCmpInv);
+          }
+#pragma unroll
+          for (int w = 16; w >= 1; w >>= 1) mn += __shfl_xor_sync(0xffffffffu, mn, w);
+          const float den = Sa + (float)m.w * nCmpInv - mn;
+          const float est = mn / den;
+          const float tol = kTolRel * fabsf(a.alpha) + kTolAbs;
+          if (den > 0.f && est > a.alpha + tol) join = true;
+          else if (den > 0.f && est < a.alpha - tol) join = false;
+          else {
+            const float sim = exact_similarity_warp(rep, ent, m.y, a.nbpr, a.B, a.keptMask, ssRep, ssCmp);
+            join = sim > a.alpha;
+            if (lane == 0) atomicAdd(a.ctrl + 6, 1u);
+          }
+        }
+        if (lane == 0) {
+          if (join) atomicMin(a.ctrl + slot, pos);
+          else if (nextSeed == kNull) atomicMin(a.ctrl + 3 + slot, pos);
+        }
+      }
+      __threadfence();
+      grid.sync();
+      const u32 fj = ctrl[slot];
+      const u32 fr = ctrl[3 + slot];
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const u32 rs = (iter + 2) % 3;
+        ctrl[rs] = kNull;
+        ctrl[3 + rs] = kNull;
+      }
+      // rejects before the first join are final for this cluster; the earliest one seeds the next
+      if (nextSeed == kNull && fr != kNull && (fj == kNull || fr < fj)) nextSeed = fr;
+      if (fj != kNull) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.cid[fj] = cluster;
+        // rep += hist(fj); sum of squares updated exactly in uint32 (wraps like the reference's)
+        const uint4 m = a.meta[fj];
+        u32 dss = 0;
+        for (u32 j = threadIdx.x; j < m.y; j += kClThreads) {
+          const uint2 en = a.enc[m.x + j];
+          const u32 r = rep[en.x];
+          const u32 nr = r + en.y;
+          dss += nr * nr - r * r;
+          rep[en.x] = nr;
+        }
+        dss = __reduce_add_sync(0xffffffffu, dss);
+        if (lane == 0) sRed[warp] = dss;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          u32 t = 0;
+          for (int w = 0; w < kClWarps; ++w) t += sRed[w];
+          sSsRep += t;
+          sS1Rep += m.w;
+        }
+        __syncthreads();
+        p = fj + 1;
+        chunk = totalWarps;
+      } else {
+        p = e;
+        if (chunk < totalWarps * 16u) chunk *= 2;
+      }
+      ++iter;
+    }
+    if (nextSeed == kNull) break;
+    seed = nextSeed;
+    ++cluster;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.numClustersOut = cluster;
+}
+
+// ------------------------------------------------------------------------------------------
+// final permutation
+// ------------------------------------------------------------------------------------------
+static __global__ void k_compose_perm(const u32* __restrict__ asc, const u32* __restrict__ indices, u32 skip, u32 n,
+                                      u32* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = asc[indices[skip + i]];
+}
+
+// ------------------------------------------------------------------------------------------
+// host drivers
+// ------------------------------------------------------------------------------------------
+struct SortedCols {
+  const u32* cols;       // per-row ascending columns (either the input or an owned sorted copy)
+  DevBuf<u32> owned;
+};
+
+static void make_sorted_cols(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32 nnz, cudaStream_t s,
+                             SortedCols& out) {
+  DevBuf<u32> flag(1);
+  SB_CUDA(cudaMemsetAsync(flag.get(), 0, 4, s));
+  k_check_rows_sorted<<<grid_for((size_t)M * 32), 256, 0, s>>>(d_rowOff, d_colIdx, M, flag.get());
+  SB_LAUNCH_CHECK();
+  u32 h = 0;
+  SB_CUDA(cudaMemcpyAsync(&h, flag.get(), 4, cudaMemcpyDeviceToHost, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+  if (!h) {
+    out.cols = d_colIdx;
+    return;
+  }
+  // file-order columns inside a row (src/Matrix.cpp:467 sorts by row only): sort (row, col) keys
+  DevBuf<u64> ka(nnz), kb(nnz);
+  k_make_row_col_keys<<<grid_for((size_t)M * 32), 256, 0, s>>>(d_rowOff, d_colIdx, M, ka.get());
+  SB_LAUNCH_CHECK();
+  const int which = radix_sort_pairs<u64>(ka.get(), kb.get(), nullptr, nullptr, nnz, 0, 32 + bits_for(M), s);
+  (void)N;
+  out.owned.alloc(nnz);
+  k_keys_low32<<<grid_for(nnz), 256, 0, s>>>(which ? kb.get() : ka.get(), out.owned.get(), nnz);
+  SB_LAUNCH_CHECK();
+  SB_CUDA(cudaStreamSynchronize(s));
+  out.cols = out.owned.get();
+}
+
+void dispersion_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32 nnz, u32 bs, u32* d_disp,
+                    u32* nbprOut, cudaStream_t s) {
+  const u32 nbpr = num_blocks_per_row(N, bs);
+  if (nbprOut) *nbprOut = nbpr;
+  SortedCols sc;
+  make_sorted_cols(d_rowOff, d_colIdx, M, N, nnz, s, sc);
+  const u32 B = cluster_blockdim(nbpr);
+  k_encode_count<<<grid_for((size_t)M * 32), 256, 0, s>>>(d_rowOff, sc.cols, M, bs, B, kept_warp_mask(B), d_disp,
+                                                         nullptr);
+  SB_LAUNCH_CHECK();
+  SB_CUDA(cudaStreamSynchronize(s));
+}
+
+void row_reorder_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32 nnz, float alpha, u32 bs,
+                     u32* d_reorderedRows, u32* numRows, int32_t* numClusters, RowReorderStats* st, cudaStream_t s) {
+  if (M == 0) { *numRows = 0; if (numClusters) *numClusters = 0; return; }
+  const u32 nbpr = num_blocks_per_row(N, bs);
+  const u32 B = cluster_blockdim(nbpr);
+  const u32 keptMask = kept_warp_mask(B);
+  if ((size_t)nbpr * 4 > 200 * 1024) fail(SDDMM_E_UNSUPPORTED, "nbpr=%u does not fit shared memory; use a larger block_size", nbpr);
+
+  SortedCols sc;
+  make_sorted_cols(d_rowOff, d_colIdx, M, N, nnz, s, sc);
+
+  // K1 pass 1: dispersion + kept-entry counts
+  DevBuf<u32> disp(M), keptCnt(M);
+  k_encode_count<<<grid_for((size_t)M * 32), 256, 0, s>>>(d_rowOff, sc.cols, M, bs, B, keptMask, disp.get(),
+                                                         keptCnt.get());
+  SB_LAUNCH_CHECK();
+
+  // K3: rows by (dispersion asc, row asc), stable
+  DevBuf<u32> keyA(M), keyB(M), ascA(M), ascB(M);
+  SB_CUDA(cudaMemcpyAsync(keyA.get(), disp.get(), (size_t)M * 4, cudaMemcpyDeviceToDevice, s));
+  iota<u32>(ascA.get(), M, 0u, s);
+  const int w1 = radix_sort_pairs<u32>(keyA.get(), keyB.get(), ascA.get(), ascB.get(), M, 0, 32, s);
+  const u32* asc = w1 ? ascB.get() : ascA.get();
+
+  DevBuf<u32> zc(1);
+  SB_CUDA(cudaMemsetAsync(zc.get(), 0, 4, s));
+  k_count_zero<<<grid_for(M), 256, 0, s>>>(disp.get(), M, zc.get());
+  SB_LAUNCH_CHECK();
+  u32 zeroRows = 0;
+  SB_CUDA(cudaMemcpyAsync(&zeroRows, zc.get(), 4, cudaMemcpyDeviceToHost, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+
+  // K1 pass 2: sparse encodings laid out in dispersion order
+  DevBuf<u32> encOff((size_t)M + 1);
+  k_gather_u32<<<grid_for(M), 256, 0, s>>>(keptCnt.get(), asc, encOff.get(), M);
+  SB_LAUNCH_CHECK();
+  SB_CUDA(cudaMemsetAsync(encOff.get() + M, 0, 4, s));
+  exclusive_scan_u32(encOff.get(), encOff.get(), (size_t)M + 1, s);
+  u32 totalEnt = 0;
+  SB_CUDA(cudaMemcpyAsync(&totalEnt, encOff.get() + M, 4, cudaMemcpyDeviceToHost, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+  DevBuf<uint2> enc(totalEnt ? totalEnt : 1);
+  DevBuf<uint4> meta(M);
+  k_encode_fill<<<grid_for((size_t)M * 32), 256, 0, s>>>(d_rowOff, sc.cols, M, bs, B, keptMask, asc, encOff.get(),
+                                                        enc.get(), meta.get());
+  SB_LAUNCH_CHECK();
+
+  // K2: clustering
+  DevBuf<u32> cid(M), ctrl(8), ncl(1);
+  k_init_cid<<<grid_for(M), 256, 0, s>>>(cid.get(), M, zeroRows);
+  SB_LAUNCH_CHECK();
+  SB_CUDA(cudaMemsetAsync(ctrl.get(), 0xFF, 6 * 4, s));
+  SB_CUDA(cudaMemsetAsync(ctrl.get() + 6, 0, 2 * 4, s));
+  SB_CUDA(cudaMemsetAsync(ncl.get(), 0, 4, s));
+  u32 exactEvals = 0;
+  if (zeroRows < M) {
+    ClusterArgs a;
+    a.M = M; a.start0 = zeroRows; a.nbpr = nbpr; a.B = B; a.keptMask = keptMask; a.alpha = alpha;
+    a.enc = enc.get(); a.meta = meta.get(); a.cid = cid.get(); a.ctrl = ctrl.get(); a.numClustersOut = ncl.get();
+    const size_t smem = (size_t)nbpr * 4;
+    SB_CUDA(cudaFuncSetAttribute(k_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int perSm = 0;
+    SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_cluster, kClThreads, smem));
+    if (perSm < 1) fail(SDDMM_E_UNSUPPORTED, "clustering kernel does not fit on an SM (nbpr=%u)", nbpr);
+    if (perSm > 2) perSm = 2;
+    // no more CTAs than there are candidate rows to look at
+    u32 grid = (u32)(perSm * device_sm_count());
+    const u32 need = ceil_div(M - zeroRows, kClWarps);
+    if (grid > need) grid = need ? need : 1;
+    void* args[] = {&a};
+    SB_CUDA(cudaLaunchCooperativeKernel((void*)k_cluster, dim3(grid), dim3(kClThreads), args, smem, s));
+    SB_LAUNCH_CHECK();
+    SB_CUDA(cudaMemcpyAsync(&exactEvals, ctrl.get() + 6, 4, cudaMemcpyDeviceToHost, s));
+  }
+
+  // :986-995  stable sort positions by cluster id; permutation = asc[indices]
+  DevBuf<u32> cidB(M), idxA(M), idxB(M);
+  iota<u32>(idxA.get(), M, 0u, s);
+  const int w2 = radix_sort_pairs<u32>(cid.get(), cidB.get(), idxA.get(), idxB.get(), M, 0, 32, s);
+  const u32* sortedCid = w2 ? cidB.get() : cid.get();
+  const u32* indices = w2 ? idxB.get() : idxA.get();
+  const u32 nR = M - zeroRows;  // :1081-1090: cluster 0 == the empty rows == the stripped prefix
+  if (nR) {
+    k_compose_perm<<<grid_for(nR), 256, 0, s>>>(asc, indices, zeroRows, nR, d_reorderedRows);
+    SB_LAUNCH_CHECK();
+  }
+  *numRows = nR;
+  // :996 quirk: cluster_cnt = sortedIds[indices[M-1]] + (zero_row_idx != 0)
+  u32 lastIdx = 0, q = 0;
+  SB_CUDA(cudaMemcpyAsync(&lastIdx, indices + (M - 1), 4, cudaMemcpyDeviceToHost, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+  SB_CUDA(cudaMemcpyAsync(&q, sortedCid + lastIdx, 4, cudaMemcpyDeviceToHost, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+  if (numClusters) *numClusters = (int32_t)(q + (zeroRows != 0 ? 1u : 0u));
+  if (st) {
+    st->nbpr = nbpr; st->blockDim = B; st->keptMask = keptMask; st->zeroRows = zeroRows;
+    st->exactEvals = exactEvals; st->encEntries = totalEnt;
+    u32 c = 0;
+    SB_CUDA(cudaMemcpy(&c, ncl.get(), 4, cudaMemcpyDeviceToHost));
+    st->clustersCreated = c;
+  }
+}
+
+}  // namespace sb

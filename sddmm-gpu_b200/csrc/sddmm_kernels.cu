@@ -1,0 +1,311 @@
+// sddmm_kernels.cu -- the two SDDMM kernels (a10, a11 of SURVEY.md 8a) and their launcher (a9).
+//
+//   k_sddmm_dense    : dense 16x16 blocks on the 5th-gen tensor cores (tcgen05.mma kind::tf32,
+//                      accumulator in TMEM).  Replaces the WMMA m16n16k8 kernels
+//                      src/sddmmKernel.cu:213-351 and :355-488.
+//                      The problem is transposed: up to 8 dense blocks = 128 gathered
+//                      B columns sit on the MMA M axis, the 16 panel rows on N (M=128, N=16, K=8).
+//                      Operands are rounded to TF32 with cvt.rna exactly like the reference's
+//                      wmma::__float_to_tf32 (sddmmKernel.cu:318-323) while they are staged into the
+//                      128B-swizzled K-major shared-memory tiles the UMMA descriptors describe.
+//   k_sddmm_residual : FP32 CUDA-core kernel over the residual COO entries, 128-bit loads of the
+//                      gathered B rows, A panel tile in shared memory, 8 lanes per non-zero with a
+//                      shuffle reduction.  Replaces src/sddmmKernel.cu:1994-2104 and :2109-2199.
+#include "layout.cuh"
+#include "sddmm_kernels.cuh"
+
+namespace sb {
+
+// =============================================================================================
+// residual kernel
+// =============================================================================================
+constexpr int kResThreads = 256;
+constexpr int kResLanes = 8;  // lanes cooperating on one non-zero
+
+__device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+static __global__ void __launch_bounds__(kResThreads)
+k_sddmm_residual(u32 M, u32 K4, const float4* __restrict__ A4, const float4* __restrict__ B4,
+                 const u32* __restrict__ R, u32 nR, const u32* __restrict__ vOff, const u32* __restrict__ sVals,
+                 const u32* __restrict__ sRows, const u32* __restrict__ sCols, const uint2* __restrict__ work,
+                 float* __restrict__ P) {
+  extern __shared__ float4 sA[];  // 16 rows x K4 float4
+  const uint2 w = work[blockIdx.x];
+  const u32 p = w.x;
+  const u32 segBeg = vOff[p] + w.y;
+  const u32 segLim = vOff[p + 1];
+  const u32 segEnd = (segLim - segBeg > kSparseChunk) ? segBeg + kSparseChunk : segLim;
+
+  for (u32 i = threadIdx.x; i < 16u * K4; i += kResThreads) {
+    const u32 r = i / K4, c = i - r * K4;
+    const u32 ri = p * 16u + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ri < nR) {
+      const u32 row = R[ri];
+      if (row < M) v = __ldg(A4 + (size_t)row * K4 + c);
+    }
+    sA[i] = v;
+  }
+  __syncthreads();
+
+  const u32 grp = threadIdx.x / kResLanes, gl = threadIdx.x % kResLanes;
+  constexpr u32 kGroups = kResThreads / kResLanes;
+  for (u32 e = segBeg + grp; e < segEnd; e += kGroups) {
+    const u32 r = sRows[e];
+    const u32 col = sCols[e];
+    const float4* __restrict__ b = B4 + (size_t)col * K4;
+    const float4* a = sA + r * K4;
+    float acc0 = 0.f, acc1 = 0.f;
+    u32 c = gl;
+    for (; c + kResLanes < K4; c += 2 * kResLanes) {
+      const float4 b0 = ldg_nc_f4(b + c);
+      const float4 b1 = ldg_nc_f4(b + c + kResLanes);
+      const float4 a0 = a[c];
+      const float4 a1 = a[c + kResLanes];
+      acc0 = fmaf(a0.x, b0.x, acc0); acc0 = fmaf(a0.y, b0.y, acc0);
+      acc0 = fmaf(a0.z, b0.z, acc0); acc0 = fmaf(a0.w, b0.w, acc0);
+      acc1 = fmaf(a1.x, b1.x, acc1); acc1 = fmaf(a1.y, b1.y, acc1);
+      acc1 = fmaf(a1.z, b1.z, acc1); acc1 = fmaf(a1.w, b1.w, acc1);
+    }
+    if (c < K4) {
+      const float4 b0 = ldg_nc_f4(b + c);
+      const float4 a0 = a[c];
+      acc0 = fmaf(a0.x, b0.x, acc0); acc0 = fmaf(a0.y, b0.y, acc0);
+      acc0 = fmaf(a0.z, b0.z, acc0); acc0 = fmaf(a0.w, b0.w, acc0);
+    }
+    float acc = acc0 + acc1;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (gl == 0) P[sVals[e]] = acc;
+  }
+}
+
+// =============================================================================================
+// dense kernel: tcgen05 / TMEM
+// =============================================================================================
+constexpr int kDnThreads = 128;               // 4 warps == the 4 TMEM lane quarters
+constexpr u32 kDnKChunk = 32;                 // floats per K step = one 128-byte swizzle row
+constexpr u32 kDnRowsB = kDenseGroupBlocks * 16;  // 128 gathered B^T rows (MMA M)
+constexpr u32 kDnStageBytes = kDnRowsB * 128 + 16 * 128;  // 16 KB + 2 KB, multiple of 1024
+constexpr u32 kDnStages = 2;
+constexpr u32 kDnTmemCols = 32;
+
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ u32 mbar_try_wait(u64* bar, u32 parity) {
+  u32 ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major),
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024), [46,48) version = 1, [61,64) layout 2.
+__device__ __forceinline__ u64 umma_desc_sw128(u32 smemAddr) {
+  u64 d = 0;
+  d |= (u64)((smemAddr & 0x3FFFFu) >> 4);
+  d |= (u64)(1024u >> 4) << 32;
+  d |= (u64)1 << 46;
+  d |= (u64)2 << 61;
+  return d;
+}
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a/b=TF32 [7,10)/[10,13),
+// K-major both, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr u32 umma_idesc_tf32(u32 Mdim, u32 Ndim) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((Ndim >> 3) << 17) | ((Mdim >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  u32 r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// stores one 16-byte chunk of row `row` (128 B per row) at its 128B-swizzled position
+__device__ __forceinline__ void st_swizzled(unsigned char* tile, u32 row, u32 chunk, float4 v) {
+  const u32 off = (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4);
+  *reinterpret_cast<float4*>(tile + off) = v;
+}
+
+static __global__ void __launch_bounds__(kDnThreads)
+k_sddmm_dense(u32 M, u32 N, u32 K, const float* __restrict__ A, const float* __restrict__ B,
+              const u32* __restrict__ R, u32 nR, const u32* __restrict__ denseCols,
+              const u32* __restrict__ blockOffsets, const u32* __restrict__ blockValues,
+              const uint2* __restrict__ work, float* __restrict__ P) {
+  extern __shared__ __align__(1024) unsigned char smemRaw[];
+  // carve: stages (1024-aligned), then barriers / indices
+  unsigned char* stages = smemRaw + ((1024u - (smem_u32(smemRaw) & 1023u)) & 1023u);
+  __shared__ u64 mbar[kDnStages];
+  __shared__ u32 tmemBase;
+  __shared__ u32 sCols[kDnRowsB];
+  __shared__ u32 sRowsA[16];
+
+  const u32 tid = threadIdx.x, warp = tid >> 5;
+  const uint2 w = work[blockIdx.x];
+  const u32 p = w.x, firstBlk = w.y;
+  const u32 blkBeg = blockOffsets[p], blkEnd = blockOffsets[p + 1];
+  const u32 nBlk = min(kDenseGroupBlocks, blkEnd - blkBeg - firstBlk);
+  const u32 colBase = (blkBeg + firstBlk) * 16u;  // denseColOffsets[p] == blockOffsets[p]*16
+
+  // gathered column / row ids (sentinel N / missing rows -> zero rows, sddmmKernel.cu:279-306)
+  sCols[tid] = (tid < nBlk * 16u) ? denseCols[colBase + tid] : N;
+  if (tid < 16) {
+    const u32 ri = p * 16u + tid;
+    sRowsA[tid] = ri < nR ? R[ri] : M;
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmemBase)),
+                 "r"(kDnTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (u32 s = 0; s < kDnStages; ++s) mbar_init(&mbar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const u32 tmem = tmemBase;
+
+  const u32 numChunks = (K + kDnKChunk - 1) / kDnKChunk;
+  constexpr u32 idesc = umma_idesc_tf32(128, 16);
+
+  for (u32 kc = 0; kc < numChunks; ++kc) {
+    const u32 s = kc % kDnStages;
+    if (kc >= kDnStages) mbar_wait(&mbar[s], ((kc / kDnStages) - 1) & 1u);  // MMA of chunk kc-2 released the stage
+    unsigned char* tileB = stages + s * kDnStageBytes;   // 128 rows x 128 B (MMA "A" operand)
+    unsigned char* tileA = tileB + kDnRowsB * 128;       // 16 rows x 128 B  (MMA "B" operand)
+    const u32 k0 = kc * kDnKChunk;
+    // ---- stage the gathered B^T rows: 8 lanes per row, 16 B each; coalesced 128 B per row
+#pragma unroll
+    for (u32 it = 0; it < 8; ++it) {
+      const u32 idx = it * kDnThreads + tid;
+      const u32 row = idx >> 3, chunk = idx & 7u;
+      const u32 col = sCols[row];
+      const u32 k = k0 + chunk * 4u;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col < N && k < K) v = __ldg(reinterpret_cast<const float4*>(B + (size_t)col * K + k));
+      v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w);
+      st_swizzled(tileB, row, chunk, v);
+    }
+    {
+      const u32 row = tid >> 3, chunk = tid & 7u;
+      const u32 arow = sRowsA[row];
+      const u32 k = k0 + chunk * 4u;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (arow < M && k < K) v = __ldg(reinterpret_cast<const float4*>(A + (size_t)arow * K + k));
+      v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w);
+      st_swizzled(tileA, row, chunk, v);
+    }
+    // generic-proxy writes -> visible to the async proxy (tensor core reads smem through it)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const u64 dB = umma_desc_sw128(smem_u32(tileB));
+      const u64 dA = umma_desc_sw128(smem_u32(tileA));
+#pragma unroll
+      for (u32 k = 0; k < kDnKChunk / 8; ++k) {
+        const u32 acc = (kc | k) ? 1u : 0u;
+        // advance 8 tf32 = 32 B inside the swizzle row: +2 in the (>>4) start-address field
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem),
+            "l"(dB + 2ull * k), "l"(dA + 2ull * k), "r"(idesc), "r"(acc)
+            : "memory");
+      }
+      // arrives on the stage barrier once the MMAs above have finished reading shared memory
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_u32(&mbar[s]))
+                   : "memory");
+    }
+  }
+  // last commit covers every earlier MMA (commits complete in order)
+  {
+    const u32 last = numChunks - 1;
+    mbar_wait(&mbar[last % kDnStages], (last / kDnStages) & 1u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+
+  // ---- epilogue: TMEM lane = gathered column slot j, register n = panel row
+  u32 acc[16];
+  const u32 taddr = tmem + ((warp * 32u) << 16);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]), "=r"(acc[7]),
+        "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]), "=r"(acc[14]),
+        "=r"(acc[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (tid < nBlk * 16u) {
+    const u32* bv = blockValues + ((size_t)(blkBeg + firstBlk) + (tid >> 4)) * 256u + (tid & 15u);
+#pragma unroll
+    for (u32 r = 0; r < 16; ++r) {
+      const u32 idx = __ldg(bv + r * 16u);
+      if (idx != kNull) P[idx] = __uint_as_float(acc[r]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kDnTmemCols) : "memory");
+  }
+}
+
+// =============================================================================================
+// launcher
+// =============================================================================================
+void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB, float* dP, cudaStream_t denseStream,
+                  cudaStream_t sparseStream, int which) {
+  if (K == 0 || (K & 3u)) fail(SDDMM_E_ARG, "K=%u must be a positive multiple of 4", K);
+  const bsmr_layout_info& I = L->info;
+  auto arr = [&](bsmr_array_id id) { return L->arr[id].get(); };
+  if (L->numDenseWork && (which & kLaunchDense)) {
+    const size_t smem = (size_t)kDnStages * kDnStageBytes + 1024;
+    static bool attrSet = false;
+    if (!attrSet) {
+      SB_CUDA(cudaFuncSetAttribute(k_sddmm_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attrSet = true;
+    }
+    k_sddmm_dense<<<L->numDenseWork, kDnThreads, smem, denseStream>>>(
+        I.M, I.N, K, dA, dB, arr(BSMR_REORDERED_ROWS), I.numRows, arr(BSMR_DENSE_COLS), arr(RPHM_BLOCK_OFFSETS),
+        arr(RPHM_BLOCK_VALUES), L->denseWork.get(), dP);
+    SB_LAUNCH_CHECK();
+  }
+  if (L->numSparseWork && (which & kLaunchSparse)) {
+    const u32 K4 = K / 4;
+    const size_t smem = (size_t)16 * K * sizeof(float);
+    if (smem > 200 * 1024) fail(SDDMM_E_UNSUPPORTED, "K=%u too large for the residual kernel's A tile", K);
+    if (smem > 48 * 1024)
+      SB_CUDA(cudaFuncSetAttribute(k_sddmm_residual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_sddmm_residual<<<L->numSparseWork, kResThreads, smem, sparseStream>>>(
+        I.M, K4, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB), arr(BSMR_REORDERED_ROWS),
+        I.numRows, arr(BSMR_SPARSE_VALUE_OFFSETS), arr(RPHM_SPARSE_VALUES), arr(RPHM_SPARSE_RELATIVE_ROWS),
+        arr(RPHM_SPARSE_COL_INDICES), L->sparseWork.get(), dP);
+    SB_LAUNCH_CHECK();
+  }
+}
+
+}  // namespace sb

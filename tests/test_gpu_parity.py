@@ -1,0 +1,230 @@
+"""GPU parity tests (-m gpu): the CUDA path, through the C ABI, against the oracle on the same inputs.
+
+Bit-exact for everything integer (dispersion, permutation, BSMR/RPHM arrays); the reference's own
+checkData tolerance (include/checkData.hpp:14-30: |a-b| < 1e-5 or |a-b|/max(|a|,|b|,1e-3) < 1e-3) for P.
+"""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from cases import GOLDEN, ROOT, gen, operands, pkg, small_cases
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CASES = small_cases()
+LAYOUT_KEYS = ("denseCols", "denseColOffsets", "sparseCols", "sparseColOffsets", "sparseValueOffsets")
+RPHM_KEYS = ("blockOffsets", "blockValues", "sparseValues", "sparseRelativeRows", "sparseColIndices",
+             "denseRowPanelIds", "denseColBlockIters", "sparseRowPanelIds", "sparseColBlockIters")
+
+
+def _bs(S):
+    return O.block_size(S.M, S.N, 180e9)
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int32) if a.dtype == np.uint32 else np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_dispersion_bitexact(name, torch_mod):
+    S, alpha, delta, K = CASES[name]
+    bs = _bs(S)
+    d, nb = pkg.dispersion_dev(_dev(torch_mod, S.row_off), _dev(torch_mod, S.col_idx), S.M, S.N, bs)
+    _, disp = O.encode_dispersion(S, bs, dense=False)
+    assert nb == O.nbpr(S.N, bs)
+    assert np.array_equal(d.cpu().numpy().view(np.uint32), disp)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_row_reorder_bitexact(name):
+    S, alpha, delta, K = CASES[name]
+    bs = _bs(S)
+    b = pkg.BSMR().rowReordering(alpha, S, block_size=bs)
+    rr = O.row_reorder(S, alpha, bs)
+    assert np.array_equal(b.reorderedRows(), rr["reorderedRows"])
+    assert b.numClusters() == rr["numClusters"]
+
+
+@pytest.mark.parametrize("alpha", [0.0, 0.2, 0.45, 0.6, 0.75, 1.0, -0.5])
+def test_row_reorder_alpha_sweep(alpha):
+    S = gen.block_structured(300, 2000, 7, 120, 0.7, seed=5, noise=0.003)
+    bs = _bs(S)
+    b = pkg.BSMR().rowReordering(alpha, S, block_size=bs)
+    rr = O.row_reorder(S, alpha, bs)
+    assert np.array_equal(b.reorderedRows(), rr["reorderedRows"])
+
+
+@pytest.mark.parametrize("bs", [16, 23, 64, 200])
+def test_row_reorder_explicit_block_size(bs):
+    S = gen.rmat(11, 8, 9)
+    b = pkg.BSMR().rowReordering(0.25, S, block_size=bs)
+    rr = O.row_reorder(S, 0.25, bs)
+    assert np.array_equal(b.reorderedRows(), rr["reorderedRows"])
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_layout_bitexact(name):
+    """column reordering + RPHM arrays from the ORACLE's row order (isolates this stage)."""
+    S, alpha, delta, K = CASES[name]
+    R = O.row_reorder(S, alpha, _bs(S))["reorderedRows"]
+    b = pkg.BSMR().colReordering(delta, S, R)
+    cr = O.col_reorder(S, R, delta)
+    rp = O.rphm_build(S, R, cr)
+    got = b.layout().arrays()
+    for k in LAYOUT_KEYS:
+        assert np.array_equal(got[k], cr[k]), k
+    for k in RPHM_KEYS:
+        assert np.array_equal(got[k], rp[k]), k
+    info = b.layout().info
+    assert info.numDenseBlocks == rp["blockOffsets"][-1]
+    assert info.numDenseThreadBlocks == rp["numDenseThreadBlocks"]
+    assert info.numSparseThreadBlocks == rp["numSparseThreadBlocks"]
+    assert info.maxNumDenseColBlocksInRowPanel == rp["maxNumDenseColBlocksInRowPanel"]
+    assert info.maxNumSparseColBlocksInRowPanel == rp["maxNumSparseColBlocksInRowPanel"]
+
+
+@pytest.mark.parametrize("delta", [0.0, 0.05, 0.5, 0.9, 1.1])
+def test_layout_delta_sweep(delta):
+    S = gen.dlmc_magnitude_mask(256, 512, 0.8, 12)
+    R = O.row_reorder(S, 0.3, 16)["reorderedRows"]
+    got = pkg.BSMR().colReordering(delta, S, R).layout().arrays()
+    cr = O.col_reorder(S, R, delta)
+    rp = O.rphm_build(S, R, cr)
+    for k in LAYOUT_KEYS:
+        assert np.array_equal(got[k], cr[k]), k
+    for k in RPHM_KEYS:
+        assert np.array_equal(got[k], rp[k]), k
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_sddmm_values_within_reference_tolerance(name):
+    """whole path on host buffers == sddmm(options, A, B, P, logger), checked with checkData."""
+    S, alpha, delta, K = CASES[name]
+    A, B = operands(S, K)
+    res = pkg.sddmm(S, A, B, alpha=alpha, delta=delta, block_size=_bs(S))
+    Pref = O.sddmm_cpu(S, A, B)
+    assert O.check_data(Pref, res["P"]) == 0
+    assert res["gpu_launches"] > 0
+    rr = O.row_reorder(S, alpha, _bs(S))
+    assert np.array_equal(res["reorderedRows"], rr["reorderedRows"])
+
+
+@pytest.mark.parametrize("K", [4, 32, 36, 64, 96, 128, 256, 512])
+@pytest.mark.parametrize("delta", [0.0, 0.3, 1.1])
+def test_sddmm_k_sweep(K, delta):
+    """delta=0: everything through the tcgen05 dense kernel; 1.1: everything residual; 0.3: both."""
+    S = gen.block_structured(200, 300, 4, 64, 0.8, seed=2, noise=0.01)
+    A, B = operands(S, K)
+    res = pkg.sddmm(S, A, B, alpha=0.3, delta=delta, block_size=16)
+    if delta == 0.0:
+        assert res["numSparseValues"] == 0
+    if delta > 1.0:
+        assert res["numDenseBlocks"] == 0
+    assert O.check_data(O.sddmm_cpu(S, A, B), res["P"]) == 0
+
+
+def test_residual_kernel_is_fp32_accurate():
+    """residual path is fp32 FMA: much tighter than the tf32 tolerance."""
+    S = gen.rmat(11, 8, 2)
+    A, B = operands(S, 128)
+    res = pkg.sddmm(S, A, B, alpha=0.3, delta=1.1, block_size=16)
+    Pref = O.sddmm_cpu(S, A, B)
+    rel = np.abs(res["P"] - Pref) / np.maximum(np.abs(Pref), 1e-3)
+    assert rel.max() < 2e-5
+
+
+def test_linearity_and_idempotence_device_api(torch_mod):
+    """size-independent properties: P(2A, B) == 2 P(A, B) exactly (power-of-two scale), re-running is idempotent."""
+    torch = torch_mod
+    S = gen.bernoulli_mask(1024, 2048, 0.97, 8)
+    A, B = operands(S, 64)
+    ro, ci = _dev(torch, S.row_off), _dev(torch, S.col_idx)
+    R, ncl, _ = pkg.row_reorder_dev(ro, ci, S.M, S.N, 0.3, 16)
+    lay, _, _ = pkg.layout_build_dev(ro, ci, S.M, S.N, R, 0.3)
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    P1, _ = pkg.sddmm_gpu(dA, dB, lay)
+    P1 = P1.clone()
+    P2, _ = pkg.sddmm_gpu(dA * 2, dB, lay)
+    torch.cuda.synchronize()
+    assert torch.equal(P2[: S.nnz], 2 * P1[: S.nnz])
+    P3, _ = pkg.sddmm_gpu(dA, dB, lay)
+    torch.cuda.synchronize()
+    assert torch.equal(P3[: S.nnz], P1[: S.nnz])
+
+
+def test_sharded_layouts_cover_every_nonzero_once(torch_mod):
+    """row-panel shards (multi-GPU layer): the union of the shards' outputs == the single layout's."""
+    torch = torch_mod
+    S = gen.rmat(12, 8, 4)
+    A, B = operands(S, 32)
+    ro, ci = _dev(torch, S.row_off), _dev(torch, S.col_idx)
+    R, _, _ = pkg.row_reorder_dev(ro, ci, S.M, S.N, 0.3, 16)
+    cuts = pkg.shard_plan(S, R.cpu().numpy().view(np.uint32), 3)
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    full, _, _ = pkg.layout_build_dev(ro, ci, S.M, S.N, R, 0.3)
+    Pfull, _ = pkg.sddmm_gpu(dA, dB, full)
+    P = torch.full((S.nnz,), float("nan"), device="cuda")
+    for s in range(3):
+        lay, _, _ = pkg.layout_build_dev(ro, ci, S.M, S.N, R, 0.3, int(cuts[s]), int(cuts[s + 1]))
+        pkg.sddmm_gpu(dA, dB, lay, P)
+    torch.cuda.synchronize()
+    assert not torch.isnan(P).any()
+    assert O.check_data(Pfull[: S.nnz].cpu().numpy(), P.cpu().numpy()) == 0
+
+
+def test_medium_uniform_roundtrip(torch_mod):
+    """20000 x 20000 at 1% (config-2 class, scaled): permutation validity + values on a row sample."""
+    torch = torch_mod
+    S = gen.uniform_random(20000, 20000, 0.01, 2)
+    K = 128
+    A, B = operands(S, K)
+    ro, ci = _dev(torch, S.row_off), _dev(torch, S.col_idx)
+    R, ncl, ms = pkg.row_reorder_dev(ro, ci, S.M, S.N, 0.3, 0)
+    Rh = R.cpu().numpy().view(np.uint32)
+    lens = np.diff(S.row_off.astype(np.int64))
+    assert np.array_equal(np.sort(Rh), np.nonzero(lens)[0])
+    lay, _, _ = pkg.layout_build_dev(ro, ci, S.M, S.N, R, 0.3)
+    assert lay.info.numDenseValues + lay.info.numSparseValues == S.nnz
+    P, _ = pkg.sddmm_gpu(torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), lay)
+    torch.cuda.synchronize()
+    Ph = P[: S.nnz].cpu().numpy()
+    rows = np.random.default_rng(0).choice(S.M, 64, replace=False)
+    for r in rows:
+        b, e = int(S.row_off[r]), int(S.row_off[r + 1])
+        ref = (A[r][None, :] * B[S.col_idx[b:e]]).sum(1, dtype=np.float64)
+        assert np.all(np.abs(Ph[b:e] - ref) / np.maximum(np.abs(ref), 1e-3) < 1e-3)
+
+
+REF_DUMP = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_DUMP), reason="reference GPU binary not shipped")
+@pytest.mark.parametrize("name", ["blocks512_a07_d03", "rmat12_a03_d03", "w3_600x4800_a05_d03"])
+def test_against_live_reference_binary(name):
+    """Same input through the UNMODIFIED reference pipeline (oracle/_ref/ref_dump) and through ours."""
+    S, alpha, delta, _K = CASES[name]
+    K = 32  # the reference's K>32 kernels fault on sm_100
+    A, B = operands(S, K)
+    tmp = tempfile.mkdtemp()
+    case = os.path.join(tmp, "case.bin")
+    gen.write_case_bin(case, S, A, B)
+    p = subprocess.run([REF_DUMP, case, repr(alpha), repr(delta), tmp], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-500:]
+    ref = {k: np.fromfile(os.path.join(tmp, k + ".u32"), dtype=np.uint32) for k in ("reorderedRows",) + LAYOUT_KEYS + RPHM_KEYS}
+    Pref = np.fromfile(os.path.join(tmp, "P.f32"), dtype=np.float32)
+    bs = [int(l.split()[1]) for l in open(os.path.join(tmp, "meta.txt")) if l.startswith("block_size")][0]
+    res = pkg.sddmm(S, A, B, alpha=alpha, delta=delta, block_size=bs)
+    for k in ref:
+        assert np.array_equal(res[k], ref[k]), k
+    assert O.check_data(Pref, res["P"]) == 0

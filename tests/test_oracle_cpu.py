@@ -1,0 +1,187 @@
+"""CPU tests (-m "not gpu"): the oracle against the reference's golden vectors, host logic, C-ABI exports.
+
+Pins:
+  * tests/golden/ref_gpu/*.npz  -- arrays produced by the UNMODIFIED reference GPU pipeline on a B200
+    (tests/make_ref_goldens.py): row permutation for every case, full BSMR/RPHM arrays for small ones.
+  * oracle/_ref/libref_cpu.so   -- the reference's own colReordering_cpu / sddmm_cpu / loader / checkData,
+    compared live when the library is present (it is built from /root/reference by build()).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from cases import GOLDEN, gen, operands, pkg, small_cases
+from oracle import oracle as O
+
+REF_GPU = os.path.join(GOLDEN, "ref_gpu")
+
+
+def _golden_specs():
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    import make_ref_goldens as m
+    return {c[0]: c for c in m.cases(big=False)}
+
+
+SPECS = _golden_specs()
+
+
+@pytest.mark.parametrize("name", sorted(SPECS))
+def test_oracle_matches_reference_gpu_golden(name):
+    """oracle/bsmr_oracle.c reproduces the reference's reorderedRows (and, where stored, every BSMR/RPHM
+    array) bit for bit."""
+    path = os.path.join(REF_GPU, name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip("golden not generated yet")
+    _, S, K, alpha, delta, _ = SPECS[name]
+    g = np.load(path)
+    bs = int(g["block_size"])
+    rr = O.row_reorder(S, alpha, bs)
+    assert np.array_equal(rr["reorderedRows"], g["reorderedRows"])
+    assert rr["numClusters"] == int(g["num_clusters"])
+    if "denseCols" in g.files:
+        cr = O.col_reorder(S, g["reorderedRows"], delta)
+        for k in ("denseCols", "denseColOffsets", "sparseCols", "sparseColOffsets", "sparseValueOffsets"):
+            assert np.array_equal(cr[k], g[k]), k
+        rp = O.rphm_build(S, g["reorderedRows"], cr)
+        for k in ("blockOffsets", "blockValues", "sparseValues", "sparseRelativeRows", "sparseColIndices",
+                  "denseRowPanelIds", "denseColBlockIters", "sparseRowPanelIds", "sparseColBlockIters"):
+            assert np.array_equal(rp[k], g[k]), k
+
+
+def test_golden_summary_says_oracle_equals_reference():
+    """The on-box comparison recorded by make_ref_goldens.py: every array of every case equal."""
+    p = os.path.join(REF_GPU, "summary.json")
+    if not os.path.exists(p):
+        pytest.skip("no summary")
+    recs = json.load(open(p))
+    checked = 0
+    for r in recs:
+        eq = r.get("oracle_equals_reference")
+        if not eq:
+            continue
+        bad = [k for k, v in eq.items() if v is False]
+        assert not bad, (r["name"], bad)
+        checked += 1
+    assert checked >= 20
+
+
+needs_ref = pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref/libref_cpu.so not built")
+
+
+@needs_ref
+@pytest.mark.parametrize("delta", [0.0, 0.1, 0.3, 0.5, 0.7, 0.9, 1.1])
+def test_col_reorder_equals_reference_host_code(delta):
+    for S in (gen.uniform_random(512, 512, 0.1, 7), gen.rmat(11, 8, 3), gen.zipf_docs(100, 3000, 9000, 2),
+              gen.with_empty_rows(gen.bernoulli_mask(200, 333, 0.7, 4), 5)):
+        bs = 16
+        R = O.row_reorder(S, 0.3, bs)["reorderedRows"]
+        a, b = O.col_reorder(S, R, delta), O.ref_col_reorder(S, R, delta)
+        for k in ("denseCols", "denseColOffsets", "sparseCols", "sparseColOffsets", "sparseValueOffsets"):
+            assert np.array_equal(a[k], b[k]), (S.name, k)
+
+
+@needs_ref
+@pytest.mark.parametrize("K", [32, 64, 100])
+def test_sddmm_cpu_bitexact_with_reference(K):
+    S = gen.rmat(10, 8, 1)
+    A, B = operands(S, K)
+    assert np.array_equal(O.sddmm_cpu(S, A, B, threads=2), O.ref_sddmm_cpu(S, A, B))
+
+
+@needs_ref
+def test_check_data_equals_reference():
+    rng = np.random.default_rng(0)
+    a = rng.random(20000, dtype=np.float32) * 50
+    b = a * (1 + rng.normal(0, 7e-4, a.shape).astype(np.float32))
+    b[::97] += 2e-5
+    a[::101] = 0
+    assert O.check_data(a, b) == O.ref_check_data(a, b)
+    assert O.check_data(a, a) == 0
+
+
+@needs_ref
+@pytest.mark.parametrize("order", ["col", "rowrev"])
+def test_mtx_loader_equals_reference(tmp_path, order):
+    S = gen.with_empty_rows(gen.uniform_random(64, 80, 0.1, 3), 5)
+    p = str(tmp_path / "a.mtx")
+    gen.write_mtx(p, S, order=order)
+    rc, mine = O.load_mtx(p)
+    rc2, ref = O.ref_load_mtx(p)
+    assert rc == 0 and rc2 == 0
+    assert mine[0] == ref[0] and mine[1] == ref[1]
+    for x, y in zip(mine[2:], ref[2:]):
+        assert np.array_equal(x, y)
+    if order == "rowrev":  # file order inside a row is kept (src/Matrix.cpp:467)
+        r0 = mine[3][mine[2][1]:mine[2][2]]
+        assert np.all(np.diff(r0.astype(np.int64)) < 0) or r0.size < 2
+
+
+@needs_ref
+def test_mtx_loader_rejects_like_reference(tmp_path):
+    p = str(tmp_path / "dup.mtx")
+    open(p, "w").write("%%MatrixMarket\n3 3 3\n1 1 1\n2 2 1\n1 1 1\n")
+    assert O.load_mtx(p)[0] != 0 and O.ref_load_mtx(p)[0] != 0
+    p = str(tmp_path / "one.mtx")
+    open(p, "w").write("%%MatrixMarket\n3 3 1\n1 1 1\n")
+    assert O.load_mtx(p)[0] != 0 and O.ref_load_mtx(p)[0] != 0
+    p = str(tmp_path / "noval.mtx")
+    open(p, "w").write("%%MatrixMarket\n3 3 2\n1 2\n3 1\n")
+    rc, m = O.load_mtx(p)
+    rc2, r = O.ref_load_mtx(p)
+    assert rc == 0 and rc2 == 0 and np.array_equal(m[3], r[3]) and np.array_equal(m[4], r[4])
+
+
+def test_block_size_rule():
+    assert O.block_size(1500, 12419, 180e9) == 16
+    assert O.block_size(100000, 100000, 180e9) == 17       # SMEM term: ceil(400000/24576)
+    assert O.block_size(4194304, 4194304, 180e9) >= 683
+    assert O.nbpr(12419, 16) == 777 and O.cluster_blockdim(777) == 224
+    assert O.kept_warps(224).tolist() == [1, 1, 0, 1, 1, 0, 0]
+    assert O.kept_warps(96).tolist() == [1, 1, 0]
+    assert O.kept_warps(256).tolist() == [1] * 8
+
+
+def test_layout_invariants_from_reference_checkers():
+    """The invariants of check_rowReordering / check_colReordering / check_rphm (src/BSMR.cpp:444-824)."""
+    for name, (S, alpha, delta, K) in small_cases().items():
+        bs = O.block_size(S.M, S.N, 180e9)
+        R = O.row_reorder(S, alpha, bs)["reorderedRows"]
+        lens = np.diff(S.row_off.astype(np.int64))
+        assert np.array_equal(np.sort(R), np.nonzero(lens)[0]), name          # every non-empty row once
+        cr = O.col_reorder(S, R, delta)
+        rp = O.rphm_build(S, R, cr)
+        bv = rp["blockValues"]
+        used = np.concatenate([bv[bv != O.NULL_VALUE], rp["sparseValues"]])
+        assert np.array_equal(np.sort(used), np.arange(S.nnz)), name          # each nnz exactly once
+        assert np.all(cr["denseColOffsets"] % 16 == 0)
+
+
+def test_c_abi_library_loads_and_exports_every_declared_symbol():
+    syms = pkg.declared_symbols()
+    assert len(syms) >= 18 and "sddmm_run_dev" in syms and "bsmr_row_reorder_dev" in syms
+    L = pkg.lib()  # raises ImportError if the .so or any symbol is missing
+    assert L.sddmm_b200_abi_version() == 1
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    S = gen.uniform_random(64, 64, 0.1, 1)
+    A, B = operands(S, 32)
+    with pytest.raises(pkg.SddmmError):
+        pkg.sddmm(S, A, B)
+
+
+def test_shard_plan_balances_nnz():
+    S = gen.rmat(12, 8, 4)
+    R = np.nonzero(np.diff(S.row_off.astype(np.int64)))[0].astype(np.uint32)
+    cuts = pkg.shard_plan(S, R, 4)
+    P = (len(R) + 15) // 16
+    assert cuts[0] == 0 and cuts[-1] == P and np.all(np.diff(cuts.astype(np.int64)) >= 0)
+    lens = np.diff(S.row_off.astype(np.int64))[R]
+    per = [lens[cuts[i] * 16: cuts[i + 1] * 16].sum() for i in range(4)]
+    assert max(per) - min(per) <= 0.25 * S.nnz / 4 + lens.max() * 16
