@@ -246,12 +246,16 @@ int sddmm_run_host(const bsmr_layout* L, uint32_t K, const float* h_A, const flo
   cudaStream_t s = streams().dense;
   Timer t(s);
   t.start();
-  DevBuf<float> dA((size_t)I.M * K), dB((size_t)I.N * K), dP(I.nnz ? I.nnz : 1);
-  SB_CUDA(cudaMemcpyAsync(dA.get(), h_A, (size_t)I.M * K * 4, cudaMemcpyHostToDevice, s));
-  SB_CUDA(cudaMemcpyAsync(dB.get(), h_B, (size_t)I.N * K * 4, cudaMemcpyHostToDevice, s));
-  SB_CUDA(cudaMemsetAsync(dP.get(), 0, (size_t)I.nnz * 4, s));  // dev::vector<float> P(nnz, 0)  sddmmKernel.cu:2525
-  run_once(L, K, dA.get(), dB.get(), dP.get(), s);
-  SB_CUDA(cudaMemcpyAsync(h_P, dP.get(), (size_t)I.nnz * 4, cudaMemcpyDeviceToHost, s));
+  const size_t nA = (size_t)I.M * K, nB = (size_t)I.N * K, nP = I.nnz ? I.nnz : 1;
+  if (L->wsA.size() < nA) L->wsA.alloc(nA);
+  if (L->wsB.size() < nB) L->wsB.alloc(nB);
+  if (L->wsP.size() < nP) L->wsP.alloc(nP);
+  float *dA = L->wsA.get(), *dB = L->wsB.get(), *dP = L->wsP.get();
+  SB_CUDA(cudaMemcpyAsync(dA, h_A, nA * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(dB, h_B, nB * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemsetAsync(dP, 0, (size_t)I.nnz * 4, s));  // dev::vector<float> P(nnz, 0)  sddmmKernel.cu:2525
+  run_once(L, K, dA, dB, dP, s);
+  SB_CUDA(cudaMemcpyAsync(h_P, dP, (size_t)I.nnz * 4, cudaMemcpyDeviceToHost, s));
   const float el = t.stop();
   if (msTotal) *msTotal = el;
   API_END

@@ -10,6 +10,9 @@ struct bsmr_layout {
   sb::DevBuf<uint2> sparseWork;  // (local panel, first residual entry of the chunk inside the panel)
   sb::u32 numDenseWork = 0, numSparseWork = 0;
   int device = 0;
+  // device staging buffers of the host-buffer entry point (sddmm_run_host), grown on demand and kept
+  // so that repeated calls do not pay cudaMalloc/cudaFree
+  mutable sb::DevBuf<float> wsA, wsB, wsP;
 };
 
 namespace sb {
