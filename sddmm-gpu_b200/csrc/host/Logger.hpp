@@ -1,0 +1,62 @@
+// Logger.hpp -- the `[key : value]` report of the reference (include/Logger.hpp:122-187) so that
+// scripts/analyze_results.cpp keeps parsing it; extra B200 keys are appended at the end.
+#pragma once
+#include <cmath>
+#include <iomanip>
+#include <iostream>
+#include <string>
+
+#include "Matrix.hpp"
+#include "Options.hpp"
+
+struct Logger {
+  std::string inputFile_, gpu_ = "unknown", buildType_ = "Release";
+  size_t M_ = 0, N_ = 0, K_ = 0, NNZ_ = 0;
+  float sparsity_ = 0.f;
+  int numRowPanels_ = 0, numDenseBlock_ = 0, numDenseThreadBlocks_ = 0, numSparseThreadBlocks_ = 0;
+  unsigned numDenseData_ = 0, numSparseData_ = 0;
+  int numITER_ = 10, numClusters_ = 1;
+  float alpha_ = 0.3f, delta_ = 0.3f, averageDensity_ = 0.f;
+  float sddmmTime_ = 0.f, denseTime_ = 0.f, sparseTime_ = 0.f, rowReorderingTime_ = 0.f, colReorderingTime_ = 0.f,
+        reorderingTime_ = 0.f, rphmTime_ = 0.f;
+  unsigned blockSize_ = 0;
+
+  void getInformation(const Options& o) {
+    inputFile_ = o.inputFile(); K_ = o.K(); numITER_ = o.numIterations();
+    alpha_ = o.similarityThresholdAlpha(); delta_ = o.blockDensityThresholdDelta();
+  }
+  void getInformation(const sparseMatrix::DataBase& m) { M_ = m.row(); N_ = m.col(); NNZ_ = m.nnz(); sparsity_ = m.getSparsity(); }
+  template <typename T>
+  void getInformation(const Matrix<T>& A, const Matrix<T>&) { K_ = A.col(); }
+
+  void printLogInformation(std::ostream& out = std::cout) const {
+    out << "[File : " << inputFile_ << "]\n";
+    out << "[Build type : " << buildType_ << "]\n";
+    out << "[Device : " << gpu_ << "]\n";
+    out << "[WMMA_M : 16], [WMMA_N : 16], [WMMA_K : 8]\n";
+    out << "[K : " << K_ << "], [M : " << M_ << "], [N : " << N_ << "], [NNZ : " << NNZ_ << "], ";
+    out << "[sparsity : " << std::fixed << std::setprecision(2) << (std::floor(sparsity_ * 10000) / 100.0) << "%]\n";
+    out << "[matrixA type : f]\n[matrixB type : f]\n[matrixC type : f]\n";
+    out << "[matrixA storageOrder : row_major]\n[matrixB storageOrder : col_major]\n";
+    out << "[Num iterations : " << numITER_ << "]\n";
+    out << "[NumRowPanel : " << numRowPanels_ << "]\n";
+    out << "[bsmr_alpha : " << alpha_ << "]\n[bsmr_delta : " << delta_ << "]\n";
+    out << "[bsmr_numClusters : " << numClusters_ << "]\n";
+    out << "[bsmr_numDenseBlock : " << numDenseBlock_ << "]\n";
+    out << "[bsmr_averageDensity : " << averageDensity_ << "]\n";
+    out << "[bsmr_rowReordering : " << rowReorderingTime_ << "]\n";
+    out << "[bsmr_colReordering : " << colReorderingTime_ << "]\n";
+    out << "[bsmr_reordering : " << reorderingTime_ << "]\n";
+    out << "[bsmr_numDenseThreadBlocks : " << numDenseThreadBlocks_ << "]\n";
+    out << "[bsmr_numSparseThreadBlocks : " << numSparseThreadBlocks_ << "]\n";
+    out << "[bsmr_numDenseData : " << numDenseData_ << "]\n";
+    out << "[bsmr_numSparseData : " << numSparseData_ << "]\n";
+    const double flops = 2.0 * static_cast<double>(NNZ_) * static_cast<double>(K_);
+    out << "[bsmr_gflops : " << (flops / (sddmmTime_ * 1e6)) << "]\n";   // Logger.hpp:178-180
+    out << "[bsmr_sddmm : " << sddmmTime_ << "]\n";
+    out << "[b200_block_size : " << blockSize_ << "]\n";
+    out << "[b200_rphm_build : " << rphmTime_ << "]\n";
+    out << "[b200_dense_kernel_ms : " << denseTime_ << "]\n";
+    out << "[b200_residual_kernel_ms : " << sparseTime_ << "]\n";
+  }
+};

@@ -1,0 +1,194 @@
+// Matrix.cpp -- loaders / generators of the host data model (see Matrix.hpp).
+// The .mtx loader reads the whole file once and parses numbers in place (the reference goes line by
+// line through std::stod and a std::set, O(nnz log nnz) with large constants);
+// duplicate detection is a sort of (row, col) keys.  Accept/reject behaviour and the resulting CSR
+// (row-only stable order) are those of src/Matrix.cpp:398-480.
+#include "Matrix.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <random>
+
+template <typename T>
+void Matrix<T>::makeData(uint64_t seed) {
+  std::mt19937 gen(static_cast<uint32_t>(seed));
+  std::uniform_real_distribution<float> dist(0.0f, 2.0f);
+  for (size_t i = 0; i < values_.size(); ++i) values_[i] = static_cast<T>(dist(gen));
+}
+template class Matrix<float>;
+
+namespace {
+
+bool read_file(const std::string& path, std::vector<char>& buf) {
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) return false;
+  std::fseek(f, 0, SEEK_END);
+  const long n = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  buf.resize(static_cast<size_t>(n) + 1);
+  const size_t got = std::fread(buf.data(), 1, static_cast<size_t>(n), f);
+  std::fclose(f);
+  buf[got] = 0;
+  buf.resize(got + 1);
+  return true;
+}
+
+inline const char* skip_blank(const char* p) {
+  while (*p == ' ' || *p == '\t' || *p == '\r') ++p;
+  return p;
+}
+inline const char* next_line(const char* p) {
+  while (*p && *p != '\n') ++p;
+  return *p ? p + 1 : p;
+}
+inline bool at_eol(const char* p) { return *p == '\n' || *p == 0; }
+
+std::string suffix_of(const std::string& f) {
+  const size_t dot = f.find_last_of('.');
+  return dot == std::string::npos ? "" : f.substr(dot);
+}
+
+}  // namespace
+
+namespace sparseMatrix {
+
+template <typename T>
+bool CSR<T>::initializeFromMatrixFile(const std::string& file) {
+  const std::string s = suffix_of(file);
+  if (s == ".mtx" || s == ".mmio") return initializeFromMtxFile(file);
+  if (s == ".smtx") return initializeFromSmtxFile(file);
+  std::cerr << "Error, file format is not supported : " << file << std::endl;
+  return false;
+}
+
+template <typename T>
+bool CSR<T>::initializeFromMtxFile(const std::string& file) {
+  std::vector<char> buf;
+  if (!read_file(file, buf)) {
+    std::cerr << "Error, file cannot be opened : " << file << std::endl;
+    return false;
+  }
+  std::cout << "sparseMatrix::CSR initialize from file : " << file << std::endl;
+  const char* p = buf.data();
+  while (*p == '%') p = next_line(p);  // skip comments
+  char* e = nullptr;
+  p = skip_blank(p);
+  row_ = static_cast<UIN>(std::strtol(p, &e, 10)); p = skip_blank(e);
+  col_ = static_cast<UIN>(std::strtol(p, &e, 10)); p = skip_blank(e);
+  nnz_ = at_eol(p) ? 0u : static_cast<UIN>(std::strtod(p, &e));
+  p = next_line(p);
+  std::vector<UIN> ri(nnz_), ci(nnz_);
+  std::vector<T> va(nnz_);
+  UIN idx = 0;
+  while (*p) {
+    const char* q = skip_blank(p);
+    if (at_eol(q)) { p = next_line(p); continue; }  // empty line
+    const long r = std::strtol(q, &e, 10); q = skip_blank(e);
+    const long c = std::strtol(q, &e, 10); q = skip_blank(e);
+    T v = static_cast<T>(0);
+    if (!at_eol(q)) v = static_cast<T>(std::strtod(q, &e));
+    if (idx >= nnz_) {
+      std::cerr << "Error, file " << file << " too many elements, exceeding the number nnz!" << std::endl;
+      return false;
+    }
+    ri[idx] = static_cast<UIN>(r - 1);
+    ci[idx] = static_cast<UIN>(c - 1);
+    va[idx] = v;
+    ++idx;
+    p = next_line(p);
+  }
+  if (idx < nnz_) {
+    std::cerr << "Error, file " << file << " elements is not enough!" << std::endl;
+    return false;
+  }
+  std::vector<uint64_t> keys(nnz_);
+  for (UIN i = 0; i < nnz_; ++i) {
+    if (ri[i] >= row_ || ci[i] >= col_) {
+      std::cerr << "Error, file " << file << " row or col is too big!" << std::endl;
+      return false;
+    }
+    keys[i] = (static_cast<uint64_t>(ri[i]) << 32) | ci[i];
+  }
+  std::sort(keys.begin(), keys.end());
+  if (std::adjacent_find(keys.begin(), keys.end()) != keys.end()) {
+    std::cerr << "Error, matrix has duplicate data!" << std::endl;
+    return false;
+  }
+  if (nnz_ <= 1) {
+    std::cerr << "Warning, file " << file << " nnz is 1, this is not a valid matrix!" << std::endl;
+    return false;
+  }
+  // stable by row only: columns keep FILE order inside a row (src/Matrix.cpp:467)
+  rowOffsets_.assign(static_cast<size_t>(row_) + 1, 0);
+  for (UIN i = 0; i < nnz_; ++i) rowOffsets_[ri[i] + 1]++;
+  for (UIN r = 0; r < row_; ++r) rowOffsets_[r + 1] += rowOffsets_[r];
+  std::vector<UIN> pos(rowOffsets_.begin(), rowOffsets_.end() - 1);
+  colIndices_.resize(nnz_);
+  values_.resize(nnz_);
+  for (UIN i = 0; i < nnz_; ++i) {
+    const UIN d = pos[ri[i]]++;
+    colIndices_[d] = ci[i];
+    values_[d] = va[i];
+  }
+  return true;
+}
+
+template <typename T>
+bool CSR<T>::initializeFromSmtxFile(const std::string& file) {
+  std::vector<char> buf;
+  if (!read_file(file, buf)) {
+    std::cerr << "Error, file cannot be opened : " << file << std::endl;
+    return false;
+  }
+  const char* p = buf.data();
+  while (*p == '%') p = next_line(p);
+  auto next_int = [&](const char*& q) -> long {
+    while (*q == ' ' || *q == '\t' || *q == '\r' || *q == ',') ++q;
+    char* e = nullptr;
+    const long v = std::strtol(q, &e, 10);
+    q = e;
+    return v;
+  };
+  row_ = static_cast<UIN>(next_int(p));
+  col_ = static_cast<UIN>(next_int(p));
+  nnz_ = static_cast<UIN>(next_int(p));
+  if (nnz_ == 0) {
+    std::cerr << "Error, file " << file << " nnz is 0!" << std::endl;
+    return false;
+  }
+  p = next_line(p);
+  rowOffsets_.resize(static_cast<size_t>(row_) + 1);
+  for (size_t i = 0; i < rowOffsets_.size(); ++i) rowOffsets_[i] = static_cast<UIN>(next_int(p));
+  p = next_line(p);
+  colIndices_.resize(nnz_);
+  values_.assign(nnz_, static_cast<T>(1));
+  for (UIN i = 0; i < nnz_; ++i) colIndices_[i] = static_cast<UIN>(next_int(p));
+  for (UIN r = 0; r < row_; ++r) {  // duplicate check per row
+    std::vector<UIN> c(colIndices_.begin() + rowOffsets_[r], colIndices_.begin() + rowOffsets_[r + 1]);
+    std::sort(c.begin(), c.end());
+    if (std::adjacent_find(c.begin(), c.end()) != c.end()) {
+      std::cerr << "Error, matrix has duplicate data!" << std::endl;
+      return false;
+    }
+  }
+  return true;
+}
+
+template <typename T>
+bool CSR<T>::outputToMarketMatrixFile(const std::string& fileName) const {
+  std::ofstream out(fileName);
+  if (!out) return false;
+  out << "%%MatrixMarket matrix coordinate real general\n" << row_ << " " << col_ << " " << nnz_ << "\n";
+  for (UIN r = 0; r < row_; ++r)
+    for (UIN i = rowOffsets_[r]; i < rowOffsets_[r + 1]; ++i)
+      out << (r + 1) << " " << (colIndices_[i] + 1) << " " << values_[i] << "\n";
+  return true;
+}
+
+template class CSR<float>;
+
+}  // namespace sparseMatrix

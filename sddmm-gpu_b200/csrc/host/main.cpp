@@ -1,0 +1,45 @@
+// main.cpp -- the `BSMR-sddmm` command line of the reference (src/main.cu:6-42) on the B200 engine:
+//   BSMR-sddmm -f file -k K -a alpha -d delta [-t 1 -l logdir]   |   BSMR-sddmm file K
+// Adds: -b block_size, -g free-memory bytes for the block-size rule, -i iterations, and `-c 1` to run
+// the host checker (the reference's compile-time VALIDATE switch, src/sddmm.cu:7).
+#include <cuda_runtime_api.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "sddmm.hpp"
+
+int main(int argc, char* argv[]) {
+  Options options(argc, argv);
+  bool validate = false;
+  for (int i = 1; i + 1 < argc; ++i)
+    if (!std::strcmp(argv[i], "-c") || !std::strcmp(argv[i], "-C")) validate = std::atoi(argv[i + 1]) != 0;
+
+  sparseMatrix::CSR<float> matrixS;
+  if (!matrixS.initializeFromMatrixFile(options.inputFile())) {
+    std::fprintf(stderr, "Error, matrix S initialize failed.\n");
+    return -1;
+  }
+  if (options.testMode()) {
+    sddmm_testMode(options, matrixS);
+    return 0;
+  }
+  const size_t K = options.K();
+  Matrix<float> matrixA(matrixS.row(), static_cast<UIN>(K), MatrixStorageOrder::row_major);
+  matrixA.makeData(1);
+  Matrix<float> matrixB(static_cast<UIN>(K), matrixS.col(), MatrixStorageOrder::col_major);
+  matrixB.makeData(2);
+
+  Logger logger;
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, 0) == cudaSuccess) logger.gpu_ = prop.name;
+  logger.getInformation(options);
+  logger.getInformation(matrixS);
+  logger.getInformation(matrixA, matrixB);
+
+  sparseMatrix::CSR<float> matrixP(matrixS);
+  sddmm(options, matrixA, matrixB, matrixP, logger);
+  if (validate) checkSddmm(matrixA, matrixB, matrixS, matrixP);
+  logger.printLogInformation();
+  return 0;
+}

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) k_panel_split(const u32* __restrict__ sor
                                                      u32 P, u32 T, u32* __restrict__ nd, u32* __restrict__ nsCols,
                                                      u32* __restrict__ nnzSparse, u32* __restrict__ nBlk,
                                                      u32* __restrict__ denseTB, u32* __restrict__ sparseTB,
-                                                     u32* __restrict__ myDenseWork, u32* __restrict__ mySparseWork,
+                                                     u32* __restrict__ myDenseWork, u32* __restrict__ mySparseWork, u32 kSparseChunk,
                                                      u32* __restrict__ maxima /* [0]=maxDenseBlk [1]=maxSparseTB [2]=denseNnz */) {
   const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const u32 nw = (gridDim.x * blockDim.x) >> 5;
@@ -214,7 +214,7 @@ __global__ void k_write_worklists(const u32* __restrict__ dOff, const u32* __res
                                   const u32* __restrict__ stbOff, const u32* __restrict__ myDOff,
                                   const u32* __restrict__ mySOff, u32 P, u32* __restrict__ dIds,
                                   u32* __restrict__ dIters, u32* __restrict__ sIds, u32* __restrict__ sIters,
-                                  uint2* __restrict__ myDense, uint2* __restrict__ mySparse) {
+                                  uint2* __restrict__ myDense, uint2* __restrict__ mySparse, u32 kSparseChunk) {
   const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const u32 nw = (gridDim.x * blockDim.x) >> 5;
   for (u32 p = gw; p < P; p += nw) {
@@ -232,6 +232,19 @@ __global__ void k_write_worklists(const u32* __restrict__ dOff, const u32* __res
     for (u32 i = lane; i < md; i += 32) myDense[myDOff[p] + i] = make_uint2(p, i * kDenseGroupBlocks);
     for (u32 i = lane; i < ms; i += 32) mySparse[mySOff[p] + i] = make_uint2(p, i * kSparseChunk);
   }
+}
+
+// chunk-major ordering of the residual work list: residual entries of a panel are ordered by
+// (count desc, col asc), i.e. chunk c of every panel covers about the same column range, so running
+// all panels' chunk c together keeps the active slice of B small enough to stay L2-resident.
+__global__ void k_work_keys(const uint2* __restrict__ work, u32 n, u32 kSparseChunk, u32* __restrict__ keys) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    keys[i] = work[i].y / kSparseChunk;
+}
+__global__ void k_gather_work(const uint2* __restrict__ in, const u32* __restrict__ idx, u32 n,
+                              uint2* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = in[idx[i]];
 }
 
 u32 read_u32(const u32* d, cudaStream_t s) {
@@ -266,6 +279,11 @@ bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u
   auto* L = new bsmr_layout();
   try {
     SB_CUDA(cudaGetDevice(&L->device));
+    L->sparseChunk = kSparseChunkDefault;
+    if (const char* e = getenv("SDDMM_B200_CHUNK")) {
+      const long v = atol(e);
+      if (v >= 32 && v <= 65536) L->sparseChunk = (u32)v;
+    }
     bsmr_layout_info& I = L->info;
     I.M = M; I.N = N; I.nnz = nnz; I.numRows = nR; I.numRowPanels = P; I.panelBegin = panelBegin;
     auto A = [&](bsmr_array_id id) -> DevBuf<u32>& { return L->arr[id]; };
@@ -341,7 +359,7 @@ bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u
     SB_CUDA(cudaMemsetAsync(maxima.get(), 0, 16, s));
     k_panel_split<<<grid_for((size_t)P * 32), 256, 0, s>>>(sortedKey, pStart.get(), P, T, nd.get(), nsCols.get(),
                                                           nnzSparse.get(), nBlk.get(), denseTB.get(), sparseTB.get(),
-                                                          myDW.get(), mySW.get(), maxima.get());
+                                                          myDW.get(), mySW.get(), L->sparseChunk, maxima.get());
     SB_LAUNCH_CHECK();
 
     // ---- 5. offsets
@@ -409,8 +427,21 @@ bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u
         A(BSMR_DENSE_COL_OFFSETS).get(), nBlk.get(), nnzSparse.get(), dtbOff.get(), stbOff.get(), myDOff.get(),
         mySOff.get(), P, A(RPHM_DENSE_ROW_PANEL_IDS).get(), A(RPHM_DENSE_COL_BLOCK_ITERS).get(),
         A(RPHM_SPARSE_ROW_PANEL_IDS).get(), A(RPHM_SPARSE_COL_BLOCK_ITERS).get(), L->denseWork.get(),
-        L->sparseWork.get());
+        L->sparseWork.get(), L->sparseChunk);
     SB_LAUNCH_CHECK();
+    if (L->numSparseWork > 1) {
+      const u32 nw = L->numSparseWork;
+      DevBuf<u32> kA(nw), kB(nw), iA(nw), iB(nw);
+      DevBuf<uint2> sorted(nw);
+      k_work_keys<<<grid_for(nw), 256, 0, s>>>(L->sparseWork.get(), nw, L->sparseChunk, kA.get());
+      SB_LAUNCH_CHECK();
+      iota<u32>(iA.get(), nw, 0u, s);
+      const int ws = radix_sort_pairs<u32>(kA.get(), kB.get(), iA.get(), iB.get(), nw, 0, 24, s);
+      k_gather_work<<<grid_for(nw), 256, 0, s>>>(L->sparseWork.get(), ws ? iB.get() : iA.get(), nw, sorted.get());
+      SB_LAUNCH_CHECK();
+      SB_CUDA(cudaStreamSynchronize(s));
+      L->sparseWork = std::move(sorted);
+    }
     u32 hmax[4];
     SB_CUDA(cudaMemcpyAsync(hmax, maxima.get(), 16, cudaMemcpyDeviceToHost, s));
     const float rMs = tR.stop();

@@ -9,6 +9,7 @@ struct bsmr_layout {
   sb::DevBuf<uint2> denseWork;   // (local panel, first dense block of the group inside the panel)
   sb::DevBuf<uint2> sparseWork;  // (local panel, first residual entry of the chunk inside the panel)
   sb::u32 numDenseWork = 0, numSparseWork = 0;
+  sb::u32 sparseChunk = 1024;  // residual entries per sparse work item
   int device = 0;
   // device staging buffers of the host-buffer entry point (sddmm_run_host), grown on demand and kept
   // so that repeated calls do not pay cudaMalloc/cudaFree
@@ -18,7 +19,7 @@ struct bsmr_layout {
 namespace sb {
 
 constexpr u32 kDenseGroupBlocks = 8;   // 8 x 16 = 128 gathered B columns per tcgen05 tile (MMA M)
-constexpr u32 kSparseChunk = 1024;     // residual entries per CTA work item
+constexpr u32 kSparseChunkDefault = 2048;  // residual entries per CTA work item (env SDDMM_B200_CHUNK overrides)
 
 bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32 nnz,
                               const u32* d_reorderedRows, u32 numRows, float delta, u32 panelBegin, u32 panelEnd,

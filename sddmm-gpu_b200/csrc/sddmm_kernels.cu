@@ -30,11 +30,18 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
   return v;
 }
 
+template <bool kL1>
+__device__ __forceinline__ float4 ld_b(const float4* p) {
+  if (kL1) return __ldg(p);
+  return ldg_nc_f4(p);
+}
+
+template <bool kL1>
 static __global__ void __launch_bounds__(kResThreads)
 k_sddmm_residual(u32 M, u32 K4, const float4* __restrict__ A4, const float4* __restrict__ B4,
                  const u32* __restrict__ R, u32 nR, const u32* __restrict__ vOff, const u32* __restrict__ sVals,
                  const u32* __restrict__ sRows, const u32* __restrict__ sCols, const uint2* __restrict__ work,
-                 float* __restrict__ P) {
+                 u32 kSparseChunk, float* __restrict__ P) {
   extern __shared__ float4 sA[];  // 16 rows x K4 float4
   const uint2 w = work[blockIdx.x];
   const u32 p = w.x;
@@ -64,8 +71,8 @@ k_sddmm_residual(u32 M, u32 K4, const float4* __restrict__ A4, const float4* __r
     float acc0 = 0.f, acc1 = 0.f;
     u32 c = gl;
     for (; c + kResLanes < K4; c += 2 * kResLanes) {
-      const float4 b0 = ldg_nc_f4(b + c);
-      const float4 b1 = ldg_nc_f4(b + c + kResLanes);
+      const float4 b0 = ld_b<kL1>(b + c);
+      const float4 b1 = ld_b<kL1>(b + c + kResLanes);
       const float4 a0 = a[c];
       const float4 a1 = a[c + kResLanes];
       acc0 = fmaf(a0.x, b0.x, acc0); acc0 = fmaf(a0.y, b0.y, acc0);
@@ -74,7 +81,7 @@ k_sddmm_residual(u32 M, u32 K4, const float4* __restrict__ A4, const float4* __r
       acc1 = fmaf(a1.z, b1.z, acc1); acc1 = fmaf(a1.w, b1.w, acc1);
     }
     if (c < K4) {
-      const float4 b0 = ldg_nc_f4(b + c);
+      const float4 b0 = ld_b<kL1>(b + c);
       const float4 a0 = a[c];
       acc0 = fmaf(a0.x, b0.x, acc0); acc0 = fmaf(a0.y, b0.y, acc0);
       acc0 = fmaf(a0.z, b0.z, acc0); acc0 = fmaf(a0.w, b0.w, acc0);
@@ -298,12 +305,13 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
     const u32 K4 = K / 4;
     const size_t smem = (size_t)16 * K * sizeof(float);
     if (smem > 200 * 1024) fail(SDDMM_E_UNSUPPORTED, "K=%u too large for the residual kernel's A tile", K);
-    if (smem > 48 * 1024)
-      SB_CUDA(cudaFuncSetAttribute(k_sddmm_residual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_sddmm_residual<<<L->numSparseWork, kResThreads, smem, sparseStream>>>(
+    static const bool useL1 = [] { const char* e = getenv("SDDMM_B200_L1"); return !e || atoi(e) != 0; }();
+    auto kern = useL1 ? k_sddmm_residual<true> : k_sddmm_residual<false>;
+    if (smem > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<L->numSparseWork, kResThreads, smem, sparseStream>>>(
         I.M, K4, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB), arr(BSMR_REORDERED_ROWS),
         I.numRows, arr(BSMR_SPARSE_VALUE_OFFSETS), arr(RPHM_SPARSE_VALUES), arr(RPHM_SPARSE_RELATIVE_ROWS),
-        arr(RPHM_SPARSE_COL_INDICES), L->sparseWork.get(), dP);
+        arr(RPHM_SPARSE_COL_INDICES), L->sparseWork.get(), L->sparseChunk, dP);
     SB_LAUNCH_CHECK();
   }
 }

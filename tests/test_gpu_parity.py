@@ -228,3 +228,34 @@ def test_against_live_reference_binary(name):
     for k in ref:
         assert np.array_equal(res[k], ref[k]), k
     assert O.check_data(Pref, res["P"]) == 0
+
+
+def test_cli_binary_matches_reference_contract(tmp_path):
+    """BSMR-sddmm -f file -k K -a alpha -d delta (src/main.cu:6-42, include/Options.hpp): runs the C++
+    host mirror end to end, validates with the host checker and prints the reference's [key : value] log."""
+    exe = os.path.join(ROOT, "sddmm-gpu_b200", "BSMR-sddmm")
+    assert os.access(exe, os.X_OK), "CLI not built"
+    S = gen.block_structured(512, 768, 6, 96, 0.8, seed=11, noise=0.004)
+    mtx = str(tmp_path / "blocks.mtx")
+    gen.write_mtx(mtx, S, order="col")
+    p = subprocess.run([exe, "-f", mtx, "-k", "64", "-a", "0.3", "-d", "0.3", "-c", "1"], capture_output=True,
+                       text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-400:]
+    out = p.stdout
+    assert "Pass! Result validates successfully." in out
+    kv = dict(l.strip("[]").split(" : ", 1) for l in out.replace("], [", "]\n[").splitlines() if " : " in l and l.startswith("["))
+    assert int(kv["NNZ"]) == S.nnz and int(kv["K"]) == 64
+    rr = O.row_reorder(S, 0.3, 16)
+    cr = O.col_reorder(S, rr["reorderedRows"], 0.3)
+    assert int(kv["NumRowPanel"]) == cr["numRowPanels"]
+    assert int(kv["bsmr_numDenseBlock"]) == int(cr["denseColOffsets"][-1]) // 16
+    assert int(kv["bsmr_numSparseData"]) == int(cr["sparseValueOffsets"][-1])
+    assert float(kv["bsmr_gflops"]) > 0
+    # positional form: prog file K
+    p = subprocess.run([exe, mtx, "32"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "[K : 32]" in p.stdout
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+    g.smoke()
