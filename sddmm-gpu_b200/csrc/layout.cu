@@ -247,6 +247,64 @@ __global__ void k_gather_work(const uint2* __restrict__ in, const u32* __restric
     out[i] = in[idx[i]];
 }
 
+
+// ---- super-panel residual layout (K7b) -----------------------------------------------------------
+// one warp per panel: key = (superPanel | col | rowInSuperPanel), payload = residual entry id
+__global__ void __launch_bounds__(256) k_sp_keys(const u32* __restrict__ vOff, const u32* __restrict__ sCols,
+                                                 const u32* __restrict__ sRows, u32 P, u32 G, int rowBits,
+                                                 int colBits, u64* __restrict__ keys, u32* __restrict__ vals) {
+  const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const u32 nw = (gridDim.x * blockDim.x) >> 5;
+  for (u32 p = gw; p < P; p += nw) {
+    const u32 b = vOff[p], e = vOff[p + 1];
+    const u64 hi = (u64)(p / G) << (rowBits + colBits);
+    const u32 rbase = (p % G) * 16u;
+    for (u32 i = b + lane; i < e; i += 32) {
+      keys[i] = hi | ((u64)sCols[i] << rowBits) | (rbase + sRows[i]);
+      vals[i] = i;
+    }
+  }
+}
+__global__ void k_sp_unpack(const u64* __restrict__ keys, const u32* __restrict__ vals,
+                            const u32* __restrict__ sVals, size_t n, int rowBits, int colBits,
+                            u32* __restrict__ col, unsigned short* __restrict__ row, u32* __restrict__ idx,
+                            u32* __restrict__ numRuns) {
+  const u64 colMask = (((u64)1) << colBits) - 1, rowMask = (((u64)1) << rowBits) - 1;
+  u32 heads = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const u64 k = keys[i];
+    col[i] = (u32)((k >> rowBits) & colMask);
+    row[i] = (unsigned short)(k & rowMask);
+    idx[i] = sVals[vals[i]];
+    heads += (i == 0 || (k >> rowBits) != (keys[i - 1] >> rowBits)) ? 1u : 0u;
+  }
+  heads = __reduce_add_sync(0xffffffffu, heads);
+  if ((threadIdx.x & 31) == 0 && heads) atomicAdd(numRuns, heads);
+}
+__global__ void k_sp_offsets(const u32* __restrict__ vOff, u32 P, u32 G, u32 numSp, u32 segLen,
+                             u32* __restrict__ off, u32* __restrict__ segCnt) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i <= numSp; i += (size_t)gridDim.x * blockDim.x) {
+    const u32 p = (u32)i * G < P ? (u32)i * G : P;
+    off[i] = vOff[p];
+    if (i < numSp) {
+      const u32 p1 = ((u32)i + 1) * G < P ? ((u32)i + 1) * G : P;
+      segCnt[i] = (vOff[p1] - vOff[p] + segLen - 1) / segLen;
+    }
+  }
+}
+__global__ void k_sp_work(const u32* __restrict__ segOff, u32 numSp, u32 segLen, uint2* __restrict__ work,
+                          u32* __restrict__ keys) {
+  const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const u32 nw = (gridDim.x * blockDim.x) >> 5;
+  for (u32 sp = gw; sp < numSp; sp += nw) {
+    const u32 b = segOff[sp], n = segOff[sp + 1] - b;
+    for (u32 j = lane; j < n; j += 32) {
+      work[b + j] = make_uint2(sp, j * segLen);
+      keys[b + j] = j;
+    }
+  }
+}
+
 u32 read_u32(const u32* d, cudaStream_t s) {
   u32 h = 0;
   SB_CUDA(cudaMemcpyAsync(&h, d, 4, cudaMemcpyDeviceToHost, s));
@@ -460,6 +518,73 @@ bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u
     delete L;
     throw;
   }
+}
+
+const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStream_t s) {
+  if (L->sp && L->sp->G == G) return L->sp.get();
+  const bsmr_layout_info& I = L->info;
+  auto sp = std::make_unique<SuperPanelLayout>();
+  sp->G = G;
+  sp->rows = G * kPanel;
+  const u32 P = I.numRowPanels;
+  sp->numSp = (P + G - 1) / G;
+  sp->numEntries = I.numSparseValues;
+  const u32 n = I.numSparseValues;
+  if (n == 0 || P == 0) {
+    sp->numWork = 0;
+    L->sp = std::move(sp);
+    return L->sp.get();
+  }
+  const int rowBits = bits_for(sp->rows - 1), colBits = bits_for(I.N), spBits = bits_for(sp->numSp);
+  const u32* vOff = L->arr[BSMR_SPARSE_VALUE_OFFSETS].get();
+  DevBuf<u64> kA(n), kB(n);
+  DevBuf<u32> vA(n), vB(n);
+  k_sp_keys<<<grid_for((size_t)P * 32), 256, 0, s>>>(vOff, L->arr[RPHM_SPARSE_COL_INDICES].get(),
+                                                    L->arr[RPHM_SPARSE_RELATIVE_ROWS].get(), P, G, rowBits, colBits,
+                                                    kA.get(), vA.get());
+  SB_LAUNCH_CHECK();
+  const int w = radix_sort_pairs<u64>(kA.get(), kB.get(), vA.get(), vB.get(), n, 0, rowBits + colBits + spBits, s);
+  sp->col.alloc(n);
+  sp->idx.alloc(n);
+  sp->row.alloc(n);
+  DevBuf<u32> nRuns(1);
+  SB_CUDA(cudaMemsetAsync(nRuns.get(), 0, 4, s));
+  k_sp_unpack<<<grid_for(n), 256, 0, s>>>(w ? kB.get() : kA.get(), w ? vB.get() : vA.get(),
+                                         L->arr[RPHM_SPARSE_VALUES].get(), n, rowBits, colBits, sp->col.get(),
+                                         sp->row.get(), sp->idx.get(), nRuns.get());
+  SB_LAUNCH_CHECK();
+  sp->numRuns = read_u32(nRuns.get(), s);
+  // segment size: 32768 entries, shrunk for small problems so that there are several CTAs per SM
+  {
+    const u32 target = (u32)device_sm_count() * 4u;
+    u32 sl = n / (target ? target : 1);
+    if (sl > 32768u) sl = 32768u;
+    if (sl < 2048u) sl = 2048u;
+    sp->segLen = (sl + 1023u) & ~1023u;
+  }
+  sp->off.alloc((size_t)sp->numSp + 1);
+  DevBuf<u32> segCnt(sp->numSp), segOff((size_t)sp->numSp + 1);
+  k_sp_offsets<<<grid_for((size_t)sp->numSp + 1), 256, 0, s>>>(vOff, P, G, sp->numSp, sp->segLen, sp->off.get(),
+                                                              segCnt.get());
+  SB_LAUNCH_CHECK();
+  scan_counts(segCnt.get(), segOff.get(), sp->numSp, s);
+  sp->numWork = read_u32(segOff.get() + sp->numSp, s);
+  if (sp->numWork) {
+    const u32 nw = sp->numWork;
+    DevBuf<uint2> work(nw), sorted(nw);
+    DevBuf<u32> k1(nw), k2(nw), i1(nw), i2(nw);
+    k_sp_work<<<grid_for((size_t)sp->numSp * 32), 256, 0, s>>>(segOff.get(), sp->numSp, sp->segLen, work.get(), k1.get());
+    SB_LAUNCH_CHECK();
+    iota<u32>(i1.get(), nw, 0u, s);
+    const int ws = radix_sort_pairs<u32>(k1.get(), k2.get(), i1.get(), i2.get(), nw, 0, 24, s);  // segment-major
+    k_gather_work<<<grid_for(nw), 256, 0, s>>>(work.get(), ws ? i2.get() : i1.get(), nw, sorted.get());
+    SB_LAUNCH_CHECK();
+    SB_CUDA(cudaStreamSynchronize(s));
+    sp->work = std::move(sorted);
+  }
+  SB_CUDA(cudaStreamSynchronize(s));
+  L->sp = std::move(sp);
+  return L->sp.get();
 }
 
 }  // namespace sb

@@ -1,6 +1,21 @@
 // layout.cuh -- the device-resident BSMR + RPHM layout object behind `bsmr_layout` (C ABI).
 #pragma once
+#include <memory>
+
 #include "common.cuh"
+
+namespace sb {
+// Private residual layout of the "super-panel" kernel (K7b): G consecutive row panels form a super-panel
+// whose A rows (16*G x K floats) fit in shared memory; its residual entries are sorted by (column, row)
+// so that one B^T row fetched from L2 is reused from registers by every entry of that column.
+struct SuperPanelLayout {
+  u32 G = 0, rows = 0, numSp = 0, segLen = 0, numWork = 0, numEntries = 0, numRuns = 0;
+  DevBuf<u32> off;              // [numSp+1] entry ranges per super-panel
+  DevBuf<u32> col, idx;         // per entry: column, CSR index
+  DevBuf<unsigned short> row;   // per entry: row inside the super-panel
+  DevBuf<uint2> work;           // (super-panel, first entry of the segment inside it), segment-major
+};
+}  // namespace sb
 
 struct bsmr_layout {
   bsmr_layout_info info{};
@@ -14,6 +29,7 @@ struct bsmr_layout {
   // device staging buffers of the host-buffer entry point (sddmm_run_host), grown on demand and kept
   // so that repeated calls do not pay cudaMalloc/cudaFree
   mutable sb::DevBuf<float> wsA, wsB, wsP;
+  mutable std::unique_ptr<sb::SuperPanelLayout> sp;  // built lazily for the K in use
 };
 
 namespace sb {
@@ -24,5 +40,8 @@ constexpr u32 kSparseChunkDefault = 2048;  // residual entries per CTA work item
 bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32 nnz,
                               const u32* d_reorderedRows, u32 numRows, float delta, u32 panelBegin, u32 panelEnd,
                               float* msCol, float* msRphm, cudaStream_t s);
+
+// (re)builds L->sp for G panels per super-panel if needed; returns it
+const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStream_t s);
 
 }  // namespace sb

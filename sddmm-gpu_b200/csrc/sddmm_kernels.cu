@@ -94,6 +94,115 @@ k_sddmm_residual(u32 M, u32 K4, const float4* __restrict__ A4, const float4* __r
   }
 }
 
+
+// =============================================================================================
+// residual kernel, super-panel form (K7b)
+//   CTA = one segment of one super-panel (G row panels) whose A rows (16*G x K) sit in shared memory.
+//   The super-panel's residual entries are sorted by (column, row); 8 lanes walk a CONTIGUOUS slice of the
+//   segment, so the entries of one column meet the same 8 lanes back to back: the gathered B^T row is
+//   fetched from L2 once (128-bit loads, 128 B per request) and then reused from registers.
+//   Control flow is warp-uniform (every group runs the same number of 8-entry blocks, tails are
+//   predicated), so all shuffles use the full mask; lane t of a group keeps the result of entry t of the
+//   block and stores it itself.  L2->SM bytes per entry drop from 4K+16 to ~4K/(entries per column)+10.
+// =============================================================================================
+template <int NB, int kThreads>
+static __global__ void __launch_bounds__(kThreads, 1)
+k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restrict__ B4, const u32* __restrict__ R,
+                    u32 nR, u32 spRows, u32 segLen, const u32* __restrict__ spOff, const u32* __restrict__ spCol,
+                    const unsigned short* __restrict__ spRow, const u32* __restrict__ spIdx,
+                    const uint2* __restrict__ work, float* __restrict__ P) {
+  extern __shared__ float4 sA[];  // spRows x K4
+  constexpr u32 K4 = 8 * NB;
+  constexpr u32 kGroups = kThreads / 8;
+  const uint2 w = work[blockIdx.x];
+  const u32 sp = w.x;
+  const u32 segBeg = spOff[sp] + w.y;
+  const u32 segLim = spOff[sp + 1];
+  const u32 segEnd = (segLim - segBeg > segLen) ? segBeg + segLen : segLim;
+
+  for (u32 i = threadIdx.x; i < spRows * K4; i += kThreads) {
+    const u32 r = i / K4, c = i - r * K4;
+    const u32 ri = sp * spRows + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ri < nR) {
+      const u32 row = R[ri];
+      if (row < M) v = __ldg(A4 + (size_t)row * K4 + c);
+    }
+    sA[i] = v;
+  }
+  __syncthreads();
+
+  const u32 grp = threadIdx.x >> 3, gl = threadIdx.x & 7u;
+  const u32 n = segEnd - segBeg;
+  const u32 per = (((n + kGroups - 1) / kGroups) + 7u) & ~7u;  // entries per group, multiple of 8
+  const u32 nBlocks = per >> 3;                                 // uniform over the whole CTA
+  const u32 gBeg = min(segEnd, segBeg + grp * per);
+  const u32 gEnd = min(segEnd, gBeg + per);
+  float4 breg[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) breg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  u32 prevCol = 0xFFFFFFFFu;
+  u32 mc = 0xFFFFFFFFu, mr = 0, mi = 0;
+  if (gBeg + gl < gEnd) {
+    mc = __ldg(spCol + gBeg + gl);
+    mr = __ldg(spRow + gBeg + gl);
+    mi = __ldg(spIdx + gBeg + gl);
+  }
+  for (u32 blk = 0; blk < nBlocks; ++blk) {
+    const u32 base = gBeg + blk * 8u;
+    // next block's metadata, one entry per lane
+    u32 nc = 0xFFFFFFFFu, nr = 0, ni = 0;
+    if (base + 8u + gl < gEnd) {
+      nc = __ldg(spCol + base + 8u + gl);
+      nr = __ldg(spRow + base + 8u + gl);
+      ni = __ldg(spIdx + base + 8u + gl);
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const u32 col = __shfl_sync(0xffffffffu, mc, t, 8);
+      const u32 row = __shfl_sync(0xffffffffu, mr, t, 8);
+      if (col != prevCol && col != 0xFFFFFFFFu) {  // new column for this group: fetch its B^T row
+        const float4* __restrict__ b = B4 + (size_t)col * K4 + gl;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) breg[j] = __ldg(b + j * 8);
+        prevCol = col;
+      }
+      const float4* a = sA + row * K4 + gl;
+      float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const float4 av = a[j * 8];
+        if (j & 1) {
+          acc1 = fmaf(av.x, breg[j].x, acc1); acc1 = fmaf(av.y, breg[j].y, acc1);
+          acc1 = fmaf(av.z, breg[j].z, acc1); acc1 = fmaf(av.w, breg[j].w, acc1);
+        } else {
+          acc0 = fmaf(av.x, breg[j].x, acc0); acc0 = fmaf(av.y, breg[j].y, acc0);
+          acc0 = fmaf(av.z, breg[j].z, acc0); acc0 = fmaf(av.w, breg[j].w, acc0);
+        }
+      }
+      float acc = acc0 + acc1;
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4, 8);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2, 8);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1, 8);
+      if (gl == (u32)t) mine = acc;
+    }
+    if (mc != 0xFFFFFFFFu) P[mi] = mine;
+    mc = nc; mr = nr; mi = ni;
+  }
+}
+
+// panels per super-panel for a given K (A tile <= ~192 KB), 0 if the super-panel kernel does not apply
+static u32 superpanel_G(u32 K) {
+  if (K % 32u || K > 512u) return 0;
+  const u32 NB = K / 32u;
+  if (NB != 1 && NB != 2 && NB != 4 && NB != 8 && NB != 16) return 0;
+  u32 rows = (192u * 1024u) / (K * 4u);
+  u32 G = rows / 16u;
+  if (G > 64u) G = 64u;
+  return G;
+}
+
 // =============================================================================================
 // dense kernel: tcgen05 / TMEM
 // =============================================================================================
@@ -303,16 +412,45 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
   }
   if (L->numSparseWork && (which & kLaunchSparse)) {
     const u32 K4 = K / 4;
-    const size_t smem = (size_t)16 * K * sizeof(float);
-    if (smem > 200 * 1024) fail(SDDMM_E_UNSUPPORTED, "K=%u too large for the residual kernel's A tile", K);
-    static const bool useL1 = [] { const char* e = getenv("SDDMM_B200_L1"); return !e || atoi(e) != 0; }();
-    auto kern = useL1 ? k_sddmm_residual<true> : k_sddmm_residual<false>;
-    if (smem > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<L->numSparseWork, kResThreads, smem, sparseStream>>>(
-        I.M, K4, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB), arr(BSMR_REORDERED_ROWS),
-        I.numRows, arr(BSMR_SPARSE_VALUE_OFFSETS), arr(RPHM_SPARSE_VALUES), arr(RPHM_SPARSE_RELATIVE_ROWS),
-        arr(RPHM_SPARSE_COL_INDICES), L->sparseWork.get(), L->sparseChunk, dP);
-    SB_LAUNCH_CHECK();
+    static const int mode = [] { const char* e = getenv("SDDMM_B200_RESIDUAL"); return e ? atoi(e) : 1; }();
+    const u32 G = mode == 1 ? superpanel_G(K) : 0;
+    if (G) {
+      const SuperPanelLayout* sp = ensure_superpanels(L, G, sparseStream);
+      // worth it only if a fetched B^T row is reused (entries per (super-panel, column) run)
+      static const float minReuse = [] { const char* e = getenv("SDDMM_B200_SP_MIN_REUSE"); return e ? (float)atof(e) : 0.0f; }();
+      const bool useSp = sp->numRuns && (float)sp->numEntries >= minReuse * (float)sp->numRuns;
+      if (!useSp) goto panel_kernel;
+      if (sp->numWork) {
+        const size_t smem = (size_t)sp->rows * K * sizeof(float);
+        auto launch = [&](auto kern, int threads) {
+          SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          kern<<<sp->numWork, threads, smem, sparseStream>>>(
+              I.M, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB), arr(BSMR_REORDERED_ROWS),
+              I.numRows, sp->rows, sp->segLen, sp->off.get(), sp->col.get(), sp->row.get(), sp->idx.get(),
+              sp->work.get(), dP);
+        };
+        switch (K / 32u) {
+          case 1: launch(k_sddmm_residual_sp<1, 1024>, 1024); break;
+          case 2: launch(k_sddmm_residual_sp<2, 1024>, 1024); break;
+          case 4: launch(k_sddmm_residual_sp<4, 1024>, 1024); break;
+          case 8: launch(k_sddmm_residual_sp<8, 512>, 512); break;
+          default: launch(k_sddmm_residual_sp<16, 512>, 512); break;
+        }
+        SB_LAUNCH_CHECK();
+      }
+    } else {
+    panel_kernel:
+      const size_t smem = (size_t)16 * K * sizeof(float);
+      if (smem > 200 * 1024) fail(SDDMM_E_UNSUPPORTED, "K=%u too large for the residual kernel's A tile", K);
+      static const bool useL1 = [] { const char* e = getenv("SDDMM_B200_L1"); return !e || atoi(e) != 0; }();
+      auto kern = useL1 ? k_sddmm_residual<true> : k_sddmm_residual<false>;
+      if (smem > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<L->numSparseWork, kResThreads, smem, sparseStream>>>(
+          I.M, K4, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB), arr(BSMR_REORDERED_ROWS),
+          I.numRows, arr(BSMR_SPARSE_VALUE_OFFSETS), arr(RPHM_SPARSE_VALUES), arr(RPHM_SPARSE_RELATIVE_ROWS),
+          arr(RPHM_SPARSE_COL_INDICES), L->sparseWork.get(), L->sparseChunk, dP);
+      SB_LAUNCH_CHECK();
+    }
   }
 }
 
