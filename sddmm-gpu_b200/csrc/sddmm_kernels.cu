@@ -307,33 +307,44 @@ k_sddmm_dense(u32 M, u32 N, u32 K, const float* __restrict__ A, const float* __r
   const u32 numChunks = (K + kDnKChunk - 1) / kDnKChunk;
   constexpr u32 idesc = umma_idesc_tf32(128, 16);
 
+  // register-staged, software-pipelined operand gather: the loads of chunk kc+1 are in flight while chunk
+  // kc is rounded (cvt.rna.tf32), stored to its swizzled stage, fenced and handed to the tensor core.
+  float4 rb[8], ra;
+  auto issue_loads = [&](u32 kc) {
+    const u32 k0 = kc * kDnKChunk;
+#pragma unroll
+    for (u32 it = 0; it < 8; ++it) {
+      const u32 idx = it * kDnThreads + tid;
+      const u32 col = sCols[idx >> 3];
+      const u32 k = k0 + (idx & 7u) * 4u;
+      rb[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col < N && k < K) rb[it] = __ldg(reinterpret_cast<const float4*>(B + (size_t)col * K + k));
+    }
+    const u32 arow = sRowsA[tid >> 3];
+    const u32 k = k0 + (tid & 7u) * 4u;
+    ra = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (arow < M && k < K) ra = __ldg(reinterpret_cast<const float4*>(A + (size_t)arow * K + k));
+  };
+  issue_loads(0);
   for (u32 kc = 0; kc < numChunks; ++kc) {
     const u32 s = kc % kDnStages;
     if (kc >= kDnStages) mbar_wait(&mbar[s], ((kc / kDnStages) - 1) & 1u);  // MMA of chunk kc-2 released the stage
     unsigned char* tileB = stages + s * kDnStageBytes;   // 128 rows x 128 B (MMA "A" operand)
     unsigned char* tileA = tileB + kDnRowsB * 128;       // 16 rows x 128 B  (MMA "B" operand)
-    const u32 k0 = kc * kDnKChunk;
-    // ---- stage the gathered B^T rows: 8 lanes per row, 16 B each; coalesced 128 B per row
+    // ---- gathered B^T rows: 8 lanes per row, 16 B each (coalesced 128 B per row), rounded like the reference
 #pragma unroll
     for (u32 it = 0; it < 8; ++it) {
       const u32 idx = it * kDnThreads + tid;
-      const u32 row = idx >> 3, chunk = idx & 7u;
-      const u32 col = sCols[row];
-      const u32 k = k0 + chunk * 4u;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col < N && k < K) v = __ldg(reinterpret_cast<const float4*>(B + (size_t)col * K + k));
+      float4 v = rb[it];
       v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w);
-      st_swizzled(tileB, row, chunk, v);
+      st_swizzled(tileB, idx >> 3, idx & 7u, v);
     }
     {
-      const u32 row = tid >> 3, chunk = tid & 7u;
-      const u32 arow = sRowsA[row];
-      const u32 k = k0 + chunk * 4u;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (arow < M && k < K) v = __ldg(reinterpret_cast<const float4*>(A + (size_t)arow * K + k));
+      float4 v = ra;
       v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w);
-      st_swizzled(tileA, row, chunk, v);
+      st_swizzled(tileA, tid >> 3, tid & 7u, v);
     }
+    if (kc + 1 < numChunks) issue_loads(kc + 1);
     // generic-proxy writes -> visible to the async proxy (tensor core reads smem through it)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
