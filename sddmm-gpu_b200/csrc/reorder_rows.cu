@@ -240,7 +240,7 @@ __device__ __forceinline__ u32 lookup_cnt(const uint2* __restrict__ e, u32 L, u3
 // cuUtil::reduce_sum (cudaUtil.cuh:13-45) for ONE pair, executed by one warp that plays the B
 // reference threads warp by warp.  Round-to-nearest intrinsics only: no contraction, no approx.
 __device__ float exact_similarity_warp(const u32* __restrict__ rep, const uint2* __restrict__ ent, u32 L, u32 nbpr,
-                                       u32 B, u32 keptMask, u32 ssRep, u32 ssCmp) {
+                                       u32 B, u32 keptMask, u32 ssRep, u32 ssCmp, u32 repStride = 1) {
   const u32 lane = threadIdx.x & 31;
   const float normRep = __fsqrt_rn(__uint2float_rn(ssRep));
   const float normCmp = __fsqrt_rn(__uint2float_rn(ssCmp));
@@ -250,7 +250,7 @@ __device__ float exact_similarity_warp(const u32* __restrict__ rep, const uint2*
     if (!((keptMask >> vw) & 1u)) continue;  // never added into shm[0] by the reference's tree
     float pmin = 0.f, pmax = 0.f;
     for (u32 i = (vw << 5) + lane; i < nbpr; i += B) {
-      const u32 r = rep[i];
+      const u32 r = rep[(size_t)i * repStride];
       const u32 c = lookup_cnt(ent, L, i);
       const float a = __fdiv_rn(__uint2float_rn(r), normRep);
       const float b = __fdiv_rn(__uint2float_rn(c), normCmp);
@@ -391,6 +391,264 @@ static __global__ void __launch_bounds__(kClThreads) k_cluster(ClusterArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// K2b: batched clustering.  Same sequential semantics, but up to G consecutive clusters are scanned in
+// ONE pass over the candidates (their representatives sit side by side in shared memory), so a
+// candidate's entry list is read from HBM once per G clusters instead of once per cluster.
+//
+//   Equivalent formulation used here (leader clustering): a row, visited in dispersion order, joins the
+//   FIRST open cluster (creation order) whose representative accepts it, where a representative holds the
+//   rows that joined it earlier; a row no open cluster accepts seeds a new cluster.  Clusters c0..c0+g-1
+//   of a batch are SPECULATED to be seeded by the next g unclustered positions s[0] < ... < s[g-1].
+//   A window evaluates, for every unclustered position, the clusters whose seed precedes it, in order,
+//   and reports the earliest position at which anything joins.  Everything before that position is
+//   final (a speculated seed that was passed without being absorbed is thereby confirmed); the join is
+//   applied and the scan resumes behind it.  If the joiner is itself a speculated seed s[j], clusters
+//   j.. of the batch are dropped (nothing of theirs was final yet) and the batch continues with j.
+// ------------------------------------------------------------------------------------------
+constexpr int kCbThreads = 1024;
+constexpr int kCbWarps = kCbThreads / 32;
+constexpr int kCbMaxG = 8;
+
+struct ClusterBatchArgs {
+  u32 M, start0, nbpr, B, keptMask, G;
+  float alpha;
+  const uint2* enc;
+  const uint4* meta;
+  u32* cid;
+  unsigned long long* slots;  // [3] earliest (pos << 8 | cluster-in-batch) that joins, per rotating window
+  u32* seeds;                 // [0] count, [1..8] positions of the next batch's seeds (written by block 0)
+  u32* stats;                 // [0] exact evaluations, [1] clusters created, [2] windows, [3] batches
+};
+
+// block 0 only: the next (up to G) unclustered positions at or after `from`, in order
+__device__ void cb_find_seeds(const ClusterBatchArgs& a, u32 from, u32* sCount) {
+  __shared__ u32 warpCnt[kCbWarps];
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) *sCount = 0;
+  __syncthreads();
+  for (u32 base = from; base < a.M; base += kCbThreads) {
+    const u32 pos = base + threadIdx.x;
+    const bool open = pos < a.M && __ldcg(a.cid + pos) == kNull;
+    const unsigned bal = __ballot_sync(0xffffffffu, open);
+    if (lane == 0) warpCnt[warp] = __popc(bal);
+    __syncthreads();
+    u32 before = *sCount;
+    for (u32 w = 0; w < warp; ++w) before += warpCnt[w];
+    const u32 rank = before + __popc(bal & ((1u << lane) - 1u));
+    if (open && rank < a.G) a.seeds[1 + rank] = pos;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      u32 t = *sCount;
+      for (int w = 0; w < kCbWarps; ++w) t += warpCnt[w];
+      *sCount = t;
+    }
+    __syncthreads();
+    if (*sCount >= a.G) break;
+  }
+  if (threadIdx.x == 0) {
+    a.seeds[0] = *sCount < a.G ? *sCount : a.G;
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int TG>  // representatives interleaved: rep[block * TG + k], so one lookup serves all TG clusters
+static __global__ void __launch_bounds__(kCbThreads, 1) k_cluster_batched(ClusterBatchArgs a) {
+  extern __shared__ __align__(16) u32 rep[];  // nbpr x TG accumulated histograms
+  __shared__ u32 sSeed[kCbMaxG], sSs[kCbMaxG], sS1[kCbMaxG];
+  __shared__ u32 sRed[kCbWarps];
+  __shared__ u32 sCount;
+  cg::grid_group grid = cg::this_grid();
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u32 totalWarps = gridDim.x * kCbWarps;
+  const u32 gw = blockIdx.x * kCbWarps + warp;
+  volatile unsigned long long* slots = a.slots;
+  volatile u32* seeds = a.seeds;
+  const float tol = kTolRel * fabsf(a.alpha) + kTolAbs;
+
+  u32 c0 = 1, iter = 0;
+  bool calm = false;  // the previous batch saw no join: open the next one with the widest window
+  if (blockIdx.x == 0) cb_find_seeds(a, a.start0, &sCount);
+  __threadfence();
+  grid.sync();
+  while (true) {
+    u32 g = seeds[0];
+    if (g == 0) break;
+    // ---- open the batch: representatives = histograms of the speculated seeds
+    __syncthreads();
+    if (threadIdx.x < g) {
+      const u32 sd = seeds[1 + threadIdx.x];
+      sSeed[threadIdx.x] = sd;
+      const uint4 m = a.meta[sd];
+      sSs[threadIdx.x] = m.z;
+      sS1[threadIdx.x] = m.w;
+    }
+    for (u32 i = threadIdx.x; i < (u32)TG * a.nbpr; i += kCbThreads) rep[i] = 0;
+    __syncthreads();
+    for (u32 k = 0; k < g; ++k) {
+      const uint4 m = a.meta[sSeed[k]];
+      for (u32 j = threadIdx.x; j < m.y; j += kCbThreads) {
+        const uint2 e = a.enc[m.x + j];
+        rep[e.x * TG + k] = e.y;
+      }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      a.cid[sSeed[0]] = c0;  // the first open position is a seed for certain
+      atomicAdd(a.stats + 3, 1u);
+    }
+    __syncthreads();
+    u32 p = sSeed[0] + 1, chunk = calm ? totalWarps * 16u : totalWarps;
+    calm = true;
+    while (p < a.M) {
+      const u32 e = (a.M - p > chunk) ? p + chunk : a.M;
+      const u32 slot = iter % 3;
+      float nRepInv[TG], Sa[TG];
+#pragma unroll
+      for (int k = 0; k < TG; ++k) {
+        const u32 ss = (u32)k < g ? sSs[k] : 0u;
+        nRepInv[k] = ss ? 1.0f / sqrtf((float)ss) : 0.f;
+        Sa[k] = (u32)k < g ? (float)sS1[k] * nRepInv[k] : 0.f;
+      }
+      for (u32 pos = p + gw; pos < e; pos += totalWarps) {
+        if (__ldcg(a.cid + pos) != kNull) continue;
+        // clusters of the batch whose seed precedes this position (seeds are ascending)
+        u32 kmax = 0;
+#pragma unroll
+        for (int k = 0; k < TG; ++k) kmax += ((u32)k < g && sSeed[k] < pos) ? 1u : 0u;
+        if (kmax == 0) continue;
+        const uint4 m = a.meta[pos];
+        const uint2* ent = a.enc + m.x;
+        const u32 ssCmp = m.z;
+        const float nCmpInv = ssCmp ? 1.0f / sqrtf((float)ssCmp) : 0.f;
+        float mn[TG];
+#pragma unroll
+        for (int k = 0; k < TG; ++k) mn[k] = 0.f;
+        // 4 entry loads in flight per lane (the lists stream from HBM: latency, not bandwidth, is the limit)
+        for (u32 j0 = lane; j0 < m.y; j0 += 128) {
+          uint2 en4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const u32 j = j0 + u * 32;
+            en4[u] = j < m.y ? ent[j] : make_uint2(0u, 0u);  // count 0 contributes min(.,0) = 0
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint2 en = en4[u];
+            const float b = (float)en.y * nCmpInv;
+            u32 rv[TG];
+            if constexpr (TG >= 4) {
+#pragma unroll
+              for (int q = 0; q < TG / 4; ++q) {
+                const uint4 v4 = *reinterpret_cast<const uint4*>(rep + (size_t)en.x * TG + q * 4);
+                rv[q * 4 + 0] = v4.x; rv[q * 4 + 1] = v4.y; rv[q * 4 + 2] = v4.z; rv[q * 4 + 3] = v4.w;
+              }
+            } else if constexpr (TG == 2) {
+              const uint2 v2 = *reinterpret_cast<const uint2*>(rep + (size_t)en.x * 2);
+              rv[0] = v2.x; rv[1] = v2.y;
+            } else {
+              rv[0] = rep[en.x];
+            }
+#pragma unroll
+            for (int k = 0; k < TG; ++k) mn[k] += fminf((float)rv[k] * nRepInv[k], b);  // clusters >= kmax are ignored below
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < TG; ++k) {
+          if ((u32)k < kmax) {
+#pragma unroll
+            for (int w = 16; w >= 1; w >>= 1) mn[k] += __shfl_xor_sync(0xffffffffu, mn[k], w);
+          }
+        }
+        u32 joinK = kNull;
+#pragma unroll
+        for (int k = 0; k < TG; ++k) {
+          if ((u32)k < kmax && joinK == kNull) {  // warp-uniform
+            const u32 ssRep = sSs[k];
+            bool join;
+            if (ssRep == 0 || ssCmp == 0) {
+              join = ((ssRep == 0 && ssCmp == 0) ? 1.0f : 0.0f) > a.alpha;  // rowReordering.cu:263-268
+            } else {
+              const float den = Sa[k] + (float)m.w * nCmpInv - mn[k];
+              const float est = mn[k] / den;
+              if (den > 0.f && est > a.alpha + tol) join = true;
+              else if (den > 0.f && est < a.alpha - tol) join = false;
+              else {
+                const float sim = exact_similarity_warp(rep + k, ent, m.y, a.nbpr, a.B, a.keptMask, ssRep, ssCmp, TG);
+                join = sim > a.alpha;
+                if (lane == 0) atomicAdd(a.stats + 0, 1u);
+              }
+            }
+            if (join) joinK = (u32)k;
+          }
+        }
+        if (joinK != kNull && lane == 0)
+          atomicMin(a.slots + slot, ((unsigned long long)pos << 8) | (unsigned long long)joinK);
+      }
+      __threadfence();
+      grid.sync();
+      const unsigned long long v = slots[slot];
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        slots[(iter + 2) % 3] = ~0ull;
+        atomicAdd(a.stats + 2, 1u);
+      }
+      const bool joined = v != ~0ull;
+      const u32 f = joined ? (u32)(v >> 8) : 0u;
+      const u32 jk = joined ? (u32)(v & 255u) : 0u;
+      const u32 limit = joined ? f : e;  // positions in [p, limit) are final
+      // speculated seeds that were passed without being absorbed are confirmed
+      if (blockIdx.x == 0 && threadIdx.x >= 1 && threadIdx.x < g) {
+        const u32 sd = sSeed[threadIdx.x];
+        if (sd >= p && sd < limit) a.cid[sd] = c0 + threadIdx.x;
+      }
+      if (joined) {
+        // was the joiner one of our speculated seeds?  then clusters from that one on never existed
+        u32 newG = g;
+        for (u32 j = 1; j < g; ++j)
+          if (sSeed[j] == f) newG = j;
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.cid[f] = c0 + jk;
+        const uint4 m = a.meta[f];
+        u32 dss = 0;
+        u32* rk = rep + jk;
+        for (u32 j = threadIdx.x; j < m.y; j += kCbThreads) {
+          const uint2 en = a.enc[m.x + j];
+          const u32 r = rk[(size_t)en.x * TG];
+          const u32 nr = r + en.y;
+          dss += nr * nr - r * r;
+          rk[(size_t)en.x * TG] = nr;
+        }
+        dss = __reduce_add_sync(0xffffffffu, dss);
+        __syncthreads();
+        if (lane == 0) sRed[warp] = dss;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          u32 t = 0;
+          for (int w = 0; w < kCbWarps; ++w) t += sRed[w];
+          sSs[jk] += t;
+          sS1[jk] += m.w;
+        }
+        __syncthreads();
+        g = newG;
+        p = f + 1;
+        chunk = totalWarps;
+        calm = false;
+      } else {
+        p = e;
+        if (chunk < totalWarps * 16u) chunk *= 2;
+      }
+      ++iter;
+    }
+    // ---- batch done: clusters c0 .. c0+g-1 are complete
+    c0 += g;
+    const u32 from = sSeed[g - 1] + 1;
+    __syncthreads();
+    if (blockIdx.x == 0) cb_find_seeds(a, from, &sCount);
+    __threadfence();
+    grid.sync();
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.stats[1] = c0 - 1;
+}
+
+// ------------------------------------------------------------------------------------------
 // final permutation
 // ------------------------------------------------------------------------------------------
 static __global__ void k_compose_perm(const u32* __restrict__ asc, const u32* __restrict__ indices, u32 skip, u32 n,
@@ -501,7 +759,38 @@ void row_reorder_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32
   SB_CUDA(cudaMemsetAsync(ctrl.get() + 6, 0, 2 * 4, s));
   SB_CUDA(cudaMemsetAsync(ncl.get(), 0, 4, s));
   u32 exactEvals = 0;
-  if (zeroRows < M) {
+  static const bool legacy = [] { const char* e = getenv("SDDMM_B200_CLUSTER"); return e && !strcmp(e, "legacy"); }();
+  DevBuf<unsigned long long> slots(4);
+  DevBuf<u32> seedsBuf(16), statsBuf(8);
+  if (zeroRows < M && !legacy) {
+    ClusterBatchArgs a;
+    a.M = M; a.start0 = zeroRows; a.nbpr = nbpr; a.B = B; a.keptMask = keptMask; a.alpha = alpha;
+    a.enc = enc.get(); a.meta = meta.get(); a.cid = cid.get(); a.slots = slots.get(); a.seeds = seedsBuf.get();
+    a.stats = statsBuf.get();
+    u32 G = (u32)((200u * 1024u) / ((size_t)nbpr * 4));
+    if (const char* e = getenv("SDDMM_B200_CLUSTER_G")) { const int v = atoi(e); if (v >= 1 && (u32)v < G) G = (u32)v; }
+    G = G >= 8 ? 8u : G >= 4 ? 4u : G >= 2 ? 2u : 1u;  // template instances
+    a.G = G;
+    SB_CUDA(cudaMemsetAsync(slots.get(), 0xFF, 4 * 8, s));
+    SB_CUDA(cudaMemsetAsync(seedsBuf.get(), 0, 16 * 4, s));
+    SB_CUDA(cudaMemsetAsync(statsBuf.get(), 0, 8 * 4, s));
+    const size_t smem = (size_t)G * nbpr * 4;
+    const void* kern = G == 8 ? (const void*)k_cluster_batched<8> : G == 4 ? (const void*)k_cluster_batched<4>
+                     : G == 2 ? (const void*)k_cluster_batched<2> : (const void*)k_cluster_batched<1>;
+    SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int perSm = 0;
+    SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, kCbThreads, smem));
+    if (perSm < 1) fail(SDDMM_E_UNSUPPORTED, "batched clustering kernel does not fit on an SM (nbpr=%u)", nbpr);
+    if (perSm > 2) perSm = 2;
+    u32 grid = (u32)(perSm * device_sm_count());
+    const u32 need = ceil_div(M - zeroRows, kCbWarps);
+    if (grid > need) grid = need ? need : 1;
+    void* args[] = {&a};
+    SB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kCbThreads), args, smem, s));
+    SB_LAUNCH_CHECK();
+    SB_CUDA(cudaMemcpyAsync(&exactEvals, statsBuf.get(), 4, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaMemcpyAsync(ncl.get(), statsBuf.get() + 1, 4, cudaMemcpyDeviceToDevice, s));
+  } else if (zeroRows < M) {
     ClusterArgs a;
     a.M = M; a.start0 = zeroRows; a.nbpr = nbpr; a.B = B; a.keptMask = keptMask; a.alpha = alpha;
     a.enc = enc.get(); a.meta = meta.get(); a.cid = cid.get(); a.ctrl = ctrl.get(); a.numClustersOut = ncl.get();
@@ -510,7 +799,10 @@ void row_reorder_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32
     int perSm = 0;
     SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_cluster, kClThreads, smem));
     if (perSm < 1) fail(SDDMM_E_UNSUPPORTED, "clustering kernel does not fit on an SM (nbpr=%u)", nbpr);
-    if (perSm > 2) perSm = 2;
+    {
+      static const int cap = [] { const char* e = getenv("SDDMM_B200_CLUSTER_CTAS_PER_SM"); return e ? atoi(e) : 6; }();
+      if (perSm > cap) perSm = cap;
+    }
     // no more CTAs than there are candidate rows to look at
     u32 grid = (u32)(perSm * device_sm_count());
     const u32 need = ceil_div(M - zeroRows, kClWarps);
