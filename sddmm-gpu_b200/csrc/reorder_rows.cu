@@ -416,6 +416,8 @@ struct ClusterBatchArgs {
   const uint4* meta;
   u32* cid;
   unsigned long long* slots;  // [3] earliest (pos << 8 | cluster-in-batch) that joins, per rotating window
+  u32* accepts;               // [3] number of accepting candidates seen in the window (same rotation)
+  u32* pend;                  // [M] assignments made in sequential mode, flushed into cid by block 0 afterwards
   u32* seeds;                 // [0] count, [1..8] positions of the next batch's seeds (written by block 0)
   u32* stats;                 // [0] exact evaluations, [1] clusters created, [2] windows, [3] batches
 };
@@ -448,6 +450,35 @@ __device__ void cb_find_seeds(const ClusterBatchArgs& a, u32 from, u32* sCount) 
   if (threadIdx.x == 0) {
     a.seeds[0] = *sCount < a.G ? *sCount : a.G;
     __threadfence();
+  }
+  __syncthreads();
+}
+
+
+// applies "row at position f joins cluster jk": rep_jk += hist(f), sum of squares updated exactly in uint32
+template <int TG>
+__device__ __forceinline__ void cb_apply_join(const ClusterBatchArgs& a, u32* rep, u32* sSs, u32* sS1, u32* sRed,
+                                              u32 f, u32 jk) {
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint4 m = a.meta[f];
+  u32 dss = 0;
+  u32* rk = rep + jk;
+  for (u32 j = threadIdx.x; j < m.y; j += kCbThreads) {
+    const uint2 en = a.enc[m.x + j];
+    const u32 r = rk[(size_t)en.x * TG];
+    const u32 nr = r + en.y;
+    dss += nr * nr - r * r;
+    rk[(size_t)en.x * TG] = nr;
+  }
+  dss = __reduce_add_sync(0xffffffffu, dss);
+  __syncthreads();
+  if (lane == 0) sRed[warp] = dss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 t = 0;
+    for (int w = 0; w < kCbWarps; ++w) t += sRed[w];
+    sSs[jk] += t;
+    sS1[jk] += m.w;
   }
   __syncthreads();
 }
@@ -509,7 +540,9 @@ static __global__ void __launch_bounds__(kCbThreads, 1) k_cluster_batched(Cluste
         nRepInv[k] = ss ? 1.0f / sqrtf((float)ss) : 0.f;
         Sa[k] = (u32)k < g ? (float)sS1[k] * nRepInv[k] : 0.f;
       }
-      for (u32 pos = p + gw; pos < e; pos += totalWarps) {
+      // position -> warp: spread consecutive positions over the CTAs first (small windows use every SM)
+      const u32 vw = warp * gridDim.x + blockIdx.x;
+      for (u32 pos = p + vw; pos < e; pos += totalWarps) {
         if (__ldcg(a.cid + pos) != kNull) continue;
         // clusters of the batch whose seed precedes this position (seeds are ascending)
         u32 kmax = 0;
@@ -581,14 +614,18 @@ static __global__ void __launch_bounds__(kCbThreads, 1) k_cluster_batched(Cluste
             if (join) joinK = (u32)k;
           }
         }
-        if (joinK != kNull && lane == 0)
+        if (joinK != kNull && lane == 0) {
           atomicMin(a.slots + slot, ((unsigned long long)pos << 8) | (unsigned long long)joinK);
+          atomicAdd(a.accepts + slot, 1u);
+        }
       }
       __threadfence();
       grid.sync();
       const unsigned long long v = slots[slot];
+      const u32 nAccept = ((volatile u32*)a.accepts)[slot];
       if (blockIdx.x == 0 && threadIdx.x == 0) {
         slots[(iter + 2) % 3] = ~0ull;
+        a.accepts[(iter + 2) % 3] = 0u;
         atomicAdd(a.stats + 2, 1u);
       }
       const bool joined = v != ~0ull;
@@ -606,30 +643,12 @@ static __global__ void __launch_bounds__(kCbThreads, 1) k_cluster_batched(Cluste
         for (u32 j = 1; j < g; ++j)
           if (sSeed[j] == f) newG = j;
         if (blockIdx.x == 0 && threadIdx.x == 0) a.cid[f] = c0 + jk;
-        const uint4 m = a.meta[f];
-        u32 dss = 0;
-        u32* rk = rep + jk;
-        for (u32 j = threadIdx.x; j < m.y; j += kCbThreads) {
-          const uint2 en = a.enc[m.x + j];
-          const u32 r = rk[(size_t)en.x * TG];
-          const u32 nr = r + en.y;
-          dss += nr * nr - r * r;
-          rk[(size_t)en.x * TG] = nr;
-        }
-        dss = __reduce_add_sync(0xffffffffu, dss);
-        __syncthreads();
-        if (lane == 0) sRed[warp] = dss;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          u32 t = 0;
-          for (int w = 0; w < kCbWarps; ++w) t += sRed[w];
-          sSs[jk] += t;
-          sS1[jk] += m.w;
-        }
-        __syncthreads();
+        cb_apply_join<TG>(a, rep, sSs, sS1, sRed, f, jk);
         g = newG;
         p = f + 1;
-        chunk = totalWarps;
+        // rows tend to join in streaks and only the first joiner of a window counts: look at a few
+        // candidates right behind it (one per CTA), then widen again while nothing joins
+        chunk = gridDim.x;
         calm = false;
       } else {
         p = e;
@@ -761,12 +780,16 @@ void row_reorder_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32
   u32 exactEvals = 0;
   static const bool legacy = [] { const char* e = getenv("SDDMM_B200_CLUSTER"); return e && !strcmp(e, "legacy"); }();
   DevBuf<unsigned long long> slots(4);
-  DevBuf<u32> seedsBuf(16), statsBuf(8);
+  DevBuf<u32> seedsBuf(16), statsBuf(8), acceptsBuf(4), pendBuf(legacy ? 1 : M);
   if (zeroRows < M && !legacy) {
     ClusterBatchArgs a;
     a.M = M; a.start0 = zeroRows; a.nbpr = nbpr; a.B = B; a.keptMask = keptMask; a.alpha = alpha;
     a.enc = enc.get(); a.meta = meta.get(); a.cid = cid.get(); a.slots = slots.get(); a.seeds = seedsBuf.get();
     a.stats = statsBuf.get();
+    a.accepts = acceptsBuf.get();
+    a.pend = pendBuf.get();
+    SB_CUDA(cudaMemsetAsync(acceptsBuf.get(), 0, 16, s));
+    SB_CUDA(cudaMemsetAsync(pendBuf.get(), 0xFF, (size_t)M * 4, s));
     u32 G = (u32)((200u * 1024u) / ((size_t)nbpr * 4));
     if (const char* e = getenv("SDDMM_B200_CLUSTER_G")) { const int v = atoi(e); if (v >= 1 && (u32)v < G) G = (u32)v; }
     G = G >= 8 ? 8u : G >= 4 ? 4u : G >= 2 ? 2u : 1u;  // template instances

@@ -59,8 +59,8 @@ class Layout:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
-            _lib.lib().bsmr_layout_destroy(h)
+        if h and _lib is not None and getattr(_lib, "_lib", None) is not None:  # not during interpreter teardown
+            _lib._lib.bsmr_layout_destroy(h)
 
     @property
     def handle(self):

@@ -1,0 +1,91 @@
+"""Same-box comparison: the UNMODIFIED reference GPU pipeline (oracle/_ref/ref_dump) vs libsddmm_b200 on the
+same inputs.  Only K <= 32 can be compared for the SDDMM kernel itself (the reference's K > 32 kernels fault on
+sm_100); reorder times are compared for every case.  Writes profiles/ref_vs_ours_r01.json.
+
+    gpurun -- python tools/compare_ref.py
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_package  # noqa: E402
+
+pkg = load_package()
+gen = pkg.generators
+from oracle import oracle as O  # noqa: E402
+
+
+def run_ref(S, A, B, alpha, delta):
+    tmp = tempfile.mkdtemp()
+    case = os.path.join(tmp, "case.bin")
+    gen.write_case_bin(case, S, A, B)
+    p = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_dump"), case, repr(alpha), repr(delta), tmp, "10"],
+                       capture_output=True, text=True, timeout=3000)
+    meta = {}
+    for line in open(os.path.join(tmp, "meta.txt")):
+        k, v = line.split()
+        try:
+            meta[k] = int(v)
+        except ValueError:
+            meta[k] = float(v)
+    R = np.fromfile(os.path.join(tmp, "reorderedRows.u32"), dtype=np.uint32)
+    P = np.fromfile(os.path.join(tmp, "P.f32"), dtype=np.float32)
+    for f in os.listdir(tmp):
+        os.remove(os.path.join(tmp, f))
+    os.rmdir(tmp)
+    return meta, R, P
+
+
+def run_ours(S, A, B, alpha, delta, bs):
+    import torch
+    ro = torch.from_numpy(S.row_off.view(np.int32)).cuda()
+    ci = torch.from_numpy(S.col_idx.view(np.int32)).cuda()
+    R, ncl, row_ms = pkg.row_reorder_dev(ro, ci, S.M, S.N, alpha, bs)
+    lay, col_ms, rphm_ms = pkg.layout_build_dev(ro, ci, S.M, S.N, R, delta)
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    dP = torch.zeros(max(1, S.nnz), dtype=torch.float32, device="cuda")
+    t = pkg.sddmm_gpu_timed(dA, dB, lay, dP, warmup=3, iters=10)
+    torch.cuda.synchronize()
+    return dict(row_ms=row_ms, col_ms=col_ms, rphm_ms=rphm_ms, **t), R.cpu().numpy().view(np.uint32), dP.cpu().numpy()[: S.nnz]
+
+
+def main():
+    cases = [
+        ("nips_surrogate 1500x12419 nnz 746k", gen.zipf_docs(1500, 12419, 746316, 1), 32),
+        ("bernoulli 4096^2 70% sparse", gen.bernoulli_mask(4096, 4096, 0.7, 30), 32),
+        ("dlmc-style 4096^2 90% sparse", gen.dlmc_magnitude_mask(4096, 4096, 0.9, 33), 32),
+        ("R-MAT scale 16 (65536^2, nnz 956k)", gen.rmat(16, 16, 4), 32),
+        ("uniform 20000^2 1%", gen.uniform_random(20000, 20000, 0.01, 2), 32),
+    ]
+    out = []
+    for name, S, K in cases:
+        A, B = gen.dense_operands(S.M, S.N, K)
+        meta, Rr, Pr = run_ref(S, A, B, 0.3, 0.3)
+        ours, Ro, Po = run_ours(S, A, B, 0.3, 0.3, int(meta["block_size"]))
+        flops = 2.0 * S.nnz * K
+        rec = dict(case=name, M=S.M, N=S.N, nnz=S.nnz, K=K, alpha=0.3, delta=0.3,
+                   same_permutation=bool(np.array_equal(Rr, Ro)),
+                   values_within_checkData=int(O.check_data(Pr, Po)) == 0 if meta.get("cuda_error", 0) == 0 else None,
+                   reference=dict(row_reorder_ms=meta["row_reorder_ms"], col_reorder_ms=meta["col_reorder_ms"],
+                                  sddmm_ms=meta["sddmm_ms"], gflops=flops / (meta["sddmm_ms"] * 1e6) if meta["sddmm_ms"] > 0 else None,
+                                  cuda_error=meta.get("cuda_error")),
+                   ours=dict(row_reorder_ms=ours["row_ms"], col_reorder_ms=ours["col_ms"], rphm_ms=ours["rphm_ms"],
+                             sddmm_ms=ours["total_ms"], gflops=flops / (ours["total_ms"] * 1e6)))
+        if meta["sddmm_ms"] > 0:
+            rec["speedup_sddmm"] = meta["sddmm_ms"] / ours["total_ms"]
+        rec["speedup_row_reorder"] = meta["row_reorder_ms"] / ours["row_ms"]
+        rec["speedup_col_reorder"] = meta["col_reorder_ms"] / (ours["col_ms"] + ours["rphm_ms"])
+        out.append(rec)
+        print(json.dumps(rec), flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "ref_vs_ours_r01.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
