@@ -157,6 +157,15 @@ int sddmm_run_timed_dev(const bsmr_layout*, uint32_t K, const float* d_A, const 
 int sddmm_run_host(const bsmr_layout*, uint32_t K, const float* h_A, const float* h_B, float* h_P,
                    float* msTotal);
 
+/* Pipelined form of sddmm_run_host for callers that stream many (A, B) batches through one layout:
+ * the call only ENQUEUES  H2D(A, B) -> SDDMM pass -> D2H(P)  for `slot` (0 or 1) on three internal streams
+ * and returns; slot s may be reused after sddmm_host_sync() or once two later calls have been enqueued and
+ * synced.  Host buffers must be page-locked for the copies to overlap.  With two slots the H2D of batch
+ * i+1, the kernels of batch i and the D2H of batch i-1 run concurrently (PCIe is full duplex).
+ * (The reference's host overload, src/sddmmKernel.cu:2518-2537, is synchronous; this is its streaming twin.) */
+int sddmm_run_host_async(const bsmr_layout*, uint32_t K, const float* h_A, const float* h_B, float* h_P, int slot);
+int sddmm_host_sync(const bsmr_layout*);
+
 /* ---- whole path on host buffers ----------------------------------------------------------------
  * replaces sddmm(options, A, B, P, logger)                src/sddmm.cu:10-39
  * = row reorder -> layout -> one SDDMM pass.  `layoutOut` (optional) receives the layout so the

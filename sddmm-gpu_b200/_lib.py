@@ -81,6 +81,8 @@ def lib():
     L.sddmm_run_dev.argtypes = [vp, u32, vp, vp, vp, vp]
     L.sddmm_run_timed_dev.argtypes = [vp, u32, vp, vp, vp, C.c_int, C.c_int, pf32, pf32, pf32]
     L.sddmm_run_host.argtypes = [vp, u32, vp, vp, vp, pf32]
+    L.sddmm_run_host_async.argtypes = [vp, u32, vp, vp, vp, C.c_int]
+    L.sddmm_host_sync.argtypes = [vp]
     L.sddmm_host.argtypes = [vp, vp, u32, u32, u32, u32, vp, vp, f32, f32, u32, vp, C.POINTER(Stats), C.POINTER(vp)]
     L.bsmr_shard_plan.argtypes = [vp, vp, u32, u32, vp]
     _lib = L

@@ -1,5 +1,6 @@
 // api.cu -- the C ABI of include/sddmm_b200.h.  Thin: argument checks, H2D/D2H for the host-buffer
 // forms, exception -> error code translation.  No CPU compute path exists behind any entry point.
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -258,6 +259,59 @@ int sddmm_run_host(const bsmr_layout* L, uint32_t K, const float* h_A, const flo
   SB_CUDA(cudaMemcpyAsync(h_P, dP, (size_t)I.nnz * 4, cudaMemcpyDeviceToHost, s));
   const float el = t.stop();
   if (msTotal) *msTotal = el;
+  API_END
+}
+
+int sddmm_run_host_async(const bsmr_layout* L, uint32_t K, const float* h_A, const float* h_B, float* h_P, int slot) {
+  API_BEGIN
+  require_device();
+  require(L && h_A && h_B && h_P && (slot == 0 || slot == 1), "arguments");
+  const bsmr_layout_info& I = L->info;
+  if (!L->pipe) {
+    auto pp = std::make_unique<bsmr_layout::HostPipe>();
+    SB_CUDA(cudaStreamCreateWithFlags(&pp->h2d, cudaStreamNonBlocking));
+    SB_CUDA(cudaStreamCreateWithFlags(&pp->comp, cudaStreamNonBlocking));
+    SB_CUDA(cudaStreamCreateWithFlags(&pp->d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      SB_CUDA(cudaEventCreateWithFlags(&pp->evH2D[i], cudaEventDisableTiming));
+      SB_CUDA(cudaEventCreateWithFlags(&pp->evComp[i], cudaEventDisableTiming));
+      SB_CUDA(cudaEventCreateWithFlags(&pp->evD2H[i], cudaEventDisableTiming));
+    }
+    L->pipe = std::move(pp);
+  }
+  bsmr_layout::HostPipe& P = *L->pipe;
+  const size_t nA = (size_t)I.M * K, nB = (size_t)I.N * K, nP = I.nnz ? I.nnz : 1;
+  if (P.A[slot].size() < nA || P.B[slot].size() < nB || P.P[slot].size() < nP) {
+    SB_CUDA(cudaDeviceSynchronize());  // growing a slot: nothing may still be using it
+    if (P.A[slot].size() < nA) P.A[slot].alloc(nA);
+    if (P.B[slot].size() < nB) P.B[slot].alloc(nB);
+    if (P.P[slot].size() < nP) P.P[slot].alloc(nP);
+  }
+  // H2D of this batch may start once the previous pass on this slot has consumed A/B
+  SB_CUDA(cudaStreamWaitEvent(P.h2d, P.evComp[slot], 0));
+  SB_CUDA(cudaMemcpyAsync(P.A[slot].get(), h_A, nA * 4, cudaMemcpyHostToDevice, P.h2d));
+  SB_CUDA(cudaMemcpyAsync(P.B[slot].get(), h_B, nB * 4, cudaMemcpyHostToDevice, P.h2d));
+  SB_CUDA(cudaEventRecord(P.evH2D[slot], P.h2d));
+  // the pass needs the operands and a P buffer whose previous contents have left for the host
+  SB_CUDA(cudaStreamWaitEvent(P.comp, P.evH2D[slot], 0));
+  SB_CUDA(cudaStreamWaitEvent(P.comp, P.evD2H[slot], 0));
+  SB_CUDA(cudaMemsetAsync(P.P[slot].get(), 0, (size_t)I.nnz * 4, P.comp));
+  run_once(L, K, P.A[slot].get(), P.B[slot].get(), P.P[slot].get(), P.comp);
+  SB_CUDA(cudaEventRecord(P.evComp[slot], P.comp));
+  SB_CUDA(cudaStreamWaitEvent(P.d2h, P.evComp[slot], 0));
+  SB_CUDA(cudaMemcpyAsync(h_P, P.P[slot].get(), (size_t)I.nnz * 4, cudaMemcpyDeviceToHost, P.d2h));
+  SB_CUDA(cudaEventRecord(P.evD2H[slot], P.d2h));
+  API_END
+}
+
+int sddmm_host_sync(const bsmr_layout* L) {
+  API_BEGIN
+  require(L, "null layout");
+  if (L->pipe) {
+    SB_CUDA(cudaStreamSynchronize(L->pipe->h2d));
+    SB_CUDA(cudaStreamSynchronize(L->pipe->comp));
+    SB_CUDA(cudaStreamSynchronize(L->pipe->d2h));
+  }
   API_END
 }
 

@@ -30,6 +30,23 @@ struct bsmr_layout {
   // so that repeated calls do not pay cudaMalloc/cudaFree
   mutable sb::DevBuf<float> wsA, wsB, wsP;
   mutable std::unique_ptr<sb::SuperPanelLayout> sp;  // built lazily for the K in use
+  // two-slot pipeline of sddmm_run_host_async
+  struct HostPipe {
+    cudaStream_t h2d = nullptr, comp = nullptr, d2h = nullptr;
+    cudaEvent_t evH2D[2] = {nullptr, nullptr}, evComp[2] = {nullptr, nullptr}, evD2H[2] = {nullptr, nullptr};
+    sb::DevBuf<float> A[2], B[2], P[2];
+    ~HostPipe() {
+      for (int i = 0; i < 2; ++i) {
+        if (evH2D[i]) cudaEventDestroy(evH2D[i]);
+        if (evComp[i]) cudaEventDestroy(evComp[i]);
+        if (evD2H[i]) cudaEventDestroy(evD2H[i]);
+      }
+      if (h2d) cudaStreamDestroy(h2d);
+      if (comp) cudaStreamDestroy(comp);
+      if (d2h) cudaStreamDestroy(d2h);
+    }
+  };
+  mutable std::unique_ptr<HostPipe> pipe;
 };
 
 namespace sb {

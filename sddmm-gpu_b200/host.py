@@ -201,6 +201,18 @@ def sddmm_gpu(A, B, rphm_or_layout, P=None):
     return P, None
 
 
+def sddmm_gpu_async(A, B, layout, P, slot):
+    """Streaming twin of the host-buffer sddmm_gpu: enqueue H2D(A,B) -> pass -> D2H(P) on `slot` (0/1) and
+    return immediately; `sddmm_gpu_sync(layout)` waits.  A, B, P: page-locked numpy arrays."""
+    lay = layout.layout() if hasattr(layout, "layout") else layout
+    check(_lib.lib().sddmm_run_host_async(lay.handle, A.shape[1], A.ctypes.data, B.ctypes.data, P.ctypes.data, int(slot)))
+
+
+def sddmm_gpu_sync(layout):
+    lay = layout.layout() if hasattr(layout, "layout") else layout
+    check(_lib.lib().sddmm_host_sync(lay.handle))
+
+
 def sddmm_gpu_timed(A, B, layout, P, warmup=3, iters=10):
     """Mean device milliseconds per pass (dense, residual, both concurrently) -- the reference's
     `sddmmTime_` loop (src/sddmmKernel.cu:2561-2659) with a warm-up."""

@@ -259,3 +259,30 @@ def test_cli_binary_matches_reference_contract(tmp_path):
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_pipelined_host_api_equals_synchronous(torch_mod):
+    """sddmm_run_host_async (two slots) returns exactly what sddmm_run_host returns, for every batch."""
+    torch = torch_mod
+    S = gen.bernoulli_mask(2048, 1024, 0.95, 3)
+    K = 64
+    lay = pkg.BSMR(0.3, 0.3, S, block_size=16).layout()
+    outs, refs = [], []
+    bufs = [torch.zeros(S.nnz, dtype=torch.float32).pin_memory() for _ in range(2)]
+    ins = []
+    for i in range(5):
+        A, B = gen.dense_operands(S.M, S.N, K, seed_a=100 + i, seed_b=200 + i)
+        ins.append((torch.from_numpy(A).pin_memory(), torch.from_numpy(B).pin_memory()))
+        refs.append(pkg.sddmm_gpu(A, B, lay)[0].copy())
+    for i, (a, b) in enumerate(ins):
+        if i >= 2:
+            pkg.sddmm_gpu_sync(lay)  # slot reuse: previous result must have been consumed
+            outs.append(bufs[i & 1].numpy().copy()) if False else None
+        pkg.sddmm_gpu_async(a.numpy(), b.numpy(), lay, bufs[i & 1].numpy(), i & 1)
+        pkg.sddmm_gpu_sync(lay)
+        assert np.array_equal(bufs[i & 1].numpy(), refs[i]), i
+    # back-to-back without intermediate syncs: last two results
+    for i in (3, 4):
+        pkg.sddmm_gpu_async(ins[i][0].numpy(), ins[i][1].numpy(), lay, bufs[i & 1].numpy(), i & 1)
+    pkg.sddmm_gpu_sync(lay)
+    assert np.array_equal(bufs[1].numpy(), refs[3]) and np.array_equal(bufs[0].numpy(), refs[4])
