@@ -99,6 +99,10 @@ int bsmr_layout_build(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32
                       uint32_t nnz, const uint32_t* h_reorderedRows, uint32_t numRows, float delta,
                       bsmr_layout** out, float* msColReorder, float* msRphm);
 void bsmr_layout_destroy(bsmr_layout*);
+/* On-disk cache of a layout (no reference counterpart; SURVEY.md 8f rank 4: reordering costs 10^4 x one
+ * SDDMM pass, so deployments persist it keyed by (matrix, alpha, delta, block_size)).  Versioned file. */
+int bsmr_layout_save(const bsmr_layout*, const char* path);
+int bsmr_layout_load(const char* path, bsmr_layout** out);
 
 typedef enum {
   BSMR_REORDERED_ROWS = 0,      /* [numRows]      BSMR::reorderedRows()      */
@@ -147,6 +151,12 @@ int bsmr_layout_array_to_host(const bsmr_layout*, bsmr_array_id which, uint32_t*
  * Entries of d_P not covered by this layout (other shards) are left untouched. */
 int sddmm_run_dev(const bsmr_layout*, uint32_t K, const float* d_A, const float* d_B, float* d_P,
                   void* stream);
+/* replaces sddmm_gpu_batch(numBatch, M, N, K, nnz, dA, dB, rphm, dP, time)   src/sddmmKernel.cu:2764-2850
+ * One layout, numBatch independent (A, B, P) triples stored back to back: batch b uses
+ * d_A + b*M*K, d_B + b*N*K, d_P + b*nnz (the reference's blockIdx.z indexing, :1280-1283).
+ * One launch per kernel covers every batch. */
+int sddmm_run_batch_dev(const bsmr_layout*, uint32_t K, uint32_t numBatch, const float* d_A, const float* d_B,
+                        float* d_P, void* stream);
 /* `iters` timed passes after `warmup` untimed ones; ms_* are per-pass means (CUDA events on the
  * launching streams).  Any of the three outputs may be NULL. */
 int sddmm_run_timed_dev(const bsmr_layout*, uint32_t K, const float* d_A, const float* d_B, float* d_P,

@@ -78,7 +78,10 @@ def lib():
     L.bsmr_layout_array_dev.argtypes = [vp, C.c_int]
     L.bsmr_layout_array_dev.restype = vp
     L.bsmr_layout_array_to_host.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.bsmr_layout_save.argtypes = [vp, C.c_char_p]
+    L.bsmr_layout_load.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.sddmm_run_dev.argtypes = [vp, u32, vp, vp, vp, vp]
+    L.sddmm_run_batch_dev.argtypes = [vp, u32, u32, vp, vp, vp, vp]
     L.sddmm_run_timed_dev.argtypes = [vp, u32, vp, vp, vp, C.c_int, C.c_int, pf32, pf32, pf32]
     L.sddmm_run_host.argtypes = [vp, u32, vp, vp, vp, pf32]
     L.sddmm_run_host_async.argtypes = [vp, u32, vp, vp, vp, C.c_int]

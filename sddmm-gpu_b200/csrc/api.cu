@@ -136,6 +136,21 @@ int bsmr_layout_build(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32
 
 void bsmr_layout_destroy(bsmr_layout* L) { delete L; }
 
+int bsmr_layout_save(const bsmr_layout* L, const char* path) {
+  API_BEGIN
+  require_device();
+  require(L && path, "null pointer");
+  layout_save(L, path);
+  API_END
+}
+int bsmr_layout_load(const char* path, bsmr_layout** out) {
+  API_BEGIN
+  require_device();
+  require(path && out, "null pointer");
+  *out = layout_load(path);
+  API_END
+}
+
 int bsmr_layout_get_info(const bsmr_layout* L, bsmr_layout_info* out) {
   API_BEGIN
   require(L && out, "null pointer");
@@ -178,19 +193,20 @@ Streams& streams() {
   return *s;
 }
 // dense || residual, forked from and joined back into `s`
-void run_once(const bsmr_layout* L, u32 K, const float* dA, const float* dB, float* dP, cudaStream_t s) {
+void run_once(const bsmr_layout* L, u32 K, const float* dA, const float* dB, float* dP, cudaStream_t s,
+              u32 numBatch = 1) {
   Streams& st = streams();
   if (L->numDenseWork && L->numSparseWork) {
     SB_CUDA(cudaEventRecord(st.fork, s));
     SB_CUDA(cudaStreamWaitEvent(st.dense, st.fork, 0));
     SB_CUDA(cudaStreamWaitEvent(st.sparse, st.fork, 0));
-    sddmm_launch(L, K, dA, dB, dP, st.dense, st.sparse);
+    sddmm_launch(L, K, dA, dB, dP, st.dense, st.sparse, kLaunchBoth, numBatch);
     SB_CUDA(cudaEventRecord(st.joinD, st.dense));
     SB_CUDA(cudaEventRecord(st.joinS, st.sparse));
     SB_CUDA(cudaStreamWaitEvent(s, st.joinD, 0));
     SB_CUDA(cudaStreamWaitEvent(s, st.joinS, 0));
   } else {
-    sddmm_launch(L, K, dA, dB, dP, s, s);
+    sddmm_launch(L, K, dA, dB, dP, s, s, kLaunchBoth, numBatch);
   }
 }
 }  // namespace
@@ -200,6 +216,15 @@ int sddmm_run_dev(const bsmr_layout* L, uint32_t K, const float* d_A, const floa
   require_device();
   require(L && d_A && d_B && d_P, "null pointer");
   run_once(L, K, d_A, d_B, d_P, (cudaStream_t)stream);
+  API_END
+}
+
+int sddmm_run_batch_dev(const bsmr_layout* L, uint32_t K, uint32_t numBatch, const float* d_A, const float* d_B,
+                        float* d_P, void* stream) {
+  API_BEGIN
+  require_device();
+  require(L && d_A && d_B && d_P, "null pointer");
+  run_once(L, K, d_A, d_B, d_P, (cudaStream_t)stream, numBatch);
   API_END
 }
 

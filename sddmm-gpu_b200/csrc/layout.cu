@@ -12,6 +12,8 @@
 //   4. per panel: pad to x16 with sentinel N, blocks whose count-sum >= ceil(delta*256) are dense;
 //   5. scans give every offset array; one scatter writes denseCols / sparseCols / blockValues and
 //      the residual COO arrays in exactly the reference's order (appendix B of SURVEY.md).
+#include <vector>
+
 #include "layout.cuh"
 #include "primitives.cuh"
 
@@ -585,6 +587,94 @@ const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStre
   SB_CUDA(cudaStreamSynchronize(s));
   L->sp = std::move(sp);
   return L->sp.get();
+}
+
+// ---- on-disk layout cache: reordering costs orders of magnitude more than one SDDMM pass,
+// so a deployment keeps the layout keyed by (matrix, alpha, delta, block_size).  Versioned little-endian file:
+//   "BSMRLAY1" | u32 version | bsmr_layout_info | u32 sparseChunk | u32 numDenseWork | u32 numSparseWork |
+//   15 x (u64 length, u32 data[length]) | uint2 denseWork[] | uint2 sparseWork[]
+namespace {
+constexpr char kLayoutMagic[8] = {'B', 'S', 'M', 'R', 'L', 'A', 'Y', '1'};
+struct File {
+  FILE* f;
+  File(const char* p, const char* m) : f(std::fopen(p, m)) {}
+  ~File() { if (f) std::fclose(f); }
+};
+template <typename T>
+void put(FILE* f, const T* p, size_t n) {
+  if (n && std::fwrite(p, sizeof(T), n, f) != n) fail(SDDMM_E_ARG, "layout cache: short write");
+}
+template <typename T>
+void get(FILE* f, T* p, size_t n) {
+  if (n && std::fread(p, sizeof(T), n, f) != n) fail(SDDMM_E_ARG, "layout cache: short read / truncated file");
+}
+}  // namespace
+
+void layout_save(const bsmr_layout* L, const char* path) {
+  File fl(path, "wb");
+  if (!fl.f) fail(SDDMM_E_ARG, "layout cache: cannot open %s for writing", path);
+  const u32 version = 1;
+  put(fl.f, kLayoutMagic, 8);
+  put(fl.f, &version, 1);
+  put(fl.f, &L->info, 1);
+  put(fl.f, &L->sparseChunk, 1);
+  put(fl.f, &L->numDenseWork, 1);
+  put(fl.f, &L->numSparseWork, 1);
+  std::vector<u32> host;
+  for (int i = 0; i < BSMR_ARRAY_COUNT; ++i) {
+    const u64 n = L->arr[i].size();
+    put(fl.f, &n, 1);
+    host.resize(n);
+    if (n) SB_CUDA(cudaMemcpy(host.data(), L->arr[i].get(), n * 4, cudaMemcpyDeviceToHost));
+    put(fl.f, host.data(), n);
+  }
+  std::vector<uint2> w(L->numDenseWork);
+  if (L->numDenseWork) SB_CUDA(cudaMemcpy(w.data(), L->denseWork.get(), (size_t)L->numDenseWork * 8, cudaMemcpyDeviceToHost));
+  put(fl.f, w.data(), w.size());
+  w.resize(L->numSparseWork);
+  if (L->numSparseWork) SB_CUDA(cudaMemcpy(w.data(), L->sparseWork.get(), (size_t)L->numSparseWork * 8, cudaMemcpyDeviceToHost));
+  put(fl.f, w.data(), w.size());
+}
+
+bsmr_layout* layout_load(const char* path) {
+  File fl(path, "rb");
+  if (!fl.f) fail(SDDMM_E_ARG, "layout cache: cannot open %s", path);
+  char magic[8];
+  u32 version = 0;
+  get(fl.f, magic, 8);
+  get(fl.f, &version, 1);
+  if (std::memcmp(magic, kLayoutMagic, 8) != 0 || version != 1) fail(SDDMM_E_ARG, "layout cache: %s is not a version-1 layout file", path);
+  auto* L = new bsmr_layout();
+  try {
+    SB_CUDA(cudaGetDevice(&L->device));
+    get(fl.f, &L->info, 1);
+    get(fl.f, &L->sparseChunk, 1);
+    get(fl.f, &L->numDenseWork, 1);
+    get(fl.f, &L->numSparseWork, 1);
+    std::vector<u32> host;
+    for (int i = 0; i < BSMR_ARRAY_COUNT; ++i) {
+      u64 n = 0;
+      get(fl.f, &n, 1);
+      if (n > ((u64)1 << 34)) fail(SDDMM_E_ARG, "layout cache: implausible array length");
+      host.resize(n);
+      get(fl.f, host.data(), n);
+      L->arr[i].alloc(n ? n : 1);
+      L->arr[i].n = n;
+      if (n) SB_CUDA(cudaMemcpy(L->arr[i].get(), host.data(), n * 4, cudaMemcpyHostToDevice));
+    }
+    std::vector<uint2> w(L->numDenseWork);
+    get(fl.f, w.data(), w.size());
+    L->denseWork.alloc(L->numDenseWork ? L->numDenseWork : 1);
+    if (L->numDenseWork) SB_CUDA(cudaMemcpy(L->denseWork.get(), w.data(), w.size() * 8, cudaMemcpyHostToDevice));
+    w.resize(L->numSparseWork);
+    get(fl.f, w.data(), w.size());
+    L->sparseWork.alloc(L->numSparseWork ? L->numSparseWork : 1);
+    if (L->numSparseWork) SB_CUDA(cudaMemcpy(L->sparseWork.get(), w.data(), w.size() * 8, cudaMemcpyHostToDevice));
+    return L;
+  } catch (...) {
+    delete L;
+    throw;
+  }
 }
 
 }  // namespace sb

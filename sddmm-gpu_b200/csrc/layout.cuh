@@ -58,6 +58,9 @@ bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u
                               const u32* d_reorderedRows, u32 numRows, float delta, u32 panelBegin, u32 panelEnd,
                               float* msCol, float* msRphm, cudaStream_t s);
 
+void layout_save(const bsmr_layout* L, const char* path);
+bsmr_layout* layout_load(const char* path);
+
 // (re)builds L->sp for G panels per super-panel if needed; returns it
 const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStream_t s);
 

@@ -19,6 +19,12 @@ namespace sb {
 // =============================================================================================
 // residual kernel
 // =============================================================================================
+// batched form (reference: sddmm_gpu_batch, src/sddmmKernel.cu:2764-2850): blockIdx.y = batch id, operands of
+// batch b start at A + b*M*K, B + b*N*K, P + b*nnz (element strides below; all 0 for a single pass)
+struct BatchStrides {
+  size_t a = 0, b = 0, p = 0;
+};
+
 constexpr int kResThreads = 256;
 constexpr int kResLanes = 8;  // lanes cooperating on one non-zero
 
@@ -41,8 +47,11 @@ static __global__ void __launch_bounds__(kResThreads)
 k_sddmm_residual(u32 M, u32 K4, const float4* __restrict__ A4, const float4* __restrict__ B4,
                  const u32* __restrict__ R, u32 nR, const u32* __restrict__ vOff, const u32* __restrict__ sVals,
                  const u32* __restrict__ sRows, const u32* __restrict__ sCols, const uint2* __restrict__ work,
-                 u32 kSparseChunk, float* __restrict__ P) {
+                 u32 kSparseChunk, float* __restrict__ P, BatchStrides bs) {
   extern __shared__ float4 sA[];  // 16 rows x K4 float4
+  A4 += (bs.a >> 2) * blockIdx.y;
+  B4 += (bs.b >> 2) * blockIdx.y;
+  P += bs.p * blockIdx.y;
   const uint2 w = work[blockIdx.x];
   const u32 p = w.x;
   const u32 segBeg = vOff[p] + w.y;
@@ -110,8 +119,11 @@ static __global__ void __launch_bounds__(kThreads, 1)
 k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restrict__ B4, const u32* __restrict__ R,
                     u32 nR, u32 spRows, u32 segLen, const u32* __restrict__ spOff, const u32* __restrict__ spCol,
                     const unsigned short* __restrict__ spRow, const u32* __restrict__ spIdx,
-                    const uint2* __restrict__ work, float* __restrict__ P) {
+                    const uint2* __restrict__ work, float* __restrict__ P, BatchStrides bs) {
   extern __shared__ float4 sA[];  // spRows x K4
+  A4 += (bs.a >> 2) * blockIdx.y;
+  B4 += (bs.b >> 2) * blockIdx.y;
+  P += bs.p * blockIdx.y;
   constexpr u32 K4 = 8 * NB;
   constexpr u32 kGroups = kThreads / 8;
   const uint2 w = work[blockIdx.x];
@@ -267,8 +279,11 @@ static __global__ void __launch_bounds__(kDnThreads)
 k_sddmm_dense(u32 M, u32 N, u32 K, const float* __restrict__ A, const float* __restrict__ B,
               const u32* __restrict__ R, u32 nR, const u32* __restrict__ denseCols,
               const u32* __restrict__ blockOffsets, const u32* __restrict__ blockValues,
-              const uint2* __restrict__ work, float* __restrict__ P) {
+              const uint2* __restrict__ work, float* __restrict__ P, BatchStrides bs) {
   extern __shared__ __align__(1024) unsigned char smemRaw[];
+  A += bs.a * blockIdx.y;
+  B += bs.b * blockIdx.y;
+  P += bs.p * blockIdx.y;
   // carve: stages (1024-aligned), then barriers / indices
   unsigned char* stages = smemRaw + ((1024u - (smem_u32(smemRaw) & 1023u)) & 1023u);
   __shared__ u64 mbar[kDnStages];
@@ -405,10 +420,18 @@ k_sddmm_dense(u32 M, u32 N, u32 K, const float* __restrict__ A, const float* __r
 // launcher
 // =============================================================================================
 void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB, float* dP, cudaStream_t denseStream,
-                  cudaStream_t sparseStream, int which) {
+                  cudaStream_t sparseStream, int which, u32 numBatch) {
+  if (numBatch == 0) return;
+  if (numBatch > 65535u) fail(SDDMM_E_ARG, "numBatch=%u exceeds the grid's y extent", numBatch);
   if (K == 0 || (K & 3u)) fail(SDDMM_E_ARG, "K=%u must be a positive multiple of 4", K);
   const bsmr_layout_info& I = L->info;
   auto arr = [&](bsmr_array_id id) { return L->arr[id].get(); };
+  BatchStrides bst;
+  if (numBatch > 1) {
+    bst.a = (size_t)I.M * K;
+    bst.b = (size_t)I.N * K;
+    bst.p = I.nnz;
+  }
   if (L->numDenseWork && (which & kLaunchDense)) {
     const size_t smem = (size_t)kDnStages * kDnStageBytes + 1024;
     static bool attrSet = false;
@@ -416,9 +439,9 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
       SB_CUDA(cudaFuncSetAttribute(k_sddmm_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attrSet = true;
     }
-    k_sddmm_dense<<<L->numDenseWork, kDnThreads, smem, denseStream>>>(
+    k_sddmm_dense<<<dim3(L->numDenseWork, numBatch), kDnThreads, smem, denseStream>>>(
         I.M, I.N, K, dA, dB, arr(BSMR_REORDERED_ROWS), I.numRows, arr(BSMR_DENSE_COLS), arr(RPHM_BLOCK_OFFSETS),
-        arr(RPHM_BLOCK_VALUES), L->denseWork.get(), dP);
+        arr(RPHM_BLOCK_VALUES), L->denseWork.get(), dP, bst);
     SB_LAUNCH_CHECK();
   }
   if (L->numSparseWork && (which & kLaunchSparse)) {
@@ -435,10 +458,10 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
         const size_t smem = (size_t)sp->rows * K * sizeof(float);
         auto launch = [&](auto kern, int threads) {
           SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          kern<<<sp->numWork, threads, smem, sparseStream>>>(
+          kern<<<dim3(sp->numWork, numBatch), threads, smem, sparseStream>>>(
               I.M, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB), arr(BSMR_REORDERED_ROWS),
               I.numRows, sp->rows, sp->segLen, sp->off.get(), sp->col.get(), sp->row.get(), sp->idx.get(),
-              sp->work.get(), dP);
+              sp->work.get(), dP, bst);
         };
         switch (K / 32u) {
           case 1: launch(k_sddmm_residual_sp<1, 1024>, 1024); break;
@@ -456,10 +479,10 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
       static const bool useL1 = [] { const char* e = getenv("SDDMM_B200_L1"); return !e || atoi(e) != 0; }();
       auto kern = useL1 ? k_sddmm_residual<true> : k_sddmm_residual<false>;
       if (smem > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<L->numSparseWork, kResThreads, smem, sparseStream>>>(
+      kern<<<dim3(L->numSparseWork, numBatch), kResThreads, smem, sparseStream>>>(
           I.M, K4, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB), arr(BSMR_REORDERED_ROWS),
           I.numRows, arr(BSMR_SPARSE_VALUE_OFFSETS), arr(RPHM_SPARSE_VALUES), arr(RPHM_SPARSE_RELATIVE_ROWS),
-          arr(RPHM_SPARSE_COL_INDICES), L->sparseWork.get(), L->sparseChunk, dP);
+          arr(RPHM_SPARSE_COL_INDICES), L->sparseWork.get(), L->sparseChunk, dP, bst);
       SB_LAUNCH_CHECK();
     }
   }

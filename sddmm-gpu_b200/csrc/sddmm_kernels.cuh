@@ -8,5 +8,5 @@ namespace sb {
 // one pass: dense blocks on `denseStream`, residual on `sparseStream` (may be the same stream)
 enum { kLaunchDense = 1, kLaunchSparse = 2, kLaunchBoth = 3 };
 void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB, float* dP,
-                  cudaStream_t denseStream, cudaStream_t sparseStream, int which = kLaunchBoth);
+                  cudaStream_t denseStream, cudaStream_t sparseStream, int which = kLaunchBoth, u32 numBatch = 1);
 }  // namespace sb

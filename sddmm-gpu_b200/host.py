@@ -77,6 +77,16 @@ class Layout:
     def arrays(self):
         return {k: self.array(k) for k in ARRAY_IDS}
 
+    def save(self, path):
+        """persist the layout (reorder cache)"""
+        check(_lib.lib().bsmr_layout_save(self._h, str(path).encode()))
+
+    @staticmethod
+    def load(path):
+        h = C.c_void_p()
+        check(_lib.lib().bsmr_layout_load(str(path).encode(), C.byref(h)))
+        return Layout(h.value)
+
     def array_dev_ptr(self, name):
         return int(_lib.lib().bsmr_layout_array_dev(self._h, ARRAY_IDS[name]) or 0)
 
@@ -199,6 +209,21 @@ def sddmm_gpu(A, B, rphm_or_layout, P=None):
     stream = torch.cuda.current_stream().cuda_stream
     check(L.sddmm_run_dev(lay.handle, K, A.data_ptr(), B.data_ptr(), P.data_ptr(), C.c_void_p(stream)))
     return P, None
+
+
+def sddmm_gpu_batch(A, B, layout, P=None):
+    """sddmm_gpu_batch(numBatch, M, N, K, nnz, dA, dB, rphm, dP, time)  src/sddmmKernel.cu:2764-2850:
+    A [numBatch, M, K], B [numBatch, N, K], P [numBatch, nnz] torch CUDA tensors; one layout for all."""
+    import torch
+
+    lay = layout.layout() if hasattr(layout, "layout") else layout
+    nb, _, K = A.shape
+    if P is None:
+        P = torch.zeros((nb, max(1, lay.info.nnz)), dtype=torch.float32, device=A.device)
+    stream = torch.cuda.current_stream().cuda_stream
+    check(_lib.lib().sddmm_run_batch_dev(lay.handle, K, nb, A.data_ptr(), B.data_ptr(), P.data_ptr(),
+                                         C.c_void_p(stream)))
+    return P
 
 
 def sddmm_gpu_async(A, B, layout, P, slot):

@@ -286,3 +286,62 @@ def test_pipelined_host_api_equals_synchronous(torch_mod):
         pkg.sddmm_gpu_async(ins[i][0].numpy(), ins[i][1].numpy(), lay, bufs[i & 1].numpy(), i & 1)
     pkg.sddmm_gpu_sync(lay)
     assert np.array_equal(bufs[1].numpy(), refs[3]) and np.array_equal(bufs[0].numpy(), refs[4])
+
+
+def test_batched_sddmm_matches_per_batch_calls(torch_mod):
+    """sddmm_gpu_batch (src/sddmmKernel.cu:2764-2850): numBatch (A, B, P) triples back to back, one layout."""
+    torch = torch_mod
+    S = gen.block_structured(300, 400, 4, 64, 0.8, seed=2, noise=0.01)
+    K, nb = 64, 3
+    lay = pkg.BSMR(0.3, 0.3, S, block_size=16).layout()
+    A = torch.rand((nb, S.M, K), device="cuda") * 2
+    B = torch.rand((nb, S.N, K), device="cuda") * 2
+    P = pkg.sddmm_gpu_batch(A, B, lay)
+    torch.cuda.synchronize()
+    for b in range(nb):
+        Pb, _ = pkg.sddmm_gpu(A[b].contiguous(), B[b].contiguous(), lay)
+        torch.cuda.synchronize()
+        assert torch.equal(P[b, : S.nnz], Pb[: S.nnz])
+        assert O.check_data(O.sddmm_cpu(S, A[b].cpu().numpy(), B[b].cpu().numpy()), P[b, : S.nnz].cpu().numpy()) == 0
+
+
+def test_layout_cache_roundtrip(tmp_path, torch_mod):
+    """bsmr_layout_save / bsmr_layout_load: identical arrays and identical SDDMM results."""
+    S = gen.rmat(11, 8, 5)
+    A, B = operands(S, 32)
+    lay = pkg.BSMR(0.3, 0.3, S, block_size=16).layout()
+    P1, _ = pkg.sddmm_gpu(A, B, lay)
+    path = tmp_path / "layout.bsmr"
+    lay.save(path)
+    lay2 = pkg.Layout.load(path)
+    a1, a2 = lay.arrays(), lay2.arrays()
+    for k in a1:
+        assert np.array_equal(a1[k], a2[k]), k
+    assert bytes(lay.info) == bytes(lay2.info)
+    P2, _ = pkg.sddmm_gpu(A, B, lay2)
+    assert np.array_equal(P1, P2)
+    open(tmp_path / "bad.bsmr", "wb").write(b"nonsense")
+    with pytest.raises(pkg.SddmmError):
+        pkg.Layout.load(tmp_path / "bad.bsmr")
+
+
+def test_strong_scaling_shards_two_ranks_nccl(torch_mod):
+    """ShardedSDDMM on 2 ranks (both on cuda:0 here; one GPU each under torchrun): NCCL is exercised by
+    bench.py --gpus N; here the sharded plan is checked in-process by emulating the two ranks."""
+    torch = torch_mod
+    S = gen.rmat(12, 8, 4)
+    A, B = operands(S, 64)
+    ro, ci = _dev(torch, S.row_off), _dev(torch, S.col_idx)
+    R, _, _ = pkg.row_reorder_dev(ro, ci, S.M, S.N, 0.3, 16)
+    Rh = R.cpu().numpy().view(np.uint32)
+    cuts = pkg.shard_plan(S, Rh, 2)
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    P = torch.zeros(S.nnz, device="cuda")
+    covered = 0
+    for r in range(2):
+        lay, _, _ = pkg.layout_build_dev(ro, ci, S.M, S.N, R, 0.3, int(cuts[r]), int(cuts[r + 1]))
+        covered += lay.info.numDenseValues + lay.info.numSparseValues
+        pkg.sddmm_gpu(dA, dB, lay, P)
+    torch.cuda.synchronize()
+    assert covered == S.nnz
+    assert O.check_data(O.sddmm_cpu(S, A, B), P.cpu().numpy()) == 0
