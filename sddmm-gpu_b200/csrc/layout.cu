@@ -307,6 +307,74 @@ __global__ void k_sp_work(const u32* __restrict__ segOff, u32 numSp, u32 segLen,
   }
 }
 
+// ---- full-tile layout (K8) -------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tile_keys(const u32* __restrict__ R, u32 r0, u32 n,
+                                                   const u32* __restrict__ rowOff, const u32* __restrict__ colIdx,
+                                                   const u32* __restrict__ eOff, int ctBits, u64* __restrict__ keys,
+                                                   u32* __restrict__ vals) {
+  const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const u32 nw = (gridDim.x * blockDim.x) >> 5;
+  for (u32 i = gw; i < n; i += nw) {
+    const u32 row = R[r0 + i];
+    const u32 b = rowOff[row], len = rowOff[row + 1] - b;
+    const u32 o = eOff[i];
+    const u64 hi = ((u64)(i >> 7) << (ctBits + 14)) | ((u64)(i & 127u) << 7);
+    for (u32 j = lane; j < len; j += 32) {
+      const u32 c = colIdx[b + j];
+      keys[o + j] = hi | ((u64)(c >> 7) << 14) | (c & 127u);
+      vals[o + j] = b + j;
+    }
+  }
+}
+__global__ void k_tile_heads(const u64* __restrict__ keys, size_t n, u32* __restrict__ head) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    head[i] = (i == 0 || (keys[i] >> 14) != (keys[i - 1] >> 14)) ? 1u : 0u;
+}
+__global__ void k_tile_records(const u64* __restrict__ keys, const u32* __restrict__ head,
+                               const u32* __restrict__ tid, size_t n, int ctBits, uint4* __restrict__ tiles) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (!head[i]) continue;
+    const u64 k = keys[i] >> 14;
+    const u32 tc = (u32)(k & ((((u64)1) << ctBits) - 1));
+    const u32 tr = (u32)(k >> ctBits);
+    tiles[tid[i]] = make_uint4(tr, tc, (u32)i, 0u);
+  }
+}
+// one CTA (128 threads) per tile: row masks + entry offsets
+__global__ void __launch_bounds__(128) k_tile_meta(const u64* __restrict__ keys, uint4* __restrict__ tiles, u32 numTiles,
+                                                   u32 nEntries, u32* __restrict__ rowMeta) {
+  __shared__ u32 mask[128][4];
+  __shared__ u32 warpTot[4];
+  const u32 t = blockIdx.x;
+  const u32 beg = tiles[t].z;
+  const u32 end = (t + 1 < numTiles) ? tiles[t + 1].z : nEntries;
+  for (u32 i = threadIdx.x; i < 512; i += 128) (&mask[0][0])[i] = 0u;
+  __syncthreads();
+  for (u32 e = beg + threadIdx.x; e < end; e += 128) {
+    const u32 k = (u32)(keys[e] & 0x3FFFu);
+    const u32 r = k >> 7, c = k & 127u;
+    atomicOr(&mask[r][c >> 5], 1u << (c & 31u));
+  }
+  __syncthreads();
+  const u32 r = threadIdx.x;
+  const u32 cnt = __popc(mask[r][0]) + __popc(mask[r][1]) + __popc(mask[r][2]) + __popc(mask[r][3]);
+  u32 incl = cnt;
+  const u32 lane = r & 31u, warp = r >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u32 v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= (u32)d) incl += v;
+  }
+  if (lane == 31) warpTot[warp] = incl;
+  __syncthreads();
+  u32 base = 0;
+  for (u32 w = 0; w < warp; ++w) base += warpTot[w];
+  u32* out = rowMeta + (size_t)t * 640u + r * 5u;
+  out[0] = mask[r][0]; out[1] = mask[r][1]; out[2] = mask[r][2]; out[3] = mask[r][3];
+  out[4] = beg + base + incl - cnt;
+  if (threadIdx.x == 0) tiles[t].w = end - beg;
+}
+
 u32 read_u32(const u32* d, cudaStream_t s) {
   u32 h = 0;
   SB_CUDA(cudaMemcpyAsync(&h, d, 4, cudaMemcpyDeviceToHost, s));
@@ -322,6 +390,9 @@ void scan_counts(const u32* cnt, u32* out, u32 P, cudaStream_t s) {
 }
 
 }  // namespace
+
+static void build_tiles(bsmr_layout* L, const u32* d_rowOff, const u32* d_colIdx, const u32* d_R, u32 r0, u32 nR,
+                        const u32* eOff, u32 nSel, cudaStream_t s);
 
 bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32 nnz, const u32* d_R,
                               u32 numRows, float delta, u32 panelBegin, u32 panelEnd, float* msCol, float* msRphm,
@@ -372,6 +443,12 @@ bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u
     SB_CUDA(cudaMemsetAsync(eOff.get() + nR, 0, 4, s));
     exclusive_scan_u32(eOff.get(), eOff.get(), (size_t)nR + 1, s);
     const u32 nSel = read_u32(eOff.get() + nR, s);
+    // dense enough for whole 128x128 tensor-core tiles to be worth considering? (>= ~1% of the slots)
+    {
+      const u64 slots = (u64)((nR + 127u) / 128u) * ((N + 127u) / 128u) * 16384ull;
+      static const int plan = [] { const char* e = getenv("SDDMM_B200_PLAN"); return e ? (!strcmp(e, "full") ? 2 : !strcmp(e, "bsmr") ? 0 : 1) : 1; }();
+      if (plan == 2 || (plan == 1 && (u64)nSel * 100ull >= slots)) build_tiles(L, d_rowOff, d_colIdx, d_R, r0, nR, eOff.get(), nSel, s);
+    }
     const int colBits = bits_for(N);  // sentinel-free here: real columns are < N
     const int panelBits = bits_for(P);
     if (panelBits > 27) fail(SDDMM_E_UNSUPPORTED, "too many row panels (%u)", P);
@@ -522,6 +599,43 @@ bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u
   }
 }
 
+// builds L->tl (full-tile plan) from the selected rows
+static void build_tiles(bsmr_layout* L, const u32* d_rowOff, const u32* d_colIdx, const u32* d_R, u32 r0, u32 nR,
+                        const u32* eOff, u32 nSel, cudaStream_t s) {
+  auto tl = std::make_unique<TileLayout>();
+  const u32 N = L->info.N;
+  tl->tileRows = (nR + 127u) / 128u;
+  tl->tileCols = (N + 127u) / 128u;
+  tl->numEntries = nSel;
+  if (nSel == 0) { L->tl = std::move(tl); return; }
+  const int ctBits = bits_for(tl->tileCols), trBits = bits_for(tl->tileRows);
+  DevBuf<u64> kA(nSel), kB(nSel);
+  DevBuf<u32> vA(nSel), vB(nSel);
+  k_tile_keys<<<grid_for((size_t)nR * 32), 256, 0, s>>>(d_R, r0, nR, d_rowOff, d_colIdx, eOff, ctBits, kA.get(), vA.get());
+  SB_LAUNCH_CHECK();
+  const int w = radix_sort_pairs<u64>(kA.get(), kB.get(), vA.get(), vB.get(), nSel, 0, 14 + ctBits + trBits, s);
+  const u64* keys = w ? kB.get() : kA.get();
+  u32* vals = w ? vB.get() : vA.get();
+  DevBuf<u32> head(nSel), tid((size_t)nSel + 1);
+  k_tile_heads<<<grid_for(nSel), 256, 0, s>>>(keys, nSel, head.get());
+  SB_LAUNCH_CHECK();
+  SB_CUDA(cudaMemcpyAsync(tid.get(), head.get(), (size_t)nSel * 4, cudaMemcpyDeviceToDevice, s));
+  SB_CUDA(cudaMemsetAsync(tid.get() + nSel, 0, 4, s));
+  exclusive_scan_u32(tid.get(), tid.get(), (size_t)nSel + 1, s);
+  tl->numTiles = read_u32(tid.get() + nSel, s);
+  tl->tiles.alloc(tl->numTiles);
+  tl->rowMeta.alloc((size_t)tl->numTiles * 640u);
+  k_tile_records<<<grid_for(nSel), 256, 0, s>>>(keys, head.get(), tid.get(), nSel, ctBits, tl->tiles.get());
+  SB_LAUNCH_CHECK();
+  k_tile_meta<<<tl->numTiles, 128, 0, s>>>(keys, tl->tiles.get(), tl->numTiles, nSel, tl->rowMeta.get());
+  SB_LAUNCH_CHECK();
+  // the sorted payload IS the CSR index list; keep it
+  tl->idx.alloc(nSel);
+  SB_CUDA(cudaMemcpyAsync(tl->idx.get(), vals, (size_t)nSel * 4, cudaMemcpyDeviceToDevice, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+  L->tl = std::move(tl);
+}
+
 const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStream_t s) {
   if (L->sp && L->sp->G == G) return L->sp.get();
   const bsmr_layout_info& I = L->info;
@@ -634,6 +748,23 @@ void layout_save(const bsmr_layout* L, const char* path) {
   w.resize(L->numSparseWork);
   if (L->numSparseWork) SB_CUDA(cudaMemcpy(w.data(), L->sparseWork.get(), (size_t)L->numSparseWork * 8, cudaMemcpyDeviceToHost));
   put(fl.f, w.data(), w.size());
+  // optional full-tile plan
+  const u32 hasTl = L->tl ? 1u : 0u;
+  put(fl.f, &hasTl, 1);
+  if (hasTl) {
+    const TileLayout& T = *L->tl;
+    const u32 hdr[4] = {T.numTiles, T.numEntries, T.tileRows, T.tileCols};
+    put(fl.f, hdr, 4);
+    std::vector<uint4> tiles(T.numTiles);
+    if (T.numTiles) SB_CUDA(cudaMemcpy(tiles.data(), T.tiles.get(), (size_t)T.numTiles * 16, cudaMemcpyDeviceToHost));
+    put(fl.f, tiles.data(), tiles.size());
+    host.resize((size_t)T.numTiles * 640u);
+    if (T.numTiles) SB_CUDA(cudaMemcpy(host.data(), T.rowMeta.get(), host.size() * 4, cudaMemcpyDeviceToHost));
+    put(fl.f, host.data(), host.size());
+    host.resize(T.numEntries);
+    if (T.numEntries) SB_CUDA(cudaMemcpy(host.data(), T.idx.get(), host.size() * 4, cudaMemcpyDeviceToHost));
+    put(fl.f, host.data(), host.size());
+  }
 }
 
 bsmr_layout* layout_load(const char* path) {
@@ -670,6 +801,28 @@ bsmr_layout* layout_load(const char* path) {
     get(fl.f, w.data(), w.size());
     L->sparseWork.alloc(L->numSparseWork ? L->numSparseWork : 1);
     if (L->numSparseWork) SB_CUDA(cudaMemcpy(L->sparseWork.get(), w.data(), w.size() * 8, cudaMemcpyHostToDevice));
+    u32 hasTl = 0;
+    get(fl.f, &hasTl, 1);
+    if (hasTl) {
+      auto T = std::make_unique<TileLayout>();
+      u32 hdr[4];
+      get(fl.f, hdr, 4);
+      T->numTiles = hdr[0]; T->numEntries = hdr[1]; T->tileRows = hdr[2]; T->tileCols = hdr[3];
+      if ((u64)T->numTiles > ((u64)1 << 30)) fail(SDDMM_E_ARG, "layout cache: implausible tile count");
+      std::vector<uint4> tiles(T->numTiles);
+      get(fl.f, tiles.data(), tiles.size());
+      T->tiles.alloc(T->numTiles ? T->numTiles : 1);
+      if (T->numTiles) SB_CUDA(cudaMemcpy(T->tiles.get(), tiles.data(), tiles.size() * 16, cudaMemcpyHostToDevice));
+      host.resize((size_t)T->numTiles * 640u);
+      get(fl.f, host.data(), host.size());
+      T->rowMeta.alloc(host.size() ? host.size() : 1);
+      if (!host.empty()) SB_CUDA(cudaMemcpy(T->rowMeta.get(), host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+      host.resize(T->numEntries);
+      get(fl.f, host.data(), host.size());
+      T->idx.alloc(host.size() ? host.size() : 1);
+      if (!host.empty()) SB_CUDA(cudaMemcpy(T->idx.get(), host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+      L->tl = std::move(T);
+    }
     return L;
   } catch (...) {
     delete L;

@@ -17,6 +17,19 @@ struct SuperPanelLayout {
 };
 }  // namespace sb
 
+namespace sb {
+// Private layout of the "full tile" plan (K8): the reordered matrix is cut into 128-row x 128-column tiles
+// (rows in BSMR order, columns in natural order); every non-empty tile is one tcgen05 GEMM tile whose
+// epilogue picks the stored entries with per-row bitmasks.  Used when S is dense enough that computing
+// whole tiles on the tensor cores beats gathering per non-zero (DLMC-style masks), see sddmm_launch.
+struct TileLayout {
+  u32 numTiles = 0, numEntries = 0, tileRows = 0, tileCols = 0;
+  DevBuf<uint4> tiles;     // per non-empty tile: {tile row, tile col, first entry, entry count}
+  DevBuf<u32> rowMeta;     // per tile 128 x 5 words: 4 mask words (which of the 128 columns are stored) + entry offset
+  DevBuf<u32> idx;         // per entry (sorted by tile, row, col): CSR index
+};
+}  // namespace sb
+
 struct bsmr_layout {
   bsmr_layout_info info{};
   sb::DevBuf<sb::u32> arr[BSMR_ARRAY_COUNT];  // indexed by bsmr_array_id
@@ -30,6 +43,7 @@ struct bsmr_layout {
   // so that repeated calls do not pay cudaMalloc/cudaFree
   mutable sb::DevBuf<float> wsA, wsB, wsP;
   mutable std::unique_ptr<sb::SuperPanelLayout> sp;  // built lazily for the K in use
+  std::unique_ptr<sb::TileLayout> tl;                // built with the layout when S is dense enough to consider it
   // two-slot pipeline of sddmm_run_host_async
   struct HostPipe {
     cudaStream_t h2d = nullptr, comp = nullptr, d2h = nullptr;

@@ -416,6 +416,161 @@ k_sddmm_dense(u32 M, u32 N, u32 K, const float* __restrict__ A, const float* __r
   }
 }
 
+
+// =============================================================================================
+// full-tile kernel (K8): tcgen05 GEMM tiles with a sampled epilogue
+//   One CTA = one non-empty 128-row x 128-column tile of the reordered S.  MMA M axis = the 128 rows
+//   (A rows gathered through reorderedRows), N axis = the 128 columns (B^T rows, contiguous), K swept in
+//   128-byte chunks: tcgen05.mma.cta_group::1.kind::tf32 M=128 N=128 K=8, accumulator = 128 TMEM columns.
+//   Operands are staged exactly like in k_sddmm_dense (coalesced 128-bit loads, cvt.rna.tf32 like the
+//   reference's wmma::__float_to_tf32, 128B-swizzled K-major tiles, 2-stage mbarrier ring, loads of the
+//   next chunk in flight).  Epilogue: TMEM lane = row; each thread walks its row's 128-bit column mask and
+//   stores the selected accumulators to P through the tile's CSR-index list.
+//   Tile traffic is 2 x 128 x K x 4 B for up to 16384 outputs, so unlike the 16-row dense blocks the
+//   operand gather is amortised over 8 panels; chosen by sddmm_launch when S is dense enough.
+// =============================================================================================
+constexpr int kTlThreads = 256;
+constexpr u32 kTlStageBytes = 2u * 128u * 128u;  // A tile + B tile, 16 KB each
+constexpr u32 kTlStages = 2;
+constexpr u32 kTlTmemCols = 128;
+
+static __global__ void __launch_bounds__(kTlThreads)
+k_sddmm_tile(u32 M, u32 N, u32 K, const float* __restrict__ A, const float* __restrict__ B,
+             const u32* __restrict__ R, u32 nR, const uint4* __restrict__ tiles, const u32* __restrict__ rowMeta,
+             const u32* __restrict__ entIdx, float* __restrict__ P, BatchStrides bs) {
+  extern __shared__ __align__(1024) unsigned char smemRaw[];
+  A += bs.a * blockIdx.y;
+  B += bs.b * blockIdx.y;
+  P += bs.p * blockIdx.y;
+  unsigned char* stages = smemRaw + ((1024u - (smem_u32(smemRaw) & 1023u)) & 1023u);
+  __shared__ u64 mbar[kTlStages];
+  __shared__ u32 tmemBase;
+  __shared__ u32 sRows[128];
+
+  const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const uint4 tile = tiles[blockIdx.x];
+  const u32 row0 = tile.x * 128u, col0 = tile.y * 128u;
+  if (tid < 128) {
+    const u32 ri = row0 + tid;
+    sRows[tid] = ri < nR ? R[ri] : M;  // rows past the end read as zeros
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmemBase)),
+                 "r"(kTlTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (u32 s = 0; s < kTlStages; ++s) mbar_init(&mbar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const u32 tmem = tmemBase;
+  const u32 numChunks = (K + kDnKChunk - 1) / kDnKChunk;
+  constexpr u32 idesc = umma_idesc_tf32(128, 128);
+
+  // 2048 float4 per chunk (1024 of A, 1024 of B): 8 per thread; unit u -> (tile, row, 16-byte chunk)
+  float4 rg[8];
+  auto issue_loads = [&](u32 kc) {
+    const u32 k0 = kc * kDnKChunk;
+#pragma unroll
+    for (u32 it = 0; it < 8; ++it) {
+      const u32 u = it * kTlThreads + tid;  // 0..2047
+      const u32 row = (u & 1023u) >> 3, ch = u & 7u;
+      const u32 k = k0 + ch * 4u;
+      rg[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (u < 1024u) {
+        const u32 ar = sRows[row];
+        if (ar < M && k < K) rg[it] = __ldg(reinterpret_cast<const float4*>(A + (size_t)ar * K + k));
+      } else {
+        const u32 c = col0 + row;
+        if (c < N && k < K) rg[it] = __ldg(reinterpret_cast<const float4*>(B + (size_t)c * K + k));
+      }
+    }
+  };
+  issue_loads(0);
+  for (u32 kc = 0; kc < numChunks; ++kc) {
+    const u32 s = kc % kTlStages;
+    if (kc >= kTlStages) mbar_wait(&mbar[s], ((kc / kTlStages) - 1) & 1u);
+    unsigned char* tileA = stages + s * kTlStageBytes;
+    unsigned char* tileB = tileA + 128u * 128u;
+#pragma unroll
+    for (u32 it = 0; it < 8; ++it) {
+      const u32 u = it * kTlThreads + tid;
+      float4 v = rg[it];
+      v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w);
+      st_swizzled(u < 1024u ? tileA : tileB, (u & 1023u) >> 3, u & 7u, v);
+    }
+    if (kc + 1 < numChunks) issue_loads(kc + 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const u64 dA = umma_desc_sw128(smem_u32(tileA));
+      const u64 dB = umma_desc_sw128(smem_u32(tileB));
+#pragma unroll
+      for (u32 k = 0; k < kDnKChunk / 8; ++k) {
+        const u32 acc = (kc | k) ? 1u : 0u;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem),
+            "l"(dA + 2ull * k), "l"(dB + 2ull * k), "r"(idesc), "r"(acc)
+            : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_u32(&mbar[s]))
+                   : "memory");
+    }
+  }
+  {
+    const u32 last = numChunks - 1;
+    mbar_wait(&mbar[last % kTlStages], (last / kTlStages) & 1u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  // ---- epilogue: warp w reads TMEM lanes 32*(w%4).. (rows) and the column half w/4
+  {
+    const u32 q4 = warp & 3u, half = warp >> 2;
+    const u32 r = q4 * 32u + lane;
+    const u32* meta = rowMeta + (size_t)blockIdx.x * 640u + r * 5u;
+    const u32 m0 = meta[0], m1 = meta[1], m2 = meta[2], m3 = meta[3];
+    u32 off = meta[4];
+    if (half) off += __popc(m0) + __popc(m1);
+#pragma unroll
+    for (u32 qq = 0; qq < 2; ++qq) {
+      const u32 q = half * 2u + qq;
+      u32 acc[32];
+      const u32 taddr = tmem + ((q4 * 32u) << 16) + q * 32u;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]),
+            "=r"(acc[7]), "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]),
+            "=r"(acc[14]), "=r"(acc[15]), "=r"(acc[16]), "=r"(acc[17]), "=r"(acc[18]), "=r"(acc[19]), "=r"(acc[20]),
+            "=r"(acc[21]), "=r"(acc[22]), "=r"(acc[23]), "=r"(acc[24]), "=r"(acc[25]), "=r"(acc[26]), "=r"(acc[27]),
+            "=r"(acc[28]), "=r"(acc[29]), "=r"(acc[30]), "=r"(acc[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const u32 mw = q == 0 ? m0 : q == 1 ? m1 : q == 2 ? m2 : m3;
+#pragma unroll
+      for (u32 b = 0; b < 32; ++b) {
+        if ((mw >> b) & 1u) {
+          P[entIdx[off]] = __uint_as_float(acc[b]);
+          ++off;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTlTmemCols) : "memory");
+  }
+}
+
 // =============================================================================================
 // launcher
 // =============================================================================================
@@ -431,6 +586,29 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
     bst.a = (size_t)I.M * K;
     bst.b = (size_t)I.N * K;
     bst.p = I.nnz;
+  }
+  // ---- plan selection: whole 128x128 tensor-core tiles (K8) vs BSMR dense blocks + residual.
+  // Cost model (cycles per SM, calibrated on B200): a tile moves 2*128*K*4 bytes from L2 (~54 B/clk/SM)
+  // and its stores cost ~1 clk each; the BSMR kernels cost about 0.03*K + 1.5 clk per non-zero.
+  if (L->tl && L->tl->numTiles) {
+    static const int plan = [] { const char* e = getenv("SDDMM_B200_PLAN"); return e ? (!strcmp(e, "full") ? 2 : !strcmp(e, "bsmr") ? 0 : 1) : 1; }();
+    const double tileCost = (double)L->tl->numTiles * (1024.0 * K / 54.0 + 600.0) + (double)L->tl->numEntries;
+    const double bsmrCost = (double)I.nnz * (0.03 * K + 1.5);
+    if (plan == 2 || (plan == 1 && tileCost < bsmrCost)) {
+      if (which & kLaunchDense) {
+        const size_t smem = (size_t)kTlStages * kTlStageBytes + 1024;
+        static bool attrSet = false;
+        if (!attrSet) {
+          SB_CUDA(cudaFuncSetAttribute(k_sddmm_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          attrSet = true;
+        }
+        k_sddmm_tile<<<dim3(L->tl->numTiles, numBatch), kTlThreads, smem, denseStream>>>(
+            I.M, I.N, K, dA, dB, arr(BSMR_REORDERED_ROWS), I.numRows, L->tl->tiles.get(), L->tl->rowMeta.get(),
+            L->tl->idx.get(), dP, bst);
+        SB_LAUNCH_CHECK();
+      }
+      return;  // every stored entry lives in exactly one tile
+    }
   }
   if (L->numDenseWork && (which & kLaunchDense)) {
     const size_t smem = (size_t)kDnStages * kDnStageBytes + 1024;
