@@ -10,6 +10,20 @@
 
 namespace sb {
 thread_local u64 g_launches = 0;
+thread_local TempState g_temp;
+TempScope::TempScope(cudaStream_t s) : saved(g_temp) {
+  static std::once_flag once;
+  std::call_once(once, [] {  // keep freed scratch memory in the pool instead of returning it to the driver
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  });
+  g_temp.active = true;
+  g_temp.stream = s;
+}
 static thread_local std::string g_err;
 void set_last_error(const std::string& m) { g_err = m; }
 int device_sm_count() {

@@ -55,27 +55,52 @@ extern thread_local u64 g_launches;
   } while (0)
 
 // ---- RAII device buffer ---------------------------------------------------------------------
+// Inside a TempScope allocations are stream-ordered (cudaMallocAsync / cudaFreeAsync on the scope's
+// stream, pool kept warm): the many short-lived scratch buffers of the sort / scan pipelines then cost
+// neither a device synchronisation nor a real cudaMalloc.  Outside a scope: plain cudaMalloc / cudaFree.
+struct TempState {
+  bool active = false;
+  cudaStream_t stream = nullptr;
+};
+extern thread_local TempState g_temp;
+struct TempScope {
+  TempState saved;
+  explicit TempScope(cudaStream_t s);
+  ~TempScope() { g_temp = saved; }
+};
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  bool pooled = false;
   DevBuf() = default;
   explicit DevBuf(size_t count) { alloc(count); }
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), pooled(o.pooled) { o.p = nullptr; o.n = 0; }
   DevBuf& operator=(DevBuf&& o) noexcept {
-    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    if (this != &o) { release(); p = o.p; n = o.n; pooled = o.pooled; o.p = nullptr; o.n = 0; }
     return *this;
   }
   ~DevBuf() { release(); }
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) SB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+    if (!count) return;
+    if (g_temp.active) {
+      SB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), g_temp.stream));
+      pooled = true;
+    } else {
+      SB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+      pooled = false;
+    }
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      if (pooled && g_temp.active) cudaFreeAsync(p, g_temp.stream);
+      else cudaFree(p);  // also valid for stream-ordered allocations (synchronises)
+    }
     p = nullptr;
     n = 0;
   }

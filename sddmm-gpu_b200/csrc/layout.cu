@@ -408,6 +408,7 @@ bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u
   const u32 T = (u32)std::ceil(delta * (float)(kPanel * kBlockCols));
 
   auto* L = new bsmr_layout();
+  TempScope tempScope(s);
   try {
     SB_CUDA(cudaGetDevice(&L->device));
     L->sparseChunk = kSparseChunkDefault;
@@ -638,6 +639,7 @@ static void build_tiles(bsmr_layout* L, const u32* d_rowOff, const u32* d_colIdx
 
 const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStream_t s) {
   if (L->sp && L->sp->G == G) return L->sp.get();
+  TempScope tempScope(s);
   const bsmr_layout_info& I = L->info;
   auto sp = std::make_unique<SuperPanelLayout>();
   sp->G = G;

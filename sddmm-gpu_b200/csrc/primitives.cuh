@@ -128,7 +128,7 @@ inline void exclusive_scan_u32(const u32* in, u32* out, size_t n, cudaStream_t s
   exclusive_scan_u32(sums.get(), sums.get(), tiles, s);
   k_scan_apply<<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, n, sums.get());
   SB_LAUNCH_CHECK();
-  SB_CUDA(cudaStreamSynchronize(s));  // sums is freed on return
+  if (!g_temp.active) SB_CUDA(cudaStreamSynchronize(s));  // sums is freed on return (stream-ordered inside a TempScope)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -246,7 +246,7 @@ inline int radix_sort_pairs(KeyT* keysA, KeyT* keysB, u32* valsA, u32* valsB, si
     SB_LAUNCH_CHECK();
     cur ^= 1;
   }
-  SB_CUDA(cudaStreamSynchronize(s));  // hist is freed on return
+  if (!g_temp.active) SB_CUDA(cudaStreamSynchronize(s));  // hist is freed on return (stream-ordered inside a TempScope)
   return cur;
 }
 

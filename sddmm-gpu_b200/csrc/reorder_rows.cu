@@ -714,6 +714,7 @@ void dispersion_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32 
                     u32* nbprOut, cudaStream_t s) {
   const u32 nbpr = num_blocks_per_row(N, bs);
   if (nbprOut) *nbprOut = nbpr;
+  TempScope tempScope(s);
   SortedCols sc;
   make_sorted_cols(d_rowOff, d_colIdx, M, N, nnz, s, sc);
   const u32 B = cluster_blockdim(nbpr);
@@ -726,6 +727,7 @@ void dispersion_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32 
 void row_reorder_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32 nnz, float alpha, u32 bs,
                      u32* d_reorderedRows, u32* numRows, int32_t* numClusters, RowReorderStats* st, cudaStream_t s) {
   if (M == 0) { *numRows = 0; if (numClusters) *numClusters = 0; return; }
+  TempScope tempScope(s);
   const u32 nbpr = num_blocks_per_row(N, bs);
   const u32 B = cluster_blockdim(nbpr);
   const u32 keptMask = kept_warp_mask(B);

@@ -46,8 +46,13 @@ def run_ours(S, A, B, alpha, delta, bs):
     import torch
     ro = torch.from_numpy(S.row_off.view(np.int32)).cuda()
     ci = torch.from_numpy(S.col_idx.view(np.int32)).cuda()
+    # second call of each stage: excludes one-time CUDA module loading / allocator warm-up
     R, ncl, row_ms = pkg.row_reorder_dev(ro, ci, S.M, S.N, alpha, bs)
+    R, ncl, row_ms2 = pkg.row_reorder_dev(ro, ci, S.M, S.N, alpha, bs)
+    row_ms = min(row_ms, row_ms2)
     lay, col_ms, rphm_ms = pkg.layout_build_dev(ro, ci, S.M, S.N, R, delta)
+    lay, col_ms2, rphm_ms2 = pkg.layout_build_dev(ro, ci, S.M, S.N, R, delta)
+    col_ms, rphm_ms = min(col_ms, col_ms2), min(rphm_ms, rphm_ms2)
     dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
     dP = torch.zeros(max(1, S.nnz), dtype=torch.float32, device="cuda")
     t = pkg.sddmm_gpu_timed(dA, dB, lay, dP, warmup=3, iters=10)
