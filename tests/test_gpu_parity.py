@@ -345,3 +345,39 @@ def test_strong_scaling_shards_two_ranks_nccl(torch_mod):
     torch.cuda.synchronize()
     assert covered == S.nnz
     assert O.check_data(O.sddmm_cpu(S, A, B), P.cpu().numpy()) == 0
+
+
+def test_error_paths_are_loud():
+    """bad arguments -> error codes with a message, never a silent fallback"""
+    S = gen.uniform_random(64, 64, 0.2, 1)
+    lay = pkg.BSMR(0.3, 0.3, S, block_size=16).layout()
+    A, B = operands(S, 6)  # K % 4 != 0
+    with pytest.raises(pkg.SddmmError) as e:
+        pkg.sddmm_gpu(A, B, lay)
+    assert e.value.code == 1 and "multiple of 4" in str(e.value)
+
+
+@pytest.mark.parametrize("shape", [(1, 40), (17, 5), (33, 2000), (300, 15)])
+def test_tiny_and_ragged_shapes(shape):
+    """single row, fewer than 16 columns, partial last panel: whole path vs oracle"""
+    M, N = shape
+    rng = np.random.default_rng(M * 1000 + N)
+    dens = 0.4
+    mask = rng.random((M, N)) < dens
+    mask[0, 0] = True
+    mask[-1, -1] = True
+    r, c = np.nonzero(mask)
+    from sddmm_gpu_b200.generators import _from_coo
+    S = _from_coo(M, N, r, c, f"tiny{M}x{N}")
+    A, B = operands(S, 32)
+    bs = _bs(S)
+    res = pkg.sddmm(S, A, B, alpha=0.3, delta=0.3, block_size=bs)
+    rr = O.row_reorder(S, 0.3, bs)
+    assert np.array_equal(res["reorderedRows"], rr["reorderedRows"])
+    cr = O.col_reorder(S, rr["reorderedRows"], 0.3)
+    rp = O.rphm_build(S, rr["reorderedRows"], cr)
+    for k in LAYOUT_KEYS:
+        assert np.array_equal(res[k], cr[k]), k
+    for k in RPHM_KEYS:
+        assert np.array_equal(res[k], rp[k]), k
+    assert O.check_data(O.sddmm_cpu(S, A, B), res["P"]) == 0
