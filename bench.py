@@ -308,22 +308,39 @@ def run_ours(args, w):
     if rank == 0:
         pk = peaks()
         dense_dominant = kt["dense_ms"] > kt["sparse_ms"]
-        if dense_dominant:
-            kname, kms = "k_sddmm_dense (tcgen05 kind::tf32)", kt["dense_ms"]
-            byts = algorithmic_bytes(S.M, S.N, K, info.numDenseValues, info.numDenseBlocks, "dense")
-        else:
-            kname, kms = "k_sddmm_residual (fp32 CUDA cores)", kt["sparse_ms"]
-            byts = algorithmic_bytes(S.M, S.N, K, info.numSparseValues, 0, "residual")
-        achieved = byts / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+        gather_bytes = float(S.nnz) * (4.0 * K + 16.0) + 4.0 * K * S.M + 4.0 * (S.M + 1)  # SURVEY 8(d) no-reuse model
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(f"{args.workload}:{'dense' if dense_dominant else 'residual'}")
-        roof = dict(bound="hbm", achieved=achieved, peak=pk["hbm_gbs"], unit="GB/s", frac=achieved / pk["hbm_gbs"],
-                    traffic=traffic, kernel=kname, kernel_ms=kms, algorithmic_bytes=byts, peak_source=pk["which"],
-                    dense_kernel_ms=kt["dense_ms"], residual_kernel_ms=kt["sparse_ms"],
-                    dense_tflops_padded=(2.0 * 256 * info.numDenseBlocks * K / (kt["dense_ms"] * 1e-3) / 1e12
-                                         if kt["dense_ms"] > 0 else 0.0))
+        if dense_dominant:
+            # tensor-core kernel (128x128 tcgen05 tiles or 16x16 BSMR blocks): padded flops vs the tf32 peak,
+            # taken as half of the measured dense bf16 peak (tf32 runs at half the bf16 rate)
+            kname, kms = "k_sddmm_tile / k_sddmm_dense (tcgen05 kind::tf32)", kt["dense_ms"]
+            tiles = (-(-S.M // 128)) * (-(-S.N // 128))
+            padded = 2.0 * 16384.0 * tiles * K if info.numDenseBlocks == 0 or True else 0.0
+            padded_blocks = 2.0 * 256.0 * info.numDenseBlocks * K
+            flops = max(padded_blocks, 2.0 * S.nnz * K)
+            byts = algorithmic_bytes(S.M, S.N, K, S.nnz, 0, "dense")
+            achieved = 2.0 * S.nnz * K / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
+            peak = pk["tf"] / 2.0
+            roof = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
+                        traffic=traffic, kernel=kname, kernel_ms=kms, algorithmic_bytes=byts,
+                        algorithmic_flops=2.0 * S.nnz * K, dense_tile_flops_if_all_tiles=padded,
+                        bsmr_block_padded_flops=padded_blocks, peak_source=pk["which"] + " bf16 / 2",
+                        hbm_view=dict(achieved_gbs=byts / (kms * 1e-3) / 1e9 if kms > 0 else 0.0, peak_gbs=pk["hbm_gbs"]),
+                        dense_kernel_ms=kt["dense_ms"], residual_kernel_ms=kt["sparse_ms"])
+        else:
+            kname, kms = "k_sddmm_residual_sp (fp32 CUDA cores, super-panel)", kt["sparse_ms"]
+            byts = algorithmic_bytes(S.M, S.N, K, info.numSparseValues, 0, "residual")
+            achieved = byts / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+            roof = dict(bound="hbm", achieved=achieved, peak=pk["hbm_gbs"], unit="GB/s", frac=achieved / pk["hbm_gbs"],
+                        traffic=traffic, kernel=kname, kernel_ms=kms, algorithmic_bytes=byts, peak_source=pk["which"],
+                        gather_model=dict(bytes=gather_bytes, achieved_gbs=gather_bytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0),
+                        smem_model=dict(bytes=4.0 * K * info.numSparseValues,
+                                        floor_ms=4.0 * K * info.numSparseValues / (148 * 128 * 1.965e9) * 1e3,
+                                        note="A operand: 4K bytes per non-zero through LDS.128, 148 SMs x 128 B/clk"),
+                        dense_kernel_ms=kt["dense_ms"], residual_kernel_ms=kt["sparse_ms"])
         cpu = None
         if world == 1 and not args.no_cpu:
             c = cpu_reference_gflops(S, A, B, K, args.cpu_rows)
