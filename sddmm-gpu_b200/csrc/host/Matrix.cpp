@@ -5,6 +5,8 @@
 // (row-only stable order) are those of src/Matrix.cpp:398-480.
 #include "Matrix.hpp"
 
+#include <omp.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -81,29 +83,61 @@ bool CSR<T>::initializeFromMtxFile(const std::string& file) {
   col_ = static_cast<UIN>(std::strtol(p, &e, 10)); p = skip_blank(e);
   nnz_ = at_eol(p) ? 0u : static_cast<UIN>(std::strtod(p, &e));
   p = next_line(p);
-  std::vector<UIN> ri(nnz_), ci(nnz_);
-  std::vector<T> va(nnz_);
-  UIN idx = 0;
-  while (*p) {
-    const char* q = skip_blank(p);
-    if (at_eol(q)) { p = next_line(p); continue; }  // empty line
-    const long r = std::strtol(q, &e, 10); q = skip_blank(e);
-    const long c = std::strtol(q, &e, 10); q = skip_blank(e);
-    T v = static_cast<T>(0);
-    if (!at_eol(q)) v = static_cast<T>(std::strtod(q, &e));
-    if (idx >= nnz_) {
-      std::cerr << "Error, file " << file << " too many elements, exceeding the number nnz!" << std::endl;
-      return false;
-    }
-    ri[idx] = static_cast<UIN>(r - 1);
-    ci[idx] = static_cast<UIN>(c - 1);
-    va[idx] = v;
-    ++idx;
-    p = next_line(p);
+  // ---- parallel parse: the body is cut into one slab per thread at line boundaries; every slab is parsed
+  // into its own vectors and the slabs are concatenated in file order (the order inside a row is part of
+  // the contract, src/Matrix.cpp:467).
+  const char* body = p;
+  const char* fileEnd = buf.data() + buf.size() - 1;  // points at the terminating 0
+  const int nThreads = std::max(1, omp_get_max_threads());
+  std::vector<const char*> cut(nThreads + 1, fileEnd);
+  cut[0] = body;
+  for (int t = 1; t < nThreads; ++t) {
+    const char* q = body + (fileEnd - body) / nThreads * t;
+    while (q < fileEnd && *q != '\n') ++q;
+    cut[t] = q < fileEnd ? q + 1 : fileEnd;
   }
-  if (idx < nnz_) {
+  for (int t = 1; t <= nThreads; ++t)
+    if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+  std::vector<std::vector<UIN>> tri(nThreads), tci(nThreads);
+  std::vector<std::vector<T>> tva(nThreads);
+#pragma omp parallel for schedule(static, 1)
+  for (int t = 0; t < nThreads; ++t) {
+    const char* q = cut[t];
+    const char* qe = cut[t + 1];
+    char* e2 = nullptr;
+    while (q < qe && *q) {
+      const char* w = skip_blank(q);
+      if (at_eol(w)) { q = next_line(q); continue; }  // empty line
+      const long r = std::strtol(w, &e2, 10); w = skip_blank(e2);
+      const long c = std::strtol(w, &e2, 10); w = skip_blank(e2);
+      T v = static_cast<T>(0);
+      if (!at_eol(w)) v = static_cast<T>(std::strtod(w, &e2));
+      tri[t].push_back(static_cast<UIN>(r - 1));
+      tci[t].push_back(static_cast<UIN>(c - 1));
+      tva[t].push_back(v);
+      q = next_line(q);
+    }
+  }
+  size_t total = 0;
+  for (int t = 0; t < nThreads; ++t) total += tri[t].size();
+  if (total > nnz_) {
+    std::cerr << "Error, file " << file << " too many elements, exceeding the number nnz!" << std::endl;
+    return false;
+  }
+  if (total < nnz_) {
     std::cerr << "Error, file " << file << " elements is not enough!" << std::endl;
     return false;
+  }
+  std::vector<UIN> ri(nnz_), ci(nnz_);
+  std::vector<T> va(nnz_);
+  {
+    size_t o = 0;
+    for (int t = 0; t < nThreads; ++t) {
+      std::copy(tri[t].begin(), tri[t].end(), ri.begin() + o);
+      std::copy(tci[t].begin(), tci[t].end(), ci.begin() + o);
+      std::copy(tva[t].begin(), tva[t].end(), va.begin() + o);
+      o += tri[t].size();
+    }
   }
   std::vector<uint64_t> keys(nnz_);
   for (UIN i = 0; i < nnz_; ++i) {

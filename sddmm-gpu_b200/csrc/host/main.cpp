@@ -20,6 +20,22 @@ int main(int argc, char* argv[]) {
     std::fprintf(stderr, "Error, matrix S initialize failed.\n");
     return -1;
   }
+  // `-x 1`: loader check only (no GPU needed): print the CSR's shape and FNV-1a checksums of its arrays
+  for (int i = 1; i + 1 < argc; ++i) {
+    if ((!std::strcmp(argv[i], "-x") || !std::strcmp(argv[i], "-X")) && std::atoi(argv[i + 1]) != 0) {
+      auto fnv = [](const void* p, size_t n) {
+        unsigned long long h = 1469598103934665603ull;
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        for (size_t j = 0; j < n; ++j) { h ^= b[j]; h *= 1099511628211ull; }
+        return h;
+      };
+      std::printf("[loader : M %u N %u nnz %u rowOff %llx colIdx %llx values %llx]\n", matrixS.row(), matrixS.col(),
+                  matrixS.nnz(), fnv(matrixS.rowOffsets().data(), matrixS.rowOffsets().size() * 4),
+                  fnv(matrixS.colIndices().data(), matrixS.colIndices().size() * 4),
+                  fnv(matrixS.values().data(), matrixS.values().size() * 4));
+      return 0;
+    }
+  }
   if (options.testMode()) {
     sddmm_testMode(options, matrixS);
     return 0;

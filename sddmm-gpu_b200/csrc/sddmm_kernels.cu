@@ -593,7 +593,8 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
   if (L->tl && L->tl->numTiles) {
     static const int plan = [] { const char* e = getenv("SDDMM_B200_PLAN"); return e ? (!strcmp(e, "full") ? 2 : !strcmp(e, "bsmr") ? 0 : 1) : 1; }();
     const double tileCost = (double)L->tl->numTiles * (1024.0 * K / 54.0 + 600.0) + (double)L->tl->numEntries;
-    const double bsmrCost = (double)I.nnz * (0.03 * K + 1.5);
+    const double covered = (double)I.numDenseValues + (double)I.numSparseValues;  // this shard's entries
+    const double bsmrCost = covered * (0.03 * K + 1.5);
     if (plan == 2 || (plan == 1 && tileCost < bsmrCost)) {
       if (which & kLaunchDense) {
         const size_t smem = (size_t)kTlStages * kTlStageBytes + 1024;

@@ -185,3 +185,37 @@ def test_shard_plan_balances_nnz():
     lens = np.diff(S.row_off.astype(np.int64))[R]
     per = [lens[cuts[i] * 16: cuts[i + 1] * 16].sum() for i in range(4)]
     assert max(per) - min(per) <= 0.25 * S.nnz / 4 + lens.max() * 16
+
+
+def _fnv(a):
+    h = 1469598103934665603
+    for b in np.ascontiguousarray(a).tobytes():
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+@pytest.mark.parametrize("order", ["col", "rowrev"])
+def test_cpp_host_loader_matches_oracle(tmp_path, order):
+    """csrc/host/Matrix.cpp (parallel in-place parser) builds the same CSR as the oracle's restatement of
+    src/Matrix.cpp:398-480 (itself pinned to the reference loader above); `BSMR-sddmm -x 1` needs no GPU."""
+    import subprocess
+    from cases import ROOT
+    exe = os.path.join(ROOT, "sddmm-gpu_b200", "BSMR-sddmm")
+    if not os.access(exe, os.X_OK):
+        pytest.skip("CLI not built")
+    S = gen.with_empty_rows(gen.rmat(9, 8, 3), 5)
+    p = str(tmp_path / "m.mtx")
+    gen.write_mtx(p, S, order=order)
+    rc, (M, N, ro, ci, va) = O.load_mtx(p)
+    assert rc == 0
+    out = subprocess.run([exe, "-f", p, "-x", "1"], capture_output=True, text=True, timeout=60).stdout
+    line = [l for l in out.splitlines() if l.startswith("[loader")][0]
+    tok = line.strip("[]").split()
+    got = dict(zip(tok[2::2], tok[3::2]))
+    assert int(got["M"]) == M and int(got["N"]) == N and int(got["nnz"]) == len(ci)
+    assert int(got["rowOff"], 16) == _fnv(ro) and int(got["colIdx"], 16) == _fnv(ci) and int(got["values"], 16) == _fnv(va)
+    # rejects what the reference rejects
+    bad = str(tmp_path / "dup.mtx")
+    open(bad, "w").write("%%MatrixMarket\n3 3 3\n1 1 1\n2 2 1\n1 1 1\n")
+    r = subprocess.run([exe, "-f", bad, "-x", "1"], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "duplicate" in r.stderr
