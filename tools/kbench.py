@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--scale", type=int, default=18)
     ap.add_argument("--sparsity", type=float, default=0.7)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--Ks", default="", help="comma list: sweep K on one layout, one JSON line per K")
     a = ap.parse_args()
     import torch
     pkg = load_package()
@@ -42,8 +43,6 @@ def main():
         S = gen.rmat(a.scale, 16, 4)
     else:
         raise SystemExit("unknown workload")
-    K = a.K
-    A, B = gen.dense_operands(S.M, S.N, K)
     ro = torch.from_numpy(S.row_off.view(np.int32)).cuda()
     ci = torch.from_numpy(S.col_idx.view(np.int32)).cuda()
     if a.reorder:
@@ -53,7 +52,15 @@ def main():
         R = torch.from_numpy(np.nonzero(lens)[0].astype(np.int32)).cuda()
         ncl, row_ms = -1, 0.0
     lay, col_ms, rphm_ms = pkg.layout_build_dev(ro, ci, S.M, S.N, R, a.delta)
-    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    for K in ([int(x) for x in a.Ks.split(",")] if a.Ks else [a.K]):
+        run_k(a, torch, pkg, gen, S, lay, K, ncl, row_ms, col_ms, rphm_ms)
+
+
+def run_k(a, torch, pkg, gen, S, lay, K, ncl, row_ms, col_ms, rphm_ms):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1001)
+    dA = torch.rand((S.M, K), device="cuda", generator=g) * 2  # U[0,2) like Matrix::makeData
+    dB = torch.rand((S.N, K), device="cuda", generator=g) * 2
     dP = torch.zeros(max(1, S.nnz), dtype=torch.float32, device="cuda")
     t = pkg.sddmm_gpu_timed(dA, dB, lay, dP, warmup=3, iters=a.iters)
     i = lay.info
@@ -66,17 +73,16 @@ def main():
     if t["dense_ms"] > 0:
         out["dense_useful_gflops"] = 2.0 * i.numDenseValues * K / (t["dense_ms"] * 1e-3) / 1e9
         out["dense_padded_tflops"] = 2.0 * 256 * i.numDenseBlocks * K / (t["dense_ms"] * 1e-3) / 1e12
-    if a.check:
-        from oracle import oracle as O
+    if a.check:  # sampled rows against fp64 on the device
         torch.cuda.synchronize()
         rows = np.random.default_rng(0).choice(S.M, 32, replace=False)
-        Ph = dP.cpu().numpy()
+        ci = torch.from_numpy(S.col_idx.view(np.int32)).cuda()
         worst = 0.0
         for r in rows:
             b, e = int(S.row_off[r]), int(S.row_off[r + 1])
             if e > b:
-                ref = (A[r][None, :].astype(np.float64) * B[S.col_idx[b:e]]).sum(1)
-                worst = max(worst, float((np.abs(Ph[b:e] - ref) / np.maximum(np.abs(ref), 1e-3)).max()))
+                ref = (dA[int(r)].double()[None, :] * dB[ci[b:e].to(torch.int64)].double()).sum(1)
+                worst = max(worst, float(((dP[b:e].double() - ref).abs() / ref.abs().clamp_min(1e-3)).max()))
         out["max_rel_err_sample"] = worst
     print(json.dumps(out), flush=True)
 
