@@ -137,6 +137,30 @@ typedef struct {
   uint32_t numSparseThreadBlocks;
 } bsmr_layout_info;
 
+/* ---- f2: the reordering statistics the reference logs after every run ------------------------
+ * replaces evaluationReordering(matrix, bsmr, logger)                src/BSMR.cpp:826-925
+ *   numDenseBlock   -> [bsmr_numDenseBlock]   dense blocks whose density (stored entries / 256) >= delta
+ *   averageDensity  -> [bsmr_averageDensity]  density summed over every non-empty dense block, divided by
+ *                                             numDenseBlock (the reference's expression, :917)
+ *   num*ThreadBlocks-> [bsmr_numDenseThreadBlocks] / [bsmr_numSparseThreadBlocks]   (:843-849)
+ *   numSparseData / numDenseData -> [bsmr_numSparseData] / [bsmr_numDenseData] = nnz - numSparseData (:923-924)
+ * and calculateNumDenseBlocksAndAverageDensityInOriginalMatrix(delta, matrix)   src/BSMR.cpp:953-994
+ *   -> [original_numDenseBlock], [original_averageDensity]: 16x16 blocks of the UNreordered matrix
+ *      (edge blocks use their clipped size) with density >= delta, and the mean density of those.
+ * Both run on the device (a key sort / a reduction) instead of the reference's host loops. */
+typedef struct {
+  uint32_t numDenseBlock;
+  float averageDensity;
+  uint32_t numDenseThreadBlocks, numSparseThreadBlocks;
+  uint32_t numDenseData, numSparseData;
+} bsmr_eval;
+int bsmr_layout_eval(const bsmr_layout*, float delta, bsmr_eval* out);
+int bsmr_original_block_stats_dev(const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N,
+                                  uint32_t nnz, float delta, uint32_t* numDenseBlocks, float* averageDensity,
+                                  void* stream);
+int bsmr_original_block_stats(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, uint32_t N,
+                              uint32_t nnz, float delta, uint32_t* numDenseBlocks, float* averageDensity);
+
 int bsmr_layout_get_info(const bsmr_layout*, bsmr_layout_info* out);
 size_t bsmr_layout_array_len(const bsmr_layout*, bsmr_array_id which);
 const uint32_t* bsmr_layout_array_dev(const bsmr_layout*, bsmr_array_id which);

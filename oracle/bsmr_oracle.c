@@ -417,6 +417,106 @@ void oracle_work_lists(u32 P, const u32* dOff, const u32* vOff, u32* numDenseTB,
 }
 
 /* ------------------------------------------------------------------------- */
+/* BSMR.cpp:953-994 calculateNumDenseBlocksAndAverageDensityInOriginalMatrix:
+ * 16x16 blocks of the UNreordered matrix, panel-major then column-block
+ * ascending (the order of the reference's two loops, which fixes the order of
+ * its float accumulation); edge blocks use their clipped size.                */
+static int cmp_u32(const void* a, const void* b) {
+  const u32 x = *(const u32*)a, y = *(const u32*)b;
+  return x < y ? -1 : x > y;
+}
+void oracle_original_block_stats(const u32* rowOff, const u32* colIdx, u32 M, u32 N, float delta,
+                                 u32* numDenseBlocks, float* averageDensity) {
+  const u32 nRP = (M + 15u) / 16u, nCB = (N + 15u) / 16u;
+  u32* cnt = (u32*)calloc(nCB ? nCB : 1, sizeof(u32));
+  u32* touched = (u32*)malloc(sizeof(u32) * (nCB ? nCB : 1));
+  u32 nDense = 0;
+  float total = 0.0f;
+  for (u32 rp = 0; rp < nRP; ++rp) {
+    const u32 r0 = rp * 16u, r1 = (r0 + 16u < M) ? r0 + 16u : M;
+    u32 nt = 0;
+    for (u32 r = r0; r < r1; ++r)
+      for (u32 i = rowOff[r]; i < rowOff[r + 1]; ++i) {
+        const u32 cb = colIdx[i] / 16u;
+        if (cnt[cb]++ == 0) touched[nt++] = cb;
+      }
+    qsort(touched, nt, sizeof(u32), cmp_u32);
+    for (u32 t = 0; t < nt; ++t) {
+      const u32 cb = touched[t];
+      const u32 c0 = cb * 16u, c1 = (c0 + 16u < N) ? c0 + 16u : N;
+      const float blockSize = (float)((r1 - r0) * (c1 - c0));
+      const float density = (float)cnt[cb] / blockSize;
+      if (density >= delta) {
+        total += density;
+        ++nDense;
+      }
+      cnt[cb] = 0;
+    }
+  }
+  free(cnt);
+  free(touched);
+  *numDenseBlocks = nDense;
+  *averageDensity = nDense > 0 ? total / (float)nDense : 0.0f;
+}
+
+/* BSMR.cpp:826-925 evaluationReordering.  out6 = numDenseBlock, numDenseThreadBlocks,
+ * numSparseThreadBlocks, numSparseData, numDenseData, (spare); *averageDensity as :917.
+ * Only the DENSE column blocks get a column set in the reference (:860-871), so the
+ * sparse blocks never count; numSparseData counts entries whose column is one of the
+ * panel's sparse columns (:873-880, :899-901).                                  */
+void oracle_evaluation_reordering(const u32* rowOff, const u32* colIdx, u32 M, u32 N, u32 nnz,
+                                  const u32* R, u32 nR, const u32* dOff, const u32* dCols,
+                                  const u32* sOff, const u32* sCols, const u32* vOff, float delta,
+                                  u32* out6, float* averageDensity) {
+  (void)M;
+  const u32 P = (nR + 15u) / 16u;
+  int* blockOfCol = (int*)malloc(sizeof(int) * ((size_t)N + 1));   /* dense block id of a column, -1 */
+  unsigned char* isSparse = (unsigned char*)calloc((size_t)N + 1, 1);
+  for (u32 c = 0; c <= N; ++c) blockOfCol[c] = -1;
+  u32 numDenseBlocks = 0, numDenseTB = 0, numSparseTB = 0, numSparseData = 0;
+  float totalDensity = 0.0f;
+  for (u32 p = 0; p < P; ++p) {
+    const u32 nDenseBlk = (u32)ceilf((float)(dOff[p + 1] - dOff[p]) / 16.0f);
+    numDenseTB += (u32)ceilf((float)nDenseBlk / 4.0f);
+    numSparseTB += (u32)ceilf((float)(vOff[p + 1] - vOff[p]) / 128.0f);
+    u32* nnzIn = (u32*)calloc(nDenseBlk ? nDenseBlk : 1, sizeof(u32));
+    for (u32 i = dOff[p]; i < dOff[p + 1]; ++i) blockOfCol[dCols[i]] = (int)((i - dOff[p]) / 16u);
+    for (u32 i = sOff[p]; i < sOff[p + 1]; ++i) isSparse[sCols[i]] = 1;
+    const u32 i0 = p * 16u, i1 = (i0 + 16u < nR) ? i0 + 16u : nR;
+    for (u32 ir = i0; ir < i1; ++ir) {
+      const u32 row = R[ir];
+      for (u32 idx = rowOff[row]; idx < rowOff[row + 1]; ++idx) {
+        const u32 col = colIdx[idx];
+        if (blockOfCol[col] >= 0) ++nnzIn[blockOfCol[col]];
+        if (isSparse[col]) ++numSparseData;
+      }
+    }
+    for (u32 b = 0; b < nDenseBlk; ++b)
+      if (nnzIn[b] > 0) {
+        const float density = (float)nnzIn[b] / 256.0f;
+        totalDensity += density;
+        if (density >= delta) ++numDenseBlocks;
+      }
+    for (u32 i = dOff[p]; i < dOff[p + 1]; ++i) blockOfCol[dCols[i]] = -1;
+    for (u32 i = sOff[p]; i < sOff[p + 1]; ++i) isSparse[sCols[i]] = 0;
+    free(nnzIn);
+  }
+  free(blockOfCol);
+  free(isSparse);
+  out6[0] = numDenseBlocks;
+  out6[1] = numDenseTB;
+  out6[2] = numSparseTB;
+  out6[3] = numSparseData;
+  out6[4] = nnz - numSparseData;
+  out6[5] = 0;
+  /* :917  `totalDensity / numDenseBlocks > 0 ? totalDensity / numDenseBlocks : 0.0f` (0/0 -> NaN -> 0) */
+  {
+    const float q = totalDensity / (float)(int)numDenseBlocks;
+    *averageDensity = q > 0 ? q : 0.0f;
+  }
+}
+
+/* ------------------------------------------------------------------------- */
 /* host.cpp:44-76: sequential-k fp32 dot per non-zero, OpenMP over rows.       */
 void oracle_sddmm_cpu(const float* A, const float* B, const u32* rowOff,
                       const u32* colIdx, u32 M, u32 K, float* P, int threads) {

@@ -89,6 +89,13 @@ int oracle_rphm_build(const uint32_t* rowOff, const uint32_t* colIdx,
                       uint32_t* sparseColIndices);
 
 /* BSMR.cpp:99-119 and :221-246 work lists.  Pass NULL outputs to get counts. */
+/* BSMR.cpp:953-994 and :826-925 (the statistics the reference logs after every run) */
+void oracle_original_block_stats(const uint32_t* rowOff, const uint32_t* colIdx, uint32_t M, uint32_t N,
+                                 float delta, uint32_t* numDenseBlocks, float* averageDensity);
+void oracle_evaluation_reordering(const uint32_t* rowOff, const uint32_t* colIdx, uint32_t M, uint32_t N,
+                                  uint32_t nnz, const uint32_t* R, uint32_t nR, const uint32_t* dOff,
+                                  const uint32_t* dCols, const uint32_t* sOff, const uint32_t* sCols,
+                                  const uint32_t* vOff, float delta, uint32_t* out6, float* averageDensity);
 void oracle_work_lists(uint32_t P, const uint32_t* denseColOffsets,
                        const uint32_t* sparseValueOffsets,
                        uint32_t* numDenseTB, uint32_t* maxDenseBlocks,

@@ -59,6 +59,11 @@ def lib():
         L.oracle_rphm_build.argtypes = [_u32p, _u32p, C.c_uint32, C.c_uint32, _u32p, C.c_uint32, _u32p, _u32p,
                                         _u32p, _u32p, _u32p, _u32p, _u32p, _u32p, _u32p, _u32p]
         L.oracle_work_lists.argtypes = [C.c_uint32, _u32p, _u32p] + [C.c_void_p] * 8
+        L.oracle_original_block_stats.argtypes = [_u32p, _u32p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p]
+        L.oracle_original_block_stats.restype = None
+        L.oracle_evaluation_reordering.argtypes = [_u32p, _u32p, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, C.c_uint32,
+                                                   _u32p, _u32p, _u32p, _u32p, _u32p, C.c_float, _u32p, C.c_void_p]
+        L.oracle_evaluation_reordering.restype = None
         L.oracle_sddmm_cpu.argtypes = [_f32p, _f32p, _u32p, _u32p, C.c_uint32, C.c_uint32, _f32p, C.c_int]
         L.oracle_check_data.restype = C.c_size_t
         L.oracle_check_data.argtypes = [_f32p, _f32p, C.c_size_t]
@@ -81,6 +86,9 @@ def ref():
         L.ref_col_reorder.restype = C.c_int
         L.ref_col_reorder.argtypes = [_u32p, _u32p, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, C.c_uint32,
                                       C.c_float, _u32p, _u32p, _u32p, C.c_void_p, C.c_void_p]
+        L.ref_evaluation_reordering.argtypes = [_u32p, _u32p, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, C.c_uint32,
+                                                C.c_float, C.c_void_p, C.c_void_p]
+        L.ref_evaluation_reordering.restype = None
         L.ref_sddmm_cpu.argtypes = [_f32p, _f32p, _u32p, _u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _f32p]
         L.ref_sddmm_prepare.restype = C.c_void_p
         L.ref_sddmm_prepare.argtypes = [_f32p, _f32p, _u32p, _u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
@@ -244,6 +252,38 @@ def ref_col_reorder(S, reordered_rows, delta):
                               dC.ctypes.data, sC.ctypes.data)
     return dict(numRowPanels=P, denseColOffsets=dO, sparseColOffsets=sO, sparseValueOffsets=vO,
                 denseCols=dC[: int(dO[-1])], sparseCols=sC[: int(sO[-1])])
+
+
+_EVAL_KEYS = ("numDenseBlock", "numDenseThreadBlocks", "numSparseThreadBlocks", "numSparseData", "numDenseData")
+
+
+def evaluation_reordering(S, reordered_rows, cr, delta):
+    """evaluationReordering + original-matrix statistics (BSMR.cpp:826-994) -> dict of the logged values."""
+    R = np.ascontiguousarray(reordered_rows, dtype=np.uint32)
+    out6 = np.zeros(6, np.uint32)
+    avg = C.c_float(0)
+    dC = np.ascontiguousarray(cr["denseCols"]) if cr["denseCols"].size else np.zeros(1, np.uint32)
+    sC = np.ascontiguousarray(cr["sparseCols"]) if cr["sparseCols"].size else np.zeros(1, np.uint32)
+    lib().oracle_evaluation_reordering(S.row_off, S.col_idx, S.M, S.N, S.nnz, R, R.shape[0], cr["denseColOffsets"], dC,
+                                       cr["sparseColOffsets"], sC, cr["sparseValueOffsets"], float(delta), out6,
+                                       C.byref(avg))
+    nd, ad = C.c_uint32(0), C.c_float(0)
+    lib().oracle_original_block_stats(S.row_off, S.col_idx, S.M, S.N, float(delta), C.byref(nd), C.byref(ad))
+    out = dict(zip(_EVAL_KEYS, (int(x) for x in out6[:5])))
+    out.update(averageDensity=avg.value, originalNumDenseBlock=nd.value, originalAverageDensity=ad.value)
+    return out
+
+
+def ref_evaluation_reordering(S, reordered_rows, delta):
+    """The reference's own evaluationReordering on a BSMR built by its CPU colReordering."""
+    R = np.ascontiguousarray(reordered_rows, dtype=np.uint32)
+    oi = (C.c_int * 6)()
+    of = (C.c_float * 2)()
+    with _quiet_stderr():
+        ref().ref_evaluation_reordering(S.row_off, S.col_idx, S.M, S.N, S.nnz, R, R.shape[0], float(delta), oi, of)
+    out = dict(zip(_EVAL_KEYS, (int(x) for x in oi[:5])))
+    out.update(averageDensity=of[0], originalNumDenseBlock=int(oi[5]), originalAverageDensity=of[1])
+    return out
 
 
 def ref_sddmm_cpu(S, A, B):

@@ -70,6 +70,30 @@ void ref_sddmm_release(void* ctx) {
   delete static_cast<RefCtx*>(ctx);
 }
 
+// evaluationReordering (src/BSMR.cpp:826-925) on a BSMR built from a caller-provided row order through the
+// reference's own BSMR::colReordering (CPU).  outi = numDenseBlock, numDenseThreadBlocks, numSparseThreadBlocks,
+// numSparseData, numDenseData, originalNumDenseBlock; outf = averageDensity, originalAverageDensity.
+void ref_evaluation_reordering(const uint32_t* rowOff, const uint32_t* colIdx, uint32_t M, uint32_t N,
+                               uint32_t nnz, const uint32_t* reorderedRows, uint32_t numRows, float delta,
+                               int* outi, float* outf) {
+  std::vector<float> vals(nnz, 1.0f);
+  sparseMatrix::CSR<float> S(M, N, nnz, rowOff, colIdx, vals.data());
+  std::vector<UIN> R(reorderedRows, reorderedRows + numRows);
+  BSMR bsmr;
+  bsmr.colReordering(delta, S, R, 1);
+  Logger lg;
+  lg.delta_ = delta;
+  evaluationReordering(S, bsmr, lg);
+  outi[0] = lg.numDenseBlock_;
+  outi[1] = lg.numDenseThreadBlocks_;
+  outi[2] = lg.numSparseThreadBlocks_;
+  outi[3] = lg.numSparseData_;
+  outi[4] = lg.numDenseData_;
+  outi[5] = lg.originalNumDenseBlock_;
+  outf[0] = lg.averageDensity_;
+  outf[1] = lg.originalAverageDensity_;
+}
+
 // checkOneData<float> applied element-wise; returns #mismatches.
 size_t ref_check_data(const float* a, const float* b, size_t n) {
   size_t e = 0;
@@ -101,3 +125,9 @@ void ref_mtx_copy(uint32_t* rowOff, uint32_t* colIdx, float* values) {
 }
 
 }  // extern "C"
+
+// src/BSMR.cpp also references the two GPU entry points of src/rowReordering.cu; they are never reached from the
+// doors above (no GPU in the CPU suite) and only exist so that libref_cpu.so has no undefined symbols.
+#include <cstdlib>
+UIN calculateBlockSize(const sparseMatrix::CSR<float>&) { std::abort(); }
+std::vector<UIN> bsa_rowReordering_gpu(const sparseMatrix::CSR<float>&, float, UIN, int&, float&) { std::abort(); }

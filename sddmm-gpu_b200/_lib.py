@@ -26,6 +26,11 @@ class LayoutInfo(C.Structure):
         "numDenseThreadBlocks", "numSparseThreadBlocks")]
 
 
+class Eval(C.Structure):
+    _fields_ = [("numDenseBlock", C.c_uint32), ("averageDensity", C.c_float), ("numDenseThreadBlocks", C.c_uint32),
+                ("numSparseThreadBlocks", C.c_uint32), ("numDenseData", C.c_uint32), ("numSparseData", C.c_uint32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("rowReorderMs", C.c_float), ("colReorderMs", C.c_float), ("rphmMs", C.c_float),
                 ("sddmmMs", C.c_float), ("numClusters", C.c_int32), ("blockSize", C.c_uint32)]
@@ -88,6 +93,9 @@ def lib():
     L.sddmm_host_sync.argtypes = [vp]
     L.sddmm_host.argtypes = [vp, vp, u32, u32, u32, u32, vp, vp, f32, f32, u32, vp, C.POINTER(Stats), C.POINTER(vp)]
     L.bsmr_shard_plan.argtypes = [vp, vp, u32, u32, vp]
+    L.bsmr_layout_eval.argtypes = [vp, f32, C.POINTER(Eval)]
+    L.bsmr_original_block_stats_dev.argtypes = [vp, vp, u32, u32, u32, f32, vp, vp, vp]
+    L.bsmr_original_block_stats.argtypes = [vp, vp, u32, u32, u32, f32, vp, vp]
     _lib = L
     return L
 

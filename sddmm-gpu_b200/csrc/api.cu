@@ -4,6 +4,7 @@
 #include <mutex>
 #include <vector>
 
+#include "eval_stats.cuh"
 #include "layout.cuh"
 #include "reorder_rows.cuh"
 #include "sddmm_kernels.cuh"
@@ -162,6 +163,35 @@ int bsmr_layout_load(const char* path, bsmr_layout** out) {
   require_device();
   require(path && out, "null pointer");
   *out = layout_load(path);
+  API_END
+}
+
+int bsmr_layout_eval(const bsmr_layout* L, float delta, bsmr_eval* out) {
+  API_BEGIN
+  require_device();
+  require(L && out, "null pointer");
+  layout_eval(L, delta, out, nullptr);
+  API_END
+}
+int bsmr_original_block_stats_dev(const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N,
+                                  uint32_t nnz, float delta, uint32_t* numDenseBlocks, float* averageDensity,
+                                  void* stream) {
+  API_BEGIN
+  require_device();
+  require(d_rowOff && (d_colIdx || nnz == 0) && numDenseBlocks && averageDensity, "null pointer");
+  original_block_stats_dev(d_rowOff, d_colIdx, M, N, nnz, delta, numDenseBlocks, averageDensity,
+                           static_cast<cudaStream_t>(stream));
+  API_END
+}
+int bsmr_original_block_stats(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, uint32_t N,
+                              uint32_t nnz, float delta, uint32_t* numDenseBlocks, float* averageDensity) {
+  API_BEGIN
+  require_device();
+  require(h_rowOff && (h_colIdx || nnz == 0) && numDenseBlocks && averageDensity, "null pointer");
+  DevBuf<u32> ro((size_t)M + 1), ci(nnz ? nnz : 1);
+  SB_CUDA(cudaMemcpy(ro.get(), h_rowOff, ((size_t)M + 1) * 4, cudaMemcpyHostToDevice));
+  SB_CUDA(cudaMemcpy(ci.get(), h_colIdx, (size_t)nnz * 4, cudaMemcpyHostToDevice));
+  original_block_stats_dev(ro.get(), ci.get(), M, N, nnz, delta, numDenseBlocks, averageDensity, nullptr);
   API_END
 }
 

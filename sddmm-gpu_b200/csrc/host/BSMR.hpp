@@ -76,3 +76,9 @@ class RPHM {
   LayoutPtr layout_;
   bsmr_layout_info info_{};
 };
+
+struct Logger;
+// evaluationReordering(matrix, bsmr, logger)  <- src/BSMR.cpp:826-925 (+ :953-994): fills the logger's
+// numDenseBlock_/averageDensity_/thread-block and data counts and the original-matrix statistics.
+// The layout of `rphm` is what the BSMR object describes; the counting runs on the device.
+void evaluationReordering(const sparseMatrix::CSR<float>& matrix, const RPHM& rphm, Logger& logger);

@@ -14,6 +14,9 @@ struct Logger {
   size_t M_ = 0, N_ = 0, K_ = 0, NNZ_ = 0;
   float sparsity_ = 0.f;
   int numRowPanels_ = 0, numDenseBlock_ = 0, numDenseThreadBlocks_ = 0, numSparseThreadBlocks_ = 0;
+  int originalNumDenseBlock_ = 0;
+  float originalAverageDensity_ = 0.f, errorRate_ = 0.f;
+  unsigned blockDimDense_ = 128, blockDimSparse_ = 1024;
   unsigned numDenseData_ = 0, numSparseData_ = 0;
   int numITER_ = 10, numClusters_ = 1;
   float alpha_ = 0.3f, delta_ = 0.3f, averageDensity_ = 0.f;
@@ -40,6 +43,8 @@ struct Logger {
     out << "[matrixA storageOrder : row_major]\n[matrixB storageOrder : col_major]\n";
     out << "[Num iterations : " << numITER_ << "]\n";
     out << "[NumRowPanel : " << numRowPanels_ << "]\n";
+    out << "[original_numDenseBlock : " << originalNumDenseBlock_ << "]\n";
+    out << "[original_averageDensity : " << originalAverageDensity_ << "]\n";
     out << "[bsmr_alpha : " << alpha_ << "]\n[bsmr_delta : " << delta_ << "]\n";
     out << "[bsmr_numClusters : " << numClusters_ << "]\n";
     out << "[bsmr_numDenseBlock : " << numDenseBlock_ << "]\n";
@@ -47,13 +52,21 @@ struct Logger {
     out << "[bsmr_rowReordering : " << rowReorderingTime_ << "]\n";
     out << "[bsmr_colReordering : " << colReorderingTime_ << "]\n";
     out << "[bsmr_reordering : " << reorderingTime_ << "]\n";
+    out << "[blockDim_dense : " << blockDimDense_ << ", 1, 1]\n";
+    out << "[blockDim_sparse : " << blockDimSparse_ << ", 1, 1]\n";
     out << "[bsmr_numDenseThreadBlocks : " << numDenseThreadBlocks_ << "]\n";
     out << "[bsmr_numSparseThreadBlocks : " << numSparseThreadBlocks_ << "]\n";
+    out << "[bsmr_threadBlockRatio : " << std::fixed << std::setprecision(2)
+        << static_cast<float>(numDenseThreadBlocks_) / numSparseThreadBlocks_ << "]\n";
     out << "[bsmr_numDenseData : " << numDenseData_ << "]\n";
     out << "[bsmr_numSparseData : " << numSparseData_ << "]\n";
+    out << "[bsmr_dataRatio: " << std::fixed << std::setprecision(2)
+        << static_cast<float>(numDenseData_) / numSparseData_ << "]\n";
     const double flops = 2.0 * static_cast<double>(NNZ_) * static_cast<double>(K_);
     out << "[bsmr_gflops : " << (flops / (sddmmTime_ * 1e6)) << "]\n";   // Logger.hpp:178-180
     out << "[bsmr_sddmm : " << sddmmTime_ << "]\n";
+    if (errorRate_ > 0)
+      out << "[checkResults : NO PASS Error rate : " << std::fixed << std::setprecision(2) << errorRate_ << "%]\n";
     out << "[b200_block_size : " << blockSize_ << "]\n";
     out << "[b200_rphm_build : " << rphmTime_ << "]\n";
     out << "[b200_dense_kernel_ms : " << denseTime_ << "]\n";

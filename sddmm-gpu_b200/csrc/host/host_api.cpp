@@ -113,8 +113,26 @@ void sddmm_gpu(UIN, UIN, UIN K, const float* dA, const float* dB, const RPHM& rp
                               &t), "sddmm_run_timed_dev"))
     return;
   logger.sddmmTime_ = t;
+  logger.blockDimSparse_ = (K % 32u == 0 && K >= 256u && K <= 512u) ? 512u : (K % 32u == 0 && K <= 512u) ? 1024u : 256u;
   logger.denseTime_ = d;
   logger.sparseTime_ = s;
+}
+
+void evaluationReordering(const sparseMatrix::CSR<float>& matrix, const RPHM& rphm, Logger& logger) {
+  bsmr_eval ev{};
+  if (!ok(bsmr_layout_eval(rphm.layout().get(), logger.delta_, &ev), "bsmr_layout_eval")) return;
+  uint32_t nd = 0;
+  float ad = 0.f;
+  ok(bsmr_original_block_stats(matrix.rowOffsets().data(), matrix.colIndices().data(), matrix.row(), matrix.col(),
+                               matrix.nnz(), logger.delta_, &nd, &ad), "bsmr_original_block_stats");
+  logger.numDenseBlock_ = static_cast<int>(ev.numDenseBlock);
+  logger.averageDensity_ = ev.averageDensity;
+  logger.numDenseThreadBlocks_ = static_cast<int>(ev.numDenseThreadBlocks);
+  logger.numSparseThreadBlocks_ = static_cast<int>(ev.numSparseThreadBlocks);
+  logger.numSparseData_ = ev.numSparseData;
+  logger.numDenseData_ = ev.numDenseData;
+  logger.originalNumDenseBlock_ = static_cast<int>(nd);
+  logger.originalAverageDensity_ = ad;
 }
 
 void sddmm(const Options& options, const Matrix<float>& A, const Matrix<float>& B, sparseMatrix::CSR<float>& P,
@@ -130,15 +148,8 @@ void sddmm(const Options& options, const Matrix<float>& A, const Matrix<float>& 
   logger.numClusters_ = bsmr.numClusters();
   logger.blockSize_ = bsmr.blockSize();
   RPHM rphm(P, bsmr);
-  logger.numDenseBlock_ = static_cast<int>(rphm.getNumDenseBlocks());
-  logger.numDenseThreadBlocks_ = static_cast<int>(rphm.numDenseThreadBlocks());
-  logger.numSparseThreadBlocks_ = static_cast<int>(rphm.numSparseThreadBlocks());
-  logger.numDenseData_ = rphm.numDenseValues();
-  logger.numSparseData_ = rphm.numSparseValues();
-  logger.averageDensity_ = rphm.getNumDenseBlocks()
-                               ? static_cast<float>(rphm.numDenseValues()) / (256.0f * rphm.getNumDenseBlocks())
-                               : 0.f;
   sddmm_gpu(A, B, rphm, P, logger);
+  evaluationReordering(P, rphm, logger);  // src/sddmm.cu:32
 }
 
 // ---- checker (verification only) ---------------------------------------------------------------------
@@ -199,10 +210,8 @@ void sddmm_testMode(const Options& options, sparseMatrix::CSR<float>& P) {
         logger.reorderingTime_ = bsmr.reorderingTime();
         logger.numRowPanels_ = bsmr.numRowPanels();
         logger.numClusters_ = bsmr.numClusters();
-        logger.numDenseBlock_ = static_cast<int>(rphm.getNumDenseBlocks());
-        logger.numDenseData_ = rphm.numDenseValues();
-        logger.numSparseData_ = rphm.numSparseValues();
         sddmm_gpu(A, B, rphm, P, logger);
+        evaluationReordering(P, rphm, logger);  // src/sddmm.cu:102
         const std::string f = options.outputLogDirectory() + "BSMR_k_" + std::to_string(k) + "_a_" + trimmed(alpha) +
                               "_d_" + trimmed(delta) + ".log";
         std::ofstream fout(f, std::ios::app);

@@ -313,6 +313,22 @@ def dispersion_dev(row_off_t, col_idx_t, M, N, block_size):
     return out[:M], nb.value
 
 
+def evaluationReordering(S, layout, delta):
+    """evaluationReordering(matrix, bsmr, logger)  src/BSMR.cpp:826-925 plus the original-matrix statistics
+    (:953-994): the dict of values the reference logs, computed on the device."""
+    L = _lib.lib()
+    lay = layout.layout() if hasattr(layout, "layout") else layout
+    ev = _lib.Eval()
+    check(L.bsmr_layout_eval(lay.handle, float(delta), C.byref(ev)))
+    nd, ad = C.c_uint32(0), C.c_float(0)
+    check(L.bsmr_original_block_stats(S.row_off.ctypes.data, S.col_idx.ctypes.data, S.M, S.N, S.nnz, float(delta),
+                                      C.byref(nd), C.byref(ad)))
+    return dict(numDenseBlock=int(ev.numDenseBlock), averageDensity=float(ev.averageDensity),
+                numDenseThreadBlocks=int(ev.numDenseThreadBlocks), numSparseThreadBlocks=int(ev.numSparseThreadBlocks),
+                numDenseData=int(ev.numDenseData), numSparseData=int(ev.numSparseData),
+                originalNumDenseBlock=int(nd.value), originalAverageDensity=float(ad.value))
+
+
 def shard_plan(S, reordered_rows, num_shards):
     L = _lib.lib()
     R = _np_u32(reordered_rows)

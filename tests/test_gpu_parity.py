@@ -94,6 +94,36 @@ def test_layout_bitexact(name):
     assert info.maxNumSparseColBlocksInRowPanel == rp["maxNumSparseColBlocksInRowPanel"]
 
 
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_evaluation_reordering_matches_oracle(name):
+    """the statistics the reference logs after every run (evaluationReordering, BSMR.cpp:826-994), computed on the
+    device; integers exact, the two average densities to float rounding."""
+    S, alpha, delta, K = CASES[name]
+    R = O.row_reorder(S, alpha, _bs(S))["reorderedRows"]
+    b = pkg.BSMR().colReordering(delta, S, R)
+    got = pkg.evaluationReordering(S, b, delta)
+    want = O.evaluation_reordering(S, R, O.col_reorder(S, R, delta), delta)
+    for k, v in want.items():
+        if isinstance(v, float):
+            assert got[k] == pytest.approx(v, rel=2e-6, abs=1e-7), (k, got[k], v)
+        else:
+            assert got[k] == v, (k, got[k], v)
+
+
+def test_original_block_stats_edges_and_threshold():
+    """clipped edge blocks (M, N not multiples of 16), every threshold side, empty rows."""
+    S = gen.with_empty_rows(gen.dlmc_magnitude_mask(203, 117, 0.5, 3), 4)
+    R = np.nonzero(np.diff(S.row_off.astype(np.int64)))[0].astype(np.uint32)
+    for delta in (0.0, 0.25, 0.5, 0.75, 1.0, 1.5):
+        lay = pkg.BSMR().colReordering(delta, S, R)
+        got = pkg.evaluationReordering(S, lay, delta)
+        want = O.evaluation_reordering(S, R, O.col_reorder(S, R, delta), delta)
+        assert got["originalNumDenseBlock"] == want["originalNumDenseBlock"], delta
+        assert got["originalAverageDensity"] == pytest.approx(want["originalAverageDensity"], rel=2e-6, abs=1e-7)
+        assert got["numDenseBlock"] == want["numDenseBlock"] and got["numSparseData"] == want["numSparseData"]
+        assert got["averageDensity"] == pytest.approx(want["averageDensity"], rel=2e-6, abs=1e-7)
+
+
 @pytest.mark.parametrize("delta", [0.0, 0.05, 0.5, 0.9, 1.1])
 def test_layout_delta_sweep(delta):
     S = gen.dlmc_magnitude_mask(256, 512, 0.8, 12)
@@ -251,6 +281,18 @@ def test_cli_binary_matches_reference_contract(tmp_path):
     assert int(kv["bsmr_numDenseBlock"]) == int(cr["denseColOffsets"][-1]) // 16
     assert int(kv["bsmr_numSparseData"]) == int(cr["sparseValueOffsets"][-1])
     assert float(kv["bsmr_gflops"]) > 0
+    # every key scripts/analyze_results.cpp parses is there, with evaluationReordering's values (src/sddmm.cu:32)
+    ev = O.evaluation_reordering(S, rr["reorderedRows"], cr, 0.3)
+    assert int(kv["original_numDenseBlock"]) == ev["originalNumDenseBlock"]
+    assert float(kv["original_averageDensity"]) == pytest.approx(ev["originalAverageDensity"], abs=0.006)  # %.2f
+    assert float(kv["bsmr_averageDensity"]) == pytest.approx(ev["averageDensity"], abs=0.006)
+    assert int(kv["bsmr_numDenseData"]) == ev["numDenseData"]
+    assert int(kv["bsmr_numDenseThreadBlocks"]) == ev["numDenseThreadBlocks"]
+    assert int(kv["bsmr_numSparseThreadBlocks"]) == ev["numSparseThreadBlocks"]
+    for key in ("blockDim_dense", "blockDim_sparse", "bsmr_threadBlockRatio", "bsmr_rowReordering", "bsmr_colReordering",
+                "bsmr_reordering", "bsmr_numClusters", "bsmr_alpha", "bsmr_delta", "bsmr_sddmm"):
+        assert key in kv, key
+    assert "[bsmr_dataRatio: " in out
     # positional form: prog file K
     p = subprocess.run([exe, mtx, "32"], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0 and "[K : 32]" in p.stdout

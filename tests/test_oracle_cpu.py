@@ -219,3 +219,21 @@ def test_cpp_host_loader_matches_oracle(tmp_path, order):
     open(bad, "w").write("%%MatrixMarket\n3 3 3\n1 1 1\n2 2 1\n1 1 1\n")
     r = subprocess.run([exe, "-f", bad, "-x", "1"], capture_output=True, text=True, timeout=60)
     assert r.returncode != 0 and "duplicate" in r.stderr
+
+
+@needs_ref
+@pytest.mark.parametrize("delta", [0.1, 0.3, 0.6])
+def test_evaluation_reordering_equals_reference_host_code(delta):
+    """oracle_evaluation_reordering / oracle_original_block_stats against the reference's own evaluationReordering
+    (src/BSMR.cpp:826-994), run on the CPU through its BSMR::colReordering."""
+    for S in (gen.block_structured(512, 768, 6, 96, 0.8, seed=11, noise=0.004), gen.rmat(10, 8, 3),
+              gen.with_empty_rows(gen.bernoulli_mask(200, 333, 0.6, 4), 5), gen.uniform_random(37, 50, 0.3, 9),
+              gen.dlmc_magnitude_mask(256, 256, 0.7, 30)):
+        R = O.row_reorder(S, 0.3, 16)["reorderedRows"]
+        cr = O.col_reorder(S, R, delta)
+        a, b = O.evaluation_reordering(S, R, cr, delta), O.ref_evaluation_reordering(S, R, delta)
+        for k in b:
+            if isinstance(b[k], float):
+                assert a[k] == pytest.approx(b[k], rel=1e-6, abs=1e-7), (S.name, k, a[k], b[k])
+            else:
+                assert a[k] == b[k], (S.name, k, a[k], b[k])
