@@ -662,9 +662,13 @@ const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStre
                                                     kA.get(), vA.get());
   SB_LAUNCH_CHECK();
   const int w = radix_sort_pairs<u64>(kA.get(), kB.get(), vA.get(), vB.get(), n, 0, rowBits + colBits + spBits, s);
-  sp->col.alloc(n);
-  sp->idx.alloc(n);
-  sp->row.alloc(n);
+  // 16 slack entries: the residual kernel reads metadata in aligned blocks of 8 that may straddle the end
+  sp->col.alloc((size_t)n + 16);
+  sp->idx.alloc((size_t)n + 16);
+  sp->row.alloc((size_t)n + 16);
+  SB_CUDA(cudaMemsetAsync(sp->col.get() + n, 0xFF, 16 * sizeof(u32), s));
+  SB_CUDA(cudaMemsetAsync(sp->idx.get() + n, 0, 16 * sizeof(u32), s));
+  SB_CUDA(cudaMemsetAsync(sp->row.get() + n, 0, 16 * sizeof(unsigned short), s));
   DevBuf<u32> nRuns(1);
   SB_CUDA(cudaMemsetAsync(nRuns.get(), 0, 4, s));
   k_sp_unpack<<<grid_for(n), 256, 0, s>>>(w ? kB.get() : kA.get(), w ? vB.get() : vA.get(),

@@ -145,42 +145,55 @@ k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restri
   __syncthreads();
 
   const u32 grp = threadIdx.x >> 3, gl = threadIdx.x & 7u;
-  const u32 n = segEnd - segBeg;
-  const u32 per = (((n + kGroups - 1) / kGroups) + 7u) & ~7u;  // entries per group, multiple of 8
-  const u32 nBlocks = per >> 3;                                 // uniform over the whole CTA
-  const u32 gBeg = min(segEnd, segBeg + grp * per);
-  const u32 gEnd = min(segEnd, gBeg + per);
+  // Groups own 8-aligned (absolute index) slices of the segment, so metadata comes in aligned 8-entry blocks:
+  // two 16-byte loads of columns and one of rows, the same addresses for the 8 lanes of a group.  Only the
+  // first / last group see entries of a neighbouring segment in their blocks; those are masked out.
+  const u32 aStart = segBeg & ~7u;
+  const u32 per = (((segEnd - aStart + kGroups - 1) / kGroups) + 7u) & ~7u;  // multiple of 8
+  const u32 nBlocks = per >> 3;                                              // uniform over the CTA
+  const u32 aBeg = min(aStart + grp * per, (segEnd + 7u) & ~7u);
+  const u32 gBeg = max(aBeg, segBeg);
+  const u32 gEnd = min(segEnd, aBeg + per);
   float4 breg[NB];
 #pragma unroll
   for (int j = 0; j < NB; ++j) breg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   u32 prevCol = 0xFFFFFFFFu;
-  u32 mc = 0xFFFFFFFFu, mr = 0, mi = 0;
-  if (gBeg + gl < gEnd) {
-    mc = __ldg(spCol + gBeg + gl);
-    mr = __ldg(spRow + gBeg + gl);
-    mi = __ldg(spIdx + gBeg + gl);
+  const uint4* col4 = reinterpret_cast<const uint4*>(spCol);
+  const uint4* row4 = reinterpret_cast<const uint4*>(spRow);
+  uint4 c0 = make_uint4(~0u, ~0u, ~0u, ~0u), c1 = c0, r8 = make_uint4(0, 0, 0, 0);
+  u32 mi = 0;
+  if (aBeg < gEnd) {
+    c0 = __ldg(col4 + (aBeg >> 2));
+    c1 = __ldg(col4 + (aBeg >> 2) + 1);
+    r8 = __ldg(row4 + (aBeg >> 3));
+    mi = __ldg(spIdx + aBeg + gl);
   }
   for (u32 blk = 0; blk < nBlocks; ++blk) {
-    const u32 base = gBeg + blk * 8u;
-    // next block's metadata, one entry per lane
-    u32 nc = 0xFFFFFFFFu, nr = 0, ni = 0;
-    if (base + 8u + gl < gEnd) {
-      nc = __ldg(spCol + base + 8u + gl);
-      nr = __ldg(spRow + base + 8u + gl);
+    const u32 base = aBeg + blk * 8u;
+    uint4 nc0 = make_uint4(~0u, ~0u, ~0u, ~0u), nc1 = nc0, nr8 = make_uint4(0, 0, 0, 0);
+    u32 ni = 0;
+    if (base + 8u < gEnd) {  // next block's metadata
+      nc0 = __ldg(col4 + ((base + 8u) >> 2));
+      nc1 = __ldg(col4 + ((base + 8u) >> 2) + 1);
+      nr8 = __ldg(row4 + ((base + 8u) >> 3));
       ni = __ldg(spIdx + base + 8u + gl);
     }
-    float mine = 0.f;
+    const u32 cols[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const u32 rows[8] = {r8.x & 0xFFFFu, r8.x >> 16, r8.y & 0xFFFFu, r8.y >> 16,
+                         r8.z & 0xFFFFu, r8.z >> 16, r8.w & 0xFFFFu, r8.w >> 16};
+    float acc[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-      const u32 col = __shfl_sync(0xffffffffu, mc, t, 8);
-      const u32 row = __shfl_sync(0xffffffffu, mr, t, 8);
-      if (col != prevCol && col != 0xFFFFFFFFu) {  // new column for this group: fetch its B^T row
+      const u32 e = base + t;
+      const bool live = e >= gBeg && e < gEnd;
+      const u32 col = cols[t];
+      if (live && col != prevCol) {  // this group moves on to a new column
         const float4* __restrict__ b = B4 + (size_t)col * K4 + gl;
 #pragma unroll
         for (int j = 0; j < NB; ++j) breg[j] = __ldg(b + j * 8);
         prevCol = col;
       }
-      const float4* a = sA + row * K4 + gl;
+      const float4* a = sA + rows[t] * K4 + gl;
       float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
@@ -193,14 +206,28 @@ k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restri
           acc0 = fmaf(av.z, breg[j].z, acc0); acc0 = fmaf(av.w, breg[j].w, acc0);
         }
       }
-      float acc = acc0 + acc1;
-      acc += __shfl_xor_sync(0xffffffffu, acc, 4, 8);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2, 8);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1, 8);
-      if (gl == (u32)t) mine = acc;
+      acc[t] = acc0 + acc1;
     }
-    if (mc != 0xFFFFFFFFu) P[mi] = mine;
-    mc = nc; mr = nr; mi = ni;
+    // transposing butterfly: 7 shuffles reduce 8 entries over the 8 lanes; lane gl ends with entry gl
+    float b4[4], b2[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = (gl & 4u) ? acc[i] : acc[i + 4];
+      const float keep = (gl & 4u) ? acc[i + 4] : acc[i];
+      b4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = (gl & 2u) ? b4[i] : b4[i + 2];
+      const float keep = (gl & 2u) ? b4[i + 2] : b4[i];
+      b2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2, 8);
+    }
+    const float send = (gl & 1u) ? b2[0] : b2[1];
+    const float keep = (gl & 1u) ? b2[1] : b2[0];
+    const float mine = keep + __shfl_xor_sync(0xffffffffu, send, 1, 8);
+    const u32 me = base + gl;
+    if (me >= gBeg && me < gEnd) P[mi] = mine;
+    c0 = nc0; c1 = nc1; r8 = nr8; mi = ni;
   }
 }
 
@@ -209,7 +236,8 @@ static u32 superpanel_G(u32 K) {
   if (K % 32u || K > 512u) return 0;
   const u32 NB = K / 32u;
   if (NB != 1 && NB != 2 && NB != 4 && NB != 8 && NB != 16) return 0;
-  u32 rows = (192u * 1024u) / (K * 4u);
+  static const u32 tileKB = [] { const char* e = getenv("SDDMM_B200_SP_SMEM_KB"); return e ? (u32)atoi(e) : 192u; }();
+  u32 rows = (tileKB * 1024u) / (K * 4u);
   u32 G = rows / 16u;
   if (G > 64u) G = 64u;
   return G;
