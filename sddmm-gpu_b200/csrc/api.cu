@@ -1,5 +1,7 @@
 // api.cu -- the C ABI of include/sddmm_b200.h.  Thin: argument checks, H2D/D2H for the host-buffer
 // forms, exception -> error code translation.  No CPU compute path exists behind any entry point.
+#include <algorithm>
+#include <chrono>
 #include <memory>
 #include <mutex>
 #include <vector>
@@ -12,18 +14,106 @@
 namespace sb {
 thread_local u64 g_launches = 0;
 thread_local TempState g_temp;
-TempScope::TempScope(cudaStream_t s) : saved(g_temp) {
-  static std::once_flag once;
-  std::call_once(once, [] {  // keep freed scratch memory in the pool instead of returning it to the driver
-    int dev = 0;
-    cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      unsigned long long thr = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+namespace {
+// Scratch arena behind TempScope (see common.cuh).
+struct Arena {
+  struct Block { size_t off, size; bool live; };
+  struct Chunk { char* base; size_t cap, top; std::vector<Block> blocks; };
+  std::vector<Chunk> chunks;
+  int depth = 0;
+  size_t total = 0;
+  static constexpr size_t kKeep = (size_t)64 << 20;
+  static constexpr size_t kMaxStep = (size_t)4 << 30;
+
+  void add_chunk(size_t cap) {
+    Chunk c{nullptr, cap, 0, {}};
+    static const bool dbg = getenv("SDDMM_B200_ARENA_DEBUG") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    SB_CUDA(cudaMalloc(reinterpret_cast<void**>(&c.base), cap));
+    if (dbg)
+      fprintf(stderr, "[arena] cudaMalloc %.1f MB: %.3f ms (total %.1f MB)\n", cap / 1048576.0,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(),
+              (total + cap) / 1048576.0);
+    chunks.push_back(std::move(c));
+    total += cap;
+  }
+  void* alloc(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    for (auto& c : chunks)
+      if (c.cap - c.top >= bytes) {
+        c.blocks.push_back({c.top, bytes, true});
+        c.top += bytes;
+        return c.base + (c.top - bytes);
+      }
+    add_chunk(std::max(bytes, std::max(kKeep, std::min(total, kMaxStep))));  // geometric, then 4 GB steps
+    Chunk& c = chunks.back();
+    c.blocks.push_back({0, bytes, true});
+    c.top = bytes;
+    return c.base;
+  }
+  void free(void* ptr) {
+    char* q = static_cast<char*>(ptr);
+    for (auto& c : chunks) {
+      if (q < c.base || q >= c.base + c.cap) continue;
+      const size_t off = (size_t)(q - c.base);
+      for (size_t i = c.blocks.size(); i-- > 0;)
+        if (c.blocks[i].off == off) { c.blocks[i].live = false; break; }
+      while (!c.blocks.empty() && !c.blocks.back().live) {
+        c.top = c.blocks.back().off;
+        c.blocks.pop_back();
+      }
+      return;
     }
-  });
+  }
+  void trim() {  // outermost scope ended: give the big chunks back, keep at most one small one
+    static const bool dbg = getenv("SDDMM_B200_ARENA_DEBUG") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    struct Report {
+      bool on; std::chrono::steady_clock::time_point t0; size_t n;
+      ~Report() {
+        if (on) fprintf(stderr, "[arena] trim of %zu chunks: %.3f ms\n", n,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+      }
+    } report{dbg, t0, chunks.size()};
+    bool kept = false;
+    std::vector<Chunk> keep;
+    for (auto& c : chunks) {
+      if (!kept && c.cap <= kKeep && c.blocks.empty()) {
+        kept = true;
+        keep.push_back(std::move(c));
+      } else {
+        cudaFree(c.base);
+      }
+    }
+    chunks = std::move(keep);
+    total = 0;
+    for (auto& c : chunks) total += c.cap;
+  }
+};
+thread_local Arena g_arena;
+}  // namespace
+
+void* temp_alloc(size_t bytes) { return g_arena.alloc(bytes); }
+void temp_free(void* p) { g_arena.free(p); }
+
+TempScope::TempScope(cudaStream_t s, size_t hintBytes) : saved(g_temp) {
+  if (g_arena.depth++ == 0 && hintBytes > g_arena.total) {
+    try {
+      g_arena.add_chunk(hintBytes - g_arena.total > Arena::kKeep ? hintBytes - g_arena.total : Arena::kKeep);
+    } catch (...) {
+      --g_arena.depth;
+      throw;
+    }
+  }
   g_temp.active = true;
   g_temp.stream = s;
+}
+TempScope::~TempScope() {
+  if (--g_arena.depth == 0) {
+    cudaStreamSynchronize(g_temp.stream);  // work that used arena memory is done before it is returned
+    g_arena.trim();
+  }
+  g_temp = saved;
 }
 static thread_local std::string g_err;
 void set_last_error(const std::string& m) { g_err = m; }

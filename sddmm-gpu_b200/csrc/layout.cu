@@ -419,10 +419,10 @@ bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u
     bsmr_layout_info& I = L->info;
     I.M = M; I.N = N; I.nnz = nnz; I.numRows = nR; I.numRowPanels = P; I.panelBegin = panelBegin;
     auto A = [&](bsmr_array_id id) -> DevBuf<u32>& { return L->arr[id]; };
-    A(BSMR_REORDERED_ROWS).alloc(nR ? nR : 1);
+    A(BSMR_REORDERED_ROWS).alloc(nR ? nR : 1, true);
     if (nR) SB_CUDA(cudaMemcpyAsync(A(BSMR_REORDERED_ROWS).get(), d_R + r0, (size_t)nR * 4, cudaMemcpyDeviceToDevice, s));
     for (bsmr_array_id id : {BSMR_DENSE_COL_OFFSETS, BSMR_SPARSE_COL_OFFSETS, BSMR_SPARSE_VALUE_OFFSETS, RPHM_BLOCK_OFFSETS}) {
-      A(id).alloc((size_t)P + 1);
+      A(id).alloc((size_t)P + 1, true);
       SB_CUDA(cudaMemsetAsync(A(id).get(), 0, ((size_t)P + 1) * 4, s));
     }
     Timer tCol(s);
@@ -431,7 +431,7 @@ bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u
       for (bsmr_array_id id : {BSMR_DENSE_COLS, BSMR_SPARSE_COLS, RPHM_BLOCK_VALUES, RPHM_SPARSE_VALUES,
                                RPHM_SPARSE_RELATIVE_ROWS, RPHM_SPARSE_COL_INDICES, RPHM_DENSE_ROW_PANEL_IDS,
                                RPHM_DENSE_COL_BLOCK_ITERS, RPHM_SPARSE_ROW_PANEL_IDS, RPHM_SPARSE_COL_BLOCK_ITERS})
-        A(id).alloc(1), A(id).n = 0;
+        A(id).alloc(1, true), A(id).n = 0;
       if (msCol) *msCol = tCol.stop();
       if (msRphm) *msRphm = 0.f;
       return L;
@@ -507,8 +507,8 @@ bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u
     const u32 dTot = read_u32(A(BSMR_DENSE_COL_OFFSETS).get() + P, s);
     const u32 sTot = read_u32(A(BSMR_SPARSE_COL_OFFSETS).get() + P, s);
     const u32 vTot = read_u32(A(BSMR_SPARSE_VALUE_OFFSETS).get() + P, s);
-    A(BSMR_DENSE_COLS).alloc(dTot ? dTot : 1); A(BSMR_DENSE_COLS).n = dTot;
-    A(BSMR_SPARSE_COLS).alloc(sTot ? sTot : 1); A(BSMR_SPARSE_COLS).n = sTot;
+    A(BSMR_DENSE_COLS).alloc(dTot ? dTot : 1, true); A(BSMR_DENSE_COLS).n = dTot;
+    A(BSMR_SPARSE_COLS).alloc(sTot ? sTot : 1, true); A(BSMR_SPARSE_COLS).n = sTot;
     k_write_cols<<<grid_for(numGroups), 256, 0, s>>>(sortedKey, order, keys, gStart.get(), pStart.get(), nd.get(),
                                                     A(BSMR_DENSE_COL_OFFSETS).get(), A(BSMR_SPARSE_COL_OFFSETS).get(),
                                                     numGroups, colBits, A(BSMR_DENSE_COLS).get(),
@@ -527,10 +527,10 @@ bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u
     scan_counts(nBlk.get(), A(RPHM_BLOCK_OFFSETS).get(), P, s);
     const u32 numBlocks = read_u32(A(RPHM_BLOCK_OFFSETS).get() + P, s);
     const size_t nbv = (size_t)numBlocks * 256u;
-    A(RPHM_BLOCK_VALUES).alloc(nbv ? nbv : 1); A(RPHM_BLOCK_VALUES).n = nbv;
+    A(RPHM_BLOCK_VALUES).alloc(nbv ? nbv : 1, true); A(RPHM_BLOCK_VALUES).n = nbv;
     fill<u32>(A(RPHM_BLOCK_VALUES).get(), nbv, kNull, s);
     for (bsmr_array_id id : {RPHM_SPARSE_VALUES, RPHM_SPARSE_RELATIVE_ROWS, RPHM_SPARSE_COL_INDICES}) {
-      A(id).alloc(vTot ? vTot : 1);
+      A(id).alloc(vTot ? vTot : 1, true);
       A(id).n = vTot;
     }
     DevBuf<u32> gSparseOff((size_t)numGroups + 1);
@@ -555,12 +555,12 @@ bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u
     const u32 nDTB = read_u32(dtbOff.get() + P, s), nSTB = read_u32(stbOff.get() + P, s);
     L->numDenseWork = read_u32(myDOff.get() + P, s);
     L->numSparseWork = read_u32(mySOff.get() + P, s);
-    A(RPHM_DENSE_ROW_PANEL_IDS).alloc(nDTB ? nDTB : 1); A(RPHM_DENSE_ROW_PANEL_IDS).n = nDTB;
-    A(RPHM_DENSE_COL_BLOCK_ITERS).alloc(nDTB ? nDTB : 1); A(RPHM_DENSE_COL_BLOCK_ITERS).n = nDTB;
-    A(RPHM_SPARSE_ROW_PANEL_IDS).alloc(nSTB ? nSTB : 1); A(RPHM_SPARSE_ROW_PANEL_IDS).n = nSTB;
-    A(RPHM_SPARSE_COL_BLOCK_ITERS).alloc(nSTB ? nSTB : 1); A(RPHM_SPARSE_COL_BLOCK_ITERS).n = nSTB;
-    L->denseWork.alloc(L->numDenseWork ? L->numDenseWork : 1);
-    L->sparseWork.alloc(L->numSparseWork ? L->numSparseWork : 1);
+    A(RPHM_DENSE_ROW_PANEL_IDS).alloc(nDTB ? nDTB : 1, true); A(RPHM_DENSE_ROW_PANEL_IDS).n = nDTB;
+    A(RPHM_DENSE_COL_BLOCK_ITERS).alloc(nDTB ? nDTB : 1, true); A(RPHM_DENSE_COL_BLOCK_ITERS).n = nDTB;
+    A(RPHM_SPARSE_ROW_PANEL_IDS).alloc(nSTB ? nSTB : 1, true); A(RPHM_SPARSE_ROW_PANEL_IDS).n = nSTB;
+    A(RPHM_SPARSE_COL_BLOCK_ITERS).alloc(nSTB ? nSTB : 1, true); A(RPHM_SPARSE_COL_BLOCK_ITERS).n = nSTB;
+    L->denseWork.alloc(L->numDenseWork ? L->numDenseWork : 1, true);
+    L->sparseWork.alloc(L->numSparseWork ? L->numSparseWork : 1, true);
     k_write_worklists<<<grid_for((size_t)P * 32), 256, 0, s>>>(
         A(BSMR_DENSE_COL_OFFSETS).get(), nBlk.get(), nnzSparse.get(), dtbOff.get(), stbOff.get(), myDOff.get(),
         mySOff.get(), P, A(RPHM_DENSE_ROW_PANEL_IDS).get(), A(RPHM_DENSE_COL_BLOCK_ITERS).get(),
@@ -570,7 +570,8 @@ bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u
     if (L->numSparseWork > 1) {
       const u32 nw = L->numSparseWork;
       DevBuf<u32> kA(nw), kB(nw), iA(nw), iB(nw);
-      DevBuf<uint2> sorted(nw);
+      DevBuf<uint2> sorted;
+      sorted.alloc(nw, true);  // becomes the layout's work list
       k_work_keys<<<grid_for(nw), 256, 0, s>>>(L->sparseWork.get(), nw, L->sparseChunk, kA.get());
       SB_LAUNCH_CHECK();
       iota<u32>(iA.get(), nw, 0u, s);
@@ -624,14 +625,14 @@ static void build_tiles(bsmr_layout* L, const u32* d_rowOff, const u32* d_colIdx
   SB_CUDA(cudaMemsetAsync(tid.get() + nSel, 0, 4, s));
   exclusive_scan_u32(tid.get(), tid.get(), (size_t)nSel + 1, s);
   tl->numTiles = read_u32(tid.get() + nSel, s);
-  tl->tiles.alloc(tl->numTiles);
-  tl->rowMeta.alloc((size_t)tl->numTiles * 640u);
+  tl->tiles.alloc(tl->numTiles, true);
+  tl->rowMeta.alloc((size_t)tl->numTiles * 640u, true);
   k_tile_records<<<grid_for(nSel), 256, 0, s>>>(keys, head.get(), tid.get(), nSel, ctBits, tl->tiles.get());
   SB_LAUNCH_CHECK();
   k_tile_meta<<<tl->numTiles, 128, 0, s>>>(keys, tl->tiles.get(), tl->numTiles, nSel, tl->rowMeta.get());
   SB_LAUNCH_CHECK();
   // the sorted payload IS the CSR index list; keep it
-  tl->idx.alloc(nSel);
+  tl->idx.alloc(nSel, true);
   SB_CUDA(cudaMemcpyAsync(tl->idx.get(), vals, (size_t)nSel * 4, cudaMemcpyDeviceToDevice, s));
   SB_CUDA(cudaStreamSynchronize(s));
   L->tl = std::move(tl);
@@ -663,9 +664,9 @@ const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStre
   SB_LAUNCH_CHECK();
   const int w = radix_sort_pairs<u64>(kA.get(), kB.get(), vA.get(), vB.get(), n, 0, rowBits + colBits + spBits, s);
   // 16 slack entries: the residual kernel reads metadata in aligned blocks of 8 that may straddle the end
-  sp->col.alloc((size_t)n + 16);
-  sp->idx.alloc((size_t)n + 16);
-  sp->row.alloc((size_t)n + 16);
+  sp->col.alloc((size_t)n + 16, true);
+  sp->idx.alloc((size_t)n + 16, true);
+  sp->row.alloc((size_t)n + 16, true);
   SB_CUDA(cudaMemsetAsync(sp->col.get() + n, 0xFF, 16 * sizeof(u32), s));
   SB_CUDA(cudaMemsetAsync(sp->idx.get() + n, 0, 16 * sizeof(u32), s));
   SB_CUDA(cudaMemsetAsync(sp->row.get() + n, 0, 16 * sizeof(unsigned short), s));
@@ -684,7 +685,7 @@ const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStre
     if (sl < 2048u) sl = 2048u;
     sp->segLen = (sl + 1023u) & ~1023u;
   }
-  sp->off.alloc((size_t)sp->numSp + 1);
+  sp->off.alloc((size_t)sp->numSp + 1, true);
   DevBuf<u32> segCnt(sp->numSp), segOff((size_t)sp->numSp + 1);
   k_sp_offsets<<<grid_for((size_t)sp->numSp + 1), 256, 0, s>>>(vOff, P, G, sp->numSp, sp->segLen, sp->off.get(),
                                                               segCnt.get());
@@ -693,7 +694,8 @@ const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStre
   sp->numWork = read_u32(segOff.get() + sp->numSp, s);
   if (sp->numWork) {
     const u32 nw = sp->numWork;
-    DevBuf<uint2> work(nw), sorted(nw);
+    DevBuf<uint2> work(nw), sorted;
+    sorted.alloc(nw, true);  // becomes the layout's work list
     DevBuf<u32> k1(nw), k2(nw), i1(nw), i2(nw);
     k_sp_work<<<grid_for((size_t)sp->numSp * 32), 256, 0, s>>>(segOff.get(), sp->numSp, sp->segLen, work.get(), k1.get());
     SB_LAUNCH_CHECK();
@@ -795,17 +797,17 @@ bsmr_layout* layout_load(const char* path) {
       if (n > ((u64)1 << 34)) fail(SDDMM_E_ARG, "layout cache: implausible array length");
       host.resize(n);
       get(fl.f, host.data(), n);
-      L->arr[i].alloc(n ? n : 1);
+      L->arr[i].alloc(n ? n : 1, true);
       L->arr[i].n = n;
       if (n) SB_CUDA(cudaMemcpy(L->arr[i].get(), host.data(), n * 4, cudaMemcpyHostToDevice));
     }
     std::vector<uint2> w(L->numDenseWork);
     get(fl.f, w.data(), w.size());
-    L->denseWork.alloc(L->numDenseWork ? L->numDenseWork : 1);
+    L->denseWork.alloc(L->numDenseWork ? L->numDenseWork : 1, true);
     if (L->numDenseWork) SB_CUDA(cudaMemcpy(L->denseWork.get(), w.data(), w.size() * 8, cudaMemcpyHostToDevice));
     w.resize(L->numSparseWork);
     get(fl.f, w.data(), w.size());
-    L->sparseWork.alloc(L->numSparseWork ? L->numSparseWork : 1);
+    L->sparseWork.alloc(L->numSparseWork ? L->numSparseWork : 1, true);
     if (L->numSparseWork) SB_CUDA(cudaMemcpy(L->sparseWork.get(), w.data(), w.size() * 8, cudaMemcpyHostToDevice));
     u32 hasTl = 0;
     get(fl.f, &hasTl, 1);
@@ -817,15 +819,15 @@ bsmr_layout* layout_load(const char* path) {
       if ((u64)T->numTiles > ((u64)1 << 30)) fail(SDDMM_E_ARG, "layout cache: implausible tile count");
       std::vector<uint4> tiles(T->numTiles);
       get(fl.f, tiles.data(), tiles.size());
-      T->tiles.alloc(T->numTiles ? T->numTiles : 1);
+      T->tiles.alloc(T->numTiles ? T->numTiles : 1, true);
       if (T->numTiles) SB_CUDA(cudaMemcpy(T->tiles.get(), tiles.data(), tiles.size() * 16, cudaMemcpyHostToDevice));
       host.resize((size_t)T->numTiles * 640u);
       get(fl.f, host.data(), host.size());
-      T->rowMeta.alloc(host.size() ? host.size() : 1);
+      T->rowMeta.alloc(host.size() ? host.size() : 1, true);
       if (!host.empty()) SB_CUDA(cudaMemcpy(T->rowMeta.get(), host.data(), host.size() * 4, cudaMemcpyHostToDevice));
       host.resize(T->numEntries);
       get(fl.f, host.data(), host.size());
-      T->idx.alloc(host.size() ? host.size() : 1);
+      T->idx.alloc(host.size() ? host.size() : 1, true);
       if (!host.empty()) SB_CUDA(cudaMemcpy(T->idx.get(), host.data(), host.size() * 4, cudaMemcpyHostToDevice));
       L->tl = std::move(T);
     }

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--scale", type=int, default=18)
     ap.add_argument("--sparsity", type=float, default=0.7)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--rebuild", action="store_true", help="build the layout twice and print both timings")
     ap.add_argument("--Ks", default="", help="comma list: sweep K on one layout, one JSON line per K")
     a = ap.parse_args()
     import torch
@@ -52,6 +53,10 @@ def main():
         R = torch.from_numpy(np.nonzero(lens)[0].astype(np.int32)).cuda()
         ncl, row_ms = -1, 0.0
     lay, col_ms, rphm_ms = pkg.layout_build_dev(ro, ci, S.M, S.N, R, a.delta)
+    if a.rebuild:  # second build in the same process: scratch pool already grown
+        del lay
+        lay, col2, rphm2 = pkg.layout_build_dev(ro, ci, S.M, S.N, R, a.delta)
+        print(json.dumps(dict(first_build_ms=[col_ms, rphm_ms], second_build_ms=[col2, rphm2])), flush=True)
     for K in ([int(x) for x in a.Ks.split(",")] if a.Ks else [a.K]):
         run_k(a, torch, pkg, gen, S, lay, K, ncl, row_ms, col_ms, rphm_ms)
 
