@@ -557,13 +557,17 @@ k_sddmm_tile(u32 M, u32 N, u32 K, const float* __restrict__ A, const float* __re
     mbar_wait(&mbar[last % kTlStages], (last / kTlStages) & 1u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
-  // ---- epilogue: warp w reads TMEM lanes 32*(w%4).. (rows) and the column half w/4
+  // ---- epilogue.  Phase 1: warp w reads TMEM lanes 32*(w%4).. (rows) and the column half w/4 and compacts
+  // the stored entries of its rows into shared memory (the operand stages are free once the last commit
+  // has arrived), in the tile's entry order (row, col).  Phase 2: the whole CTA walks the tile's entry list
+  // with coalesced, independent loads of the CSR indices and scatters the values.
+  float* sOut = reinterpret_cast<float*>(stages);  // <= 16384 floats = the two stages
   {
     const u32 q4 = warp & 3u, half = warp >> 2;
     const u32 r = q4 * 32u + lane;
     const u32* meta = rowMeta + (size_t)blockIdx.x * 640u + r * 5u;
     const u32 m0 = meta[0], m1 = meta[1], m2 = meta[2], m3 = meta[3];
-    u32 off = meta[4];
+    u32 off = meta[4] - tile.z;  // relative to the tile's first entry
     if (half) off += __popc(m0) + __popc(m1);
 #pragma unroll
     for (u32 qq = 0; qq < 2; ++qq) {
@@ -586,7 +590,7 @@ k_sddmm_tile(u32 M, u32 N, u32 K, const float* __restrict__ A, const float* __re
 #pragma unroll
       for (u32 b = 0; b < 32; ++b) {
         if ((mw >> b) & 1u) {
-          P[entIdx[off]] = __uint_as_float(acc[b]);
+          sOut[off] = __uint_as_float(acc[b]);
           ++off;
         }
       }
@@ -594,6 +598,20 @@ k_sddmm_tile(u32 M, u32 N, u32 K, const float* __restrict__ A, const float* __re
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  {
+    const u32 cnt = tile.w;
+    const u32* __restrict__ idx = entIdx + tile.z;
+    u32 e = tid;
+    for (; e + 3u * kTlThreads < cnt; e += 4u * kTlThreads) {
+      const u32 i0 = __ldg(idx + e), i1 = __ldg(idx + e + kTlThreads), i2 = __ldg(idx + e + 2u * kTlThreads),
+                i3 = __ldg(idx + e + 3u * kTlThreads);
+      P[i0] = sOut[e];
+      P[i1] = sOut[e + kTlThreads];
+      P[i2] = sOut[e + 2u * kTlThreads];
+      P[i3] = sOut[e + 3u * kTlThreads];
+    }
+    for (; e < cnt; e += kTlThreads) P[__ldg(idx + e)] = sOut[e];
+  }
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTlTmemCols) : "memory");
   }
