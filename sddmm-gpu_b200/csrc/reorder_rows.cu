@@ -810,6 +810,7 @@ void row_reorder_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32
     u32 grid = (u32)(perSm * device_sm_count());
     const u32 need = ceil_div(M - zeroRows, kCbWarps);
     if (grid > need) grid = need ? need : 1;
+    if (const char* e = getenv("SDDMM_B200_CLUSTER_GRID")) { const int v = atoi(e); if (v >= 1 && (u32)v < grid) grid = (u32)v; }
     void* args[] = {&a};
     SB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kCbThreads), args, smem, s));
     SB_LAUNCH_CHECK();
