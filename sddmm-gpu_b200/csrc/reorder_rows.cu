@@ -411,6 +411,7 @@ constexpr int kCbMaxG = 8;
 
 struct ClusterBatchArgs {
   u32 M, start0, nbpr, B, keptMask, G;
+  u32 laneRows;  // != 0: rows with at most this many kept blocks are evaluated one per LANE (short-row matrices)
   float alpha;
   const uint2* enc;
   const uint4* meta;
@@ -483,16 +484,148 @@ __device__ __forceinline__ void cb_apply_join(const ClusterBatchArgs& a, u32* re
   __syncthreads();
 }
 
+// One candidate row against the first kmax clusters of the batch, the whole warp on the row (entries over
+// lanes).  Returns the cluster it joins (warp-uniform) or kNull.  Clusters are tried in order; the estimate
+// decides unless it is within `tol` of alpha, then the literal reduction tree does.
+template <int TG>
+__device__ __forceinline__ u32 cb_eval_row_warp(const ClusterBatchArgs& a, const u32* rep, const u32* sSs,
+                                                const float (&nRepInv)[TG], const float (&Sa)[TG], const uint4 m,
+                                                const u32 kmax, const float tol, const u32 lane) {
+  const uint2* ent = a.enc + m.x;
+  const u32 ssCmp = m.z;
+  const float nCmpInv = ssCmp ? 1.0f / sqrtf((float)ssCmp) : 0.f;
+  float mn[TG];
+#pragma unroll
+  for (int k = 0; k < TG; ++k) mn[k] = 0.f;
+  // 4 entry loads in flight per lane (the lists stream from HBM: latency, not bandwidth, is the limit)
+  for (u32 j0 = lane; j0 < m.y; j0 += 128) {
+    uint2 en4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const u32 j = j0 + u * 32;
+      en4[u] = j < m.y ? ent[j] : make_uint2(0u, 0u);  // count 0 contributes min(.,0) = 0
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint2 en = en4[u];
+      const float b = (float)en.y * nCmpInv;
+      u32 rv[TG];
+      if constexpr (TG >= 4) {
+#pragma unroll
+        for (int q = 0; q < TG / 4; ++q) {
+          const uint4 v4 = *reinterpret_cast<const uint4*>(rep + (size_t)en.x * TG + q * 4);
+          rv[q * 4 + 0] = v4.x; rv[q * 4 + 1] = v4.y; rv[q * 4 + 2] = v4.z; rv[q * 4 + 3] = v4.w;
+        }
+      } else if constexpr (TG == 2) {
+        const uint2 v2 = *reinterpret_cast<const uint2*>(rep + (size_t)en.x * 2);
+        rv[0] = v2.x; rv[1] = v2.y;
+      } else {
+        rv[0] = rep[en.x];
+      }
+#pragma unroll
+      for (int k = 0; k < TG; ++k) mn[k] += fminf((float)rv[k] * nRepInv[k], b);  // clusters >= kmax are ignored below
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < TG; ++k) {
+    if ((u32)k < kmax) {
+#pragma unroll
+      for (int w = 16; w >= 1; w >>= 1) mn[k] += __shfl_xor_sync(0xffffffffu, mn[k], w);
+    }
+  }
+  u32 joinK = kNull;
+#pragma unroll
+  for (int k = 0; k < TG; ++k) {
+    if ((u32)k < kmax && joinK == kNull) {  // warp-uniform
+      const u32 ssRep = sSs[k];
+      bool join;
+      if (ssRep == 0 || ssCmp == 0) {
+        join = ((ssRep == 0 && ssCmp == 0) ? 1.0f : 0.0f) > a.alpha;  // rowReordering.cu:263-268
+      } else {
+        const float den = Sa[k] + (float)m.w * nCmpInv - mn[k];
+        const float est = mn[k] / den;
+        if (den > 0.f && est > a.alpha + tol) join = true;
+        else if (den > 0.f && est < a.alpha - tol) join = false;
+        else {
+          const float sim = exact_similarity_warp(rep + k, ent, m.y, a.nbpr, a.B, a.keptMask, ssRep, ssCmp, TG);
+          join = sim > a.alpha;
+          if (lane == 0) atomicAdd(a.stats + 0, 1u);
+        }
+      }
+      if (join) joinK = (u32)k;
+    }
+  }
+  return joinK;
+}
+
+// The same decision for a SHORT row by one lane on its own (no shuffles).  If any cluster that has to be
+// decided is ambiguous the lane gives up (*again = true) and the row is redone by cb_eval_row_warp.
+template <int TG>
+__device__ __forceinline__ u32 cb_eval_row_lane(const ClusterBatchArgs& a, const u32* rep, const u32* sSs,
+                                                const float (&nRepInv)[TG], const float (&Sa)[TG], const uint4 m,
+                                                const u32 kmax, const float tol, bool* again) {
+  const uint2* ent = a.enc + m.x;
+  const u32 ssCmp = m.z;
+  const float nCmpInv = ssCmp ? 1.0f / sqrtf((float)ssCmp) : 0.f;
+  float mn[TG];
+#pragma unroll
+  for (int k = 0; k < TG; ++k) mn[k] = 0.f;
+  for (u32 j0 = 0; j0 < m.y; j0 += 4) {  // 4 independent entry loads in flight
+    uint2 en4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) en4[u] = j0 + u < m.y ? ent[j0 + u] : make_uint2(0u, 0u);  // count 0 adds 0
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint2 en = en4[u];
+      const float b = (float)en.y * nCmpInv;
+      u32 rv[TG];
+      if constexpr (TG >= 4) {
+#pragma unroll
+        for (int q = 0; q < TG / 4; ++q) {
+          const uint4 v4 = *reinterpret_cast<const uint4*>(rep + (size_t)en.x * TG + q * 4);
+          rv[q * 4 + 0] = v4.x; rv[q * 4 + 1] = v4.y; rv[q * 4 + 2] = v4.z; rv[q * 4 + 3] = v4.w;
+        }
+      } else if constexpr (TG == 2) {
+        const uint2 v2 = *reinterpret_cast<const uint2*>(rep + (size_t)en.x * 2);
+        rv[0] = v2.x; rv[1] = v2.y;
+      } else {
+        rv[0] = rep[en.x];
+      }
+#pragma unroll
+      for (int k = 0; k < TG; ++k) mn[k] += fminf((float)rv[k] * nRepInv[k], b);
+    }
+  }
+  u32 joinK = kNull;
+  *again = false;
+#pragma unroll
+  for (int k = 0; k < TG; ++k) {
+    if ((u32)k < kmax && joinK == kNull && !*again) {
+      const u32 ssRep = sSs[k];
+      if (ssRep == 0 || ssCmp == 0) {
+        if (((ssRep == 0 && ssCmp == 0) ? 1.0f : 0.0f) > a.alpha) joinK = (u32)k;
+      } else {
+        const float den = Sa[k] + (float)m.w * nCmpInv - mn[k];
+        const float est = mn[k] / den;
+        if (den > 0.f && est > a.alpha + tol) joinK = (u32)k;
+        else if (!(den > 0.f && est < a.alpha - tol)) *again = true;
+      }
+    }
+  }
+  return joinK;
+}
+
 template <int TG>  // representatives interleaved: rep[block * TG + k], so one lookup serves all TG clusters
 static __global__ void __launch_bounds__(kCbThreads, 1) k_cluster_batched(ClusterBatchArgs a) {
   extern __shared__ __align__(16) u32 rep[];  // nbpr x TG accumulated histograms
   __shared__ u32 sSeed[kCbMaxG], sSs[kCbMaxG], sS1[kCbMaxG];
   __shared__ u32 sRed[kCbWarps];
   __shared__ u32 sCount;
+  __shared__ u32 sTodo[kCbThreads], sTodoCnt;
   cg::grid_group grid = cg::this_grid();
   const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const u32 totalWarps = gridDim.x * kCbWarps;
   const u32 gw = blockIdx.x * kCbWarps + warp;
+  if (threadIdx.x == 0) sTodoCnt = 0;
   volatile unsigned long long* slots = a.slots;
   volatile u32* seeds = a.seeds;
   const float tol = kTolRel * fabsf(a.alpha) + kTolAbs;
@@ -528,7 +661,8 @@ static __global__ void __launch_bounds__(kCbThreads, 1) k_cluster_batched(Cluste
       atomicAdd(a.stats + 3, 1u);
     }
     __syncthreads();
-    u32 p = sSeed[0] + 1, chunk = calm ? totalWarps * 16u : totalWarps;
+    const u32 unit = a.laneRows ? 32u : 1u;  // positions one warp looks at per step
+    u32 p = sSeed[0] + 1, chunk = (calm ? totalWarps * 16u : totalWarps) * unit;
     calm = true;
     while (p < a.M) {
       const u32 e = (a.M - p > chunk) ? p + chunk : a.M;
@@ -542,81 +676,67 @@ static __global__ void __launch_bounds__(kCbThreads, 1) k_cluster_batched(Cluste
       }
       // position -> warp: spread consecutive positions over the CTAs first (small windows use every SM)
       const u32 vw = warp * gridDim.x + blockIdx.x;
-      for (u32 pos = p + vw; pos < e; pos += totalWarps) {
-        if (__ldcg(a.cid + pos) != kNull) continue;
-        // clusters of the batch whose seed precedes this position (seeds are ascending)
-        u32 kmax = 0;
+      if (a.laneRows) {
+        // short-row matrices: a warp takes 32 consecutive positions, one per lane.  Rows that are long, or whose
+        // estimate is ambiguous, go to a per-CTA list and are then redone one per WARP (a run of long rows
+        // would otherwise be serialised inside one warp).
+        const u32 span = totalWarps * 32u;
+        const u32 nIter = (e - p + span - 1) / span;  // uniform over the grid
+        for (u32 it = 0; it < nIter; ++it) {
+          const u32 pos = p + it * span + vw * 32u + lane;
+          u32 kmax = 0;
+          uint4 m = make_uint4(0u, 0u, 0u, 0u);
+          if (pos < e && __ldcg(a.cid + pos) == kNull) {
 #pragma unroll
-        for (int k = 0; k < TG; ++k) kmax += ((u32)k < g && sSeed[k] < pos) ? 1u : 0u;
-        if (kmax == 0) continue;
-        const uint4 m = a.meta[pos];
-        const uint2* ent = a.enc + m.x;
-        const u32 ssCmp = m.z;
-        const float nCmpInv = ssCmp ? 1.0f / sqrtf((float)ssCmp) : 0.f;
-        float mn[TG];
-#pragma unroll
-        for (int k = 0; k < TG; ++k) mn[k] = 0.f;
-        // 4 entry loads in flight per lane (the lists stream from HBM: latency, not bandwidth, is the limit)
-        for (u32 j0 = lane; j0 < m.y; j0 += 128) {
-          uint2 en4[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const u32 j = j0 + u * 32;
-            en4[u] = j < m.y ? ent[j] : make_uint2(0u, 0u);  // count 0 contributes min(.,0) = 0
+            for (int k = 0; k < TG; ++k) kmax += ((u32)k < g && sSeed[k] < pos) ? 1u : 0u;
+            if (kmax) m = a.meta[pos];
           }
+          u32 joinK = kNull;
+          bool again = false;
+          if (kmax) {
+            if (m.y <= a.laneRows) joinK = cb_eval_row_lane<TG>(a, rep, sSs, nRepInv, Sa, m, kmax, tol, &again);
+            else again = true;
+          }
+          if (again) {
+            sTodo[atomicAdd(&sTodoCnt, 1u)] = pos;  // at most one per thread and step
+            atomicAdd(a.stats + 4, 1u);
+          }
+          // lanes hold ascending positions: only the first accepting lane can be the window's first joiner
+          const unsigned acc = __ballot_sync(0xffffffffu, joinK != kNull);
+          if (acc && (int)lane == __ffs(acc) - 1) {
+            atomicMin(a.slots + slot, ((unsigned long long)pos << 8) | (unsigned long long)joinK);
+            atomicAdd(a.accepts + slot, (u32)__popc(acc));
+          }
+          __syncthreads();
+          const u32 nTodo = sTodoCnt;
+          for (u32 i = warp; i < nTodo; i += kCbWarps) {
+            const u32 tp = sTodo[i];
+            u32 ks = 0;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint2 en = en4[u];
-            const float b = (float)en.y * nCmpInv;
-            u32 rv[TG];
-            if constexpr (TG >= 4) {
-#pragma unroll
-              for (int q = 0; q < TG / 4; ++q) {
-                const uint4 v4 = *reinterpret_cast<const uint4*>(rep + (size_t)en.x * TG + q * 4);
-                rv[q * 4 + 0] = v4.x; rv[q * 4 + 1] = v4.y; rv[q * 4 + 2] = v4.z; rv[q * 4 + 3] = v4.w;
-              }
-            } else if constexpr (TG == 2) {
-              const uint2 v2 = *reinterpret_cast<const uint2*>(rep + (size_t)en.x * 2);
-              rv[0] = v2.x; rv[1] = v2.y;
-            } else {
-              rv[0] = rep[en.x];
+            for (int k = 0; k < TG; ++k) ks += ((u32)k < g && sSeed[k] < tp) ? 1u : 0u;
+            const u32 jk = cb_eval_row_warp<TG>(a, rep, sSs, nRepInv, Sa, a.meta[tp], ks, tol, lane);
+            if (jk != kNull && lane == 0) {
+              atomicMin(a.slots + slot, ((unsigned long long)tp << 8) | (unsigned long long)jk);
+              atomicAdd(a.accepts + slot, 1u);
             }
-#pragma unroll
-            for (int k = 0; k < TG; ++k) mn[k] += fminf((float)rv[k] * nRepInv[k], b);  // clusters >= kmax are ignored below
           }
+          __syncthreads();
+          if (threadIdx.x == 0) sTodoCnt = 0;
         }
+      } else {
+        for (u32 pos = p + vw; pos < e; pos += totalWarps) {
+          if (__ldcg(a.cid + pos) != kNull) continue;
+          // clusters of the batch whose seed precedes this position (seeds are ascending)
+          u32 kmax = 0;
 #pragma unroll
-        for (int k = 0; k < TG; ++k) {
-          if ((u32)k < kmax) {
-#pragma unroll
-            for (int w = 16; w >= 1; w >>= 1) mn[k] += __shfl_xor_sync(0xffffffffu, mn[k], w);
+          for (int k = 0; k < TG; ++k) kmax += ((u32)k < g && sSeed[k] < pos) ? 1u : 0u;
+          if (kmax == 0) continue;
+          const uint4 m = a.meta[pos];
+          const u32 joinK = cb_eval_row_warp<TG>(a, rep, sSs, nRepInv, Sa, m, kmax, tol, lane);
+          if (joinK != kNull && lane == 0) {
+            atomicMin(a.slots + slot, ((unsigned long long)pos << 8) | (unsigned long long)joinK);
+            atomicAdd(a.accepts + slot, 1u);
           }
-        }
-        u32 joinK = kNull;
-#pragma unroll
-        for (int k = 0; k < TG; ++k) {
-          if ((u32)k < kmax && joinK == kNull) {  // warp-uniform
-            const u32 ssRep = sSs[k];
-            bool join;
-            if (ssRep == 0 || ssCmp == 0) {
-              join = ((ssRep == 0 && ssCmp == 0) ? 1.0f : 0.0f) > a.alpha;  // rowReordering.cu:263-268
-            } else {
-              const float den = Sa[k] + (float)m.w * nCmpInv - mn[k];
-              const float est = mn[k] / den;
-              if (den > 0.f && est > a.alpha + tol) join = true;
-              else if (den > 0.f && est < a.alpha - tol) join = false;
-              else {
-                const float sim = exact_similarity_warp(rep + k, ent, m.y, a.nbpr, a.B, a.keptMask, ssRep, ssCmp, TG);
-                join = sim > a.alpha;
-                if (lane == 0) atomicAdd(a.stats + 0, 1u);
-              }
-            }
-            if (join) joinK = (u32)k;
-          }
-        }
-        if (joinK != kNull && lane == 0) {
-          atomicMin(a.slots + slot, ((unsigned long long)pos << 8) | (unsigned long long)joinK);
-          atomicAdd(a.accepts + slot, 1u);
         }
       }
       __threadfence();
@@ -648,11 +768,13 @@ static __global__ void __launch_bounds__(kCbThreads, 1) k_cluster_batched(Cluste
         p = f + 1;
         // rows tend to join in streaks and only the first joiner of a window counts: look at a few
         // candidates right behind it (one per CTA), then widen again while nothing joins
-        chunk = gridDim.x;
+        chunk = gridDim.x * unit;
         calm = false;
       } else {
         p = e;
-        if (chunk < totalWarps * 16u) chunk *= 2;
+        // every window costs a grid-wide barrier: with one candidate per lane a wasted position is cheap, so
+        // widen faster
+        if (chunk < totalWarps * 16u * unit) chunk *= a.laneRows ? 8u : 2u;
       }
       ++iter;
     }
@@ -790,6 +912,12 @@ void row_reorder_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32
     a.stats = statsBuf.get();
     a.accepts = acceptsBuf.get();
     a.pend = pendBuf.get();
+    // short-row matrices (graphs): evaluate one candidate per lane (SDDMM_B200_CLUSTER_LANE=0 turns it off)
+    {
+      static const int laneCfg = [] { const char* e = getenv("SDDMM_B200_CLUSTER_LANE"); return e ? atoi(e) : -1; }();
+      const double avgEnt = (double)totalEnt / (double)(M - zeroRows);
+      a.laneRows = laneCfg == 0 ? 0u : laneCfg > 0 ? (u32)laneCfg : (avgEnt <= 24.0 ? 64u : 0u);
+    }
     SB_CUDA(cudaMemsetAsync(acceptsBuf.get(), 0, 16, s));
     SB_CUDA(cudaMemsetAsync(pendBuf.get(), 0xFF, (size_t)M * 4, s));
     u32 G = (u32)((200u * 1024u) / ((size_t)nbpr * 4));
@@ -815,6 +943,13 @@ void row_reorder_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32
     SB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kCbThreads), args, smem, s));
     SB_LAUNCH_CHECK();
     SB_CUDA(cudaMemcpyAsync(&exactEvals, statsBuf.get(), 4, cudaMemcpyDeviceToHost, s));
+    if (getenv("SDDMM_B200_CLUSTER_DEBUG")) {
+      u32 hs[8];
+      SB_CUDA(cudaMemcpyAsync(hs, statsBuf.get(), sizeof hs, cudaMemcpyDeviceToHost, s));
+      SB_CUDA(cudaStreamSynchronize(s));
+      fprintf(stderr, "[cluster] rows %u entries %u G %u grid %u laneRows %u: exact %u clusters %u windows %u batches %u redo %u\n",
+              M - zeroRows, totalEnt, G, grid, a.laneRows, hs[0], hs[1], hs[2], hs[3], hs[4]);
+    }
     SB_CUDA(cudaMemcpyAsync(ncl.get(), statsBuf.get() + 1, 4, cudaMemcpyDeviceToDevice, s));
   } else if (zeroRows < M) {
     ClusterArgs a;
