@@ -14,6 +14,9 @@
 //      the residual COO arrays in exactly the reference's order (appendix B of SURVEY.md).
 #include <vector>
 
+#include <algorithm>
+#include <vector>
+
 #include "layout.cuh"
 #include "primitives.cuh"
 
@@ -635,7 +638,34 @@ static void build_tiles(bsmr_layout* L, const u32* d_rowOff, const u32* d_colIdx
   tl->idx.alloc(nSel, true);
   SB_CUDA(cudaMemcpyAsync(tl->idx.get(), vals, (size_t)nSel * 4, cudaMemcpyDeviceToDevice, s));
   SB_CUDA(cudaStreamSynchronize(s));
+  build_quads(*tl);
   L->tl = std::move(tl);
+}
+
+void build_quads(TileLayout& T) {
+  T.numQuads = 0;
+  if (!T.numTiles) return;
+  std::vector<uint4> tiles(T.numTiles);
+  SB_CUDA(cudaMemcpy(tiles.data(), T.tiles.get(), (size_t)T.numTiles * sizeof(uint4), cudaMemcpyDeviceToHost));
+  // tiles are sorted by (row, col); quads in order of first appearance keyed by (row/2, col/2)
+  std::vector<std::pair<u64, u32>> keyed(T.numTiles);
+  for (u32 i = 0; i < T.numTiles; ++i) keyed[i] = {((u64)(tiles[i].x >> 1) << 32) | (tiles[i].y >> 1), i};
+  std::sort(keyed.begin(), keyed.end());
+  std::vector<uint2> quads;
+  std::vector<u32> members;
+  for (u32 i = 0; i < T.numTiles; ++i) {
+    if (i == 0 || keyed[i].first != keyed[i - 1].first) {
+      quads.push_back(make_uint2((u32)(keyed[i].first >> 32), (u32)(keyed[i].first & 0xFFFFFFFFu)));
+      members.insert(members.end(), 4, 0xFFFFFFFFu);
+    }
+    const uint4& t = tiles[keyed[i].second];
+    members[(quads.size() - 1) * 4 + (t.x & 1u) * 2u + (t.y & 1u)] = keyed[i].second;
+  }
+  T.numQuads = (u32)quads.size();
+  T.quads.alloc(quads.size(), true);
+  T.quadTiles.alloc(members.size(), true);
+  SB_CUDA(cudaMemcpy(T.quads.get(), quads.data(), quads.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+  SB_CUDA(cudaMemcpy(T.quadTiles.get(), members.data(), members.size() * 4, cudaMemcpyHostToDevice));
 }
 
 const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStream_t s) {
@@ -829,6 +859,7 @@ bsmr_layout* layout_load(const char* path) {
       get(fl.f, host.data(), host.size());
       T->idx.alloc(host.size() ? host.size() : 1, true);
       if (!host.empty()) SB_CUDA(cudaMemcpy(T->idx.get(), host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+      build_quads(*T);
       L->tl = std::move(T);
     }
     return L;

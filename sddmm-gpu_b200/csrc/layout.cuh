@@ -27,7 +27,13 @@ struct TileLayout {
   DevBuf<uint4> tiles;     // per non-empty tile: {tile row, tile col, first entry, entry count}
   DevBuf<u32> rowMeta;     // per tile 128 x 5 words: 4 mask words (which of the 128 columns are stored) + entry offset
   DevBuf<u32> idx;         // per entry (sorted by tile, row, col): CSR index
+  // 2x2 groups of tiles for the cluster form of the tile kernel (operands multicast inside a 4-CTA cluster):
+  // quads[q] = {quad row, quad col}; quadTiles[4q + 2*dr + dc] = index into tiles[] or 0xFFFFFFFF (no entries)
+  u32 numQuads = 0;
+  DevBuf<uint2> quads;
+  DevBuf<u32> quadTiles;
 };
+void build_quads(TileLayout& T);  // from T.tiles (host pass over the tile list)
 }  // namespace sb
 
 struct bsmr_layout {
@@ -42,6 +48,15 @@ struct bsmr_layout {
   // device staging buffers of the host-buffer entry point (sddmm_run_host), grown on demand and kept
   // so that repeated calls do not pay cudaMalloc/cudaFree
   mutable sb::DevBuf<float> wsA, wsB, wsP;
+  // TMA form of the tile plan: TF32-rounded, row-gathered copies of the operands (rewritten every pass) and the
+  // tensor maps describing them; (re)built when K or the batch count changes
+  struct TileTma {
+    sb::u32 K = 0, numBatch = 0;
+    sb::DevBuf<float> rA, rB;                  // [numBatch][numRows][K], [numBatch][N][K]
+    alignas(64) unsigned char mapA[128], mapB[128];      // CUtensorMap (box 128 rows), kept opaque here
+    alignas(64) unsigned char mapA64[128], mapB64[128];  // box 64 rows: the halves a cluster member multicasts
+  };
+  mutable std::unique_ptr<TileTma> tma;
   mutable std::unique_ptr<sb::SuperPanelLayout> sp;  // built lazily for the K in use
   std::unique_ptr<sb::TileLayout> tl;                // built with the layout when S is dense enough to consider it
   // two-slot pipeline of sddmm_run_host_async

@@ -11,6 +11,10 @@
 //   k_sddmm_residual : FP32 CUDA-core kernel over the residual COO entries, 128-bit loads of the
 //                      gathered B rows, A panel tile in shared memory, 8 lanes per non-zero with a
 //                      shuffle reduction.  Replaces src/sddmmKernel.cu:1994-2104 and :2109-2199.
+#include <algorithm>
+
+#include <cuda.h>  // CUtensorMap and its enums only; the encoder is fetched through cudaGetDriverEntryPoint
+
 #include "layout.cuh"
 #include "sddmm_kernels.cuh"
 
@@ -618,6 +622,431 @@ k_sddmm_tile(u32 M, u32 N, u32 K, const float* __restrict__ A, const float* __re
 }
 
 // =============================================================================================
+// tile kernel, TMA form (K9): the operands are first rounded to TF32 (cvt.rna, as everywhere) into
+// row-gathered copies Ar [numRows x K], Br [N x K]; the tile kernel then has ONE thread issue
+// cp.async.bulk.tensor loads of 128 x 32-float boxes (SWIZZLE_128B, the layout the UMMA descriptors
+// expect; rows past the end and the K tail are zero-filled by the TMA unit), ONE thread issue the
+// tcgen05.mma's, and full/empty mbarriers between them.  The 256 threads only meet again for the
+// epilogue.  Compared with k_sddmm_tile this removes the LDG -> cvt -> STS work (55 % of the issue
+// slots there) from the SM.
+// =============================================================================================
+static __global__ void __launch_bounds__(256) k_round_operands(u32 M, u32 N, u32 K4, const float4* __restrict__ A,
+                                                               const float4* __restrict__ B,
+                                                               const u32* __restrict__ R, u32 nR,
+                                                               float4* __restrict__ Ar, float4* __restrict__ Br,
+                                                               BatchStrides bs) {
+  A += (bs.a >> 2) * blockIdx.y;
+  B += (bs.b >> 2) * blockIdx.y;
+  Ar += (size_t)nR * K4 * blockIdx.y;
+  Br += (size_t)N * K4 * blockIdx.y;
+  const size_t nA = (size_t)nR * K4, nB = (size_t)N * K4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nA + nB; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < nA) {
+      const u32 r = (u32)(i / K4), c = (u32)(i - (size_t)r * K4);
+      const u32 row = R[r];
+      if (row < M) v = __ldg(A + (size_t)row * K4 + c);
+    } else {
+      v = __ldg(B + (i - nA));
+    }
+    v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w);
+    if (i < nA) Ar[i] = v;
+    else Br[i - nA] = v;
+  }
+}
+
+// bounded wait: a protocol error must end in a launch failure, never in a hung GPU
+__device__ __forceinline__ void mbar_wait_bounded(u64* bar, u32 parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(u32 dstSmem, const void* map, u32 barSmem, u32 c0, u32 c1, u32 c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dstSmem), "l"(map), "r"(barSmem), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+template <u32 kStagesT>
+static __global__ void __launch_bounds__(kTlThreads)
+k_sddmm_tile_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, u32 K,
+                 const uint4* __restrict__ tiles, const u32* __restrict__ rowMeta, const u32* __restrict__ entIdx,
+                 float* __restrict__ P, size_t pStride) {
+  extern __shared__ __align__(1024) unsigned char smemRaw[];
+  P += pStride * blockIdx.y;
+  unsigned char* stages = smemRaw + ((1024u - (smem_u32(smemRaw) & 1023u)) & 1023u);
+  __shared__ u64 fullBar[kStagesT], emptyBar[kStagesT], accBar;
+  __shared__ u32 tmemBase;
+
+  const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const uint4 tile = tiles[blockIdx.x];
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmemBase)),
+                 "r"(kTlTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (u32 s = 0; s < kStagesT; ++s) {
+      mbar_init(&fullBar[s], 1);
+      mbar_init(&emptyBar[s], 1);
+    }
+    mbar_init(&accBar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const u32 tmem = tmemBase;
+  const u32 numChunks = (K + kDnKChunk - 1) / kDnKChunk;
+  constexpr u32 idesc = umma_idesc_tf32(128, 128);
+
+  if (warp == 0) {
+    // ---- producer: one thread feeds the stages through the TMA unit
+    for (u32 kc = 0; kc < numChunks; ++kc) {
+      const u32 s = kc % kStagesT;
+      if (lane == 0) {
+        if (kc >= kStagesT) mbar_wait_bounded(&emptyBar[s], ((kc / kStagesT) - 1) & 1u);
+        const u32 bar = smem_u32(&fullBar[s]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kTlStageBytes) : "memory");
+        const u32 dst = smem_u32(stages + s * kTlStageBytes);
+        tma_load_3d(dst, &mapA, bar, kc * kDnKChunk, tile.x * 128u, blockIdx.y);
+        tma_load_3d(dst + 128u * 128u, &mapB, bar, kc * kDnKChunk, tile.y * 128u, blockIdx.y);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer
+    for (u32 kc = 0; kc < numChunks; ++kc) {
+      const u32 s = kc % kStagesT;
+      if (lane == 0) {
+        mbar_wait_bounded(&fullBar[s], (kc / kStagesT) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const u32 base = smem_u32(stages + s * kTlStageBytes);
+        const u64 dA = umma_desc_sw128(base);
+        const u64 dB = umma_desc_sw128(base + 128u * 128u);
+#pragma unroll
+        for (u32 k = 0; k < kDnKChunk / 8; ++k) {
+          const u32 acc = (kc | k) ? 1u : 0u;
+          asm volatile(
+              "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem),
+              "l"(dA + 2ull * k), "l"(dB + 2ull * k), "r"(idesc), "r"(acc)
+              : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         smem_u32(&emptyBar[s]))
+                     : "memory");
+        if (kc + 1 == numChunks)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                           smem_u32(&accBar))
+                       : "memory");
+      }
+      __syncwarp();
+    }
+  }
+  mbar_wait_bounded(&accBar, 0u);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  __syncthreads();  // every MMA has finished reading the stages: they become the epilogue's staging area
+
+  float* sOut = reinterpret_cast<float*>(stages);
+  {
+    const u32 q4 = warp & 3u, half = warp >> 2;
+    const u32 r = q4 * 32u + lane;
+    const u32* meta = rowMeta + (size_t)blockIdx.x * 640u + r * 5u;
+    const u32 m0 = meta[0], m1 = meta[1], m2 = meta[2], m3 = meta[3];
+    u32 off = meta[4] - tile.z;
+    if (half) off += __popc(m0) + __popc(m1);
+#pragma unroll
+    for (u32 qq = 0; qq < 2; ++qq) {
+      const u32 q = half * 2u + qq;
+      u32 acc[32];
+      const u32 taddr = tmem + ((q4 * 32u) << 16) + q * 32u;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]),
+            "=r"(acc[7]), "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]),
+            "=r"(acc[14]), "=r"(acc[15]), "=r"(acc[16]), "=r"(acc[17]), "=r"(acc[18]), "=r"(acc[19]), "=r"(acc[20]),
+            "=r"(acc[21]), "=r"(acc[22]), "=r"(acc[23]), "=r"(acc[24]), "=r"(acc[25]), "=r"(acc[26]), "=r"(acc[27]),
+            "=r"(acc[28]), "=r"(acc[29]), "=r"(acc[30]), "=r"(acc[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const u32 mw = q == 0 ? m0 : q == 1 ? m1 : q == 2 ? m2 : m3;
+#pragma unroll
+      for (u32 b = 0; b < 32; ++b) {
+        if ((mw >> b) & 1u) {
+          sOut[off] = __uint_as_float(acc[b]);
+          ++off;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  {
+    const u32 cnt = tile.w;
+    const u32* __restrict__ idx = entIdx + tile.z;
+    u32 e = tid;
+    for (; e + 3u * kTlThreads < cnt; e += 4u * kTlThreads) {
+      const u32 i0 = __ldg(idx + e), i1 = __ldg(idx + e + kTlThreads), i2 = __ldg(idx + e + 2u * kTlThreads),
+                i3 = __ldg(idx + e + 3u * kTlThreads);
+      P[i0] = sOut[e];
+      P[i1] = sOut[e + kTlThreads];
+      P[i2] = sOut[e + 2u * kTlThreads];
+      P[i3] = sOut[e + 3u * kTlThreads];
+    }
+    for (; e < cnt; e += kTlThreads) P[__ldg(idx + e)] = sOut[e];
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTlTmemCols) : "memory");
+  }
+}
+
+// ---- cluster form: a 2x2 group of tiles runs as one 4-CTA cluster.  The A tile of a tile row is shared by the
+// two CTAs of that row, the B tile of a tile column by the two CTAs of that column: every CTA fetches HALF of
+// its A tile and HALF of its B tile (64-row boxes) and multicasts each half to itself and the partner, so the
+// L2 -> SM operand traffic halves.  A stage may be refilled once the local MMA and both partners' MMAs are
+// done with it: the local commit arrives on emptyBar, the partners' producers arrive remotely on peerBar.
+__device__ __forceinline__ u32 cluster_ctarank() {
+  u32 r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(u64* bar, u32 rank) {
+  u32 remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_bounded(u64* bar, u32 parity) {
+  const long long t0 = clock64();
+  u32 ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!ok && clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d_mc(u32 dstSmem, const void* map, u32 barSmem, u32 c0, u32 c1, u32 c2,
+                                               unsigned short mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dstSmem), "l"(map), "r"(barSmem), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+
+template <u32 kStagesT>
+static __global__ void __launch_bounds__(kTlThreads)
+k_sddmm_tile_tma4(const __grid_constant__ CUtensorMap mapA64, const __grid_constant__ CUtensorMap mapB64, u32 K,
+                  const uint2* __restrict__ quads, const u32* __restrict__ quadTiles, const uint4* __restrict__ tiles,
+                  const u32* __restrict__ rowMeta, const u32* __restrict__ entIdx, float* __restrict__ P,
+                  size_t pStride) {
+  extern __shared__ __align__(1024) unsigned char smemRaw[];
+  P += pStride * blockIdx.y;
+  unsigned char* stages = smemRaw + ((1024u - (smem_u32(smemRaw) & 1023u)) & 1023u);
+  __shared__ u64 fullBar[kStagesT], emptyBar[kStagesT], peerBar[kStagesT], accBar;
+  __shared__ u32 tmemBase;
+
+  const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const u32 rank = cluster_ctarank(), dr = rank >> 1, dc = rank & 1u;
+  const u32 quad = blockIdx.x >> 2;
+  const uint2 qrc = quads[quad];
+  const u32 tr = qrc.x * 2u + dr, tc = qrc.y * 2u + dc;
+  const u32 tileIdx = quadTiles[quad * 4u + rank];
+  const uint4 tile = tileIdx != kNull ? tiles[tileIdx] : make_uint4(tr, tc, 0u, 0u);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmemBase)),
+                 "r"(kTlTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (u32 s = 0; s < kStagesT; ++s) {
+      mbar_init(&fullBar[s], 1);
+      mbar_init(&emptyBar[s], 1);
+      mbar_init(&peerBar[s], 2);  // the row partner and the column partner
+    }
+    mbar_init(&accBar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();  // every member's barriers exist before any multicast or remote arrive can land
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const u32 tmem = tmemBase;
+  const u32 numChunks = (K + kDnKChunk - 1) / kDnKChunk;
+  constexpr u32 idesc = umma_idesc_tf32(128, 128);
+  const u32 rowPartner = rank ^ 1u, colPartner = rank ^ 2u;
+  const unsigned short maskRow = (unsigned short)((1u << rank) | (1u << rowPartner));
+  const unsigned short maskCol = (unsigned short)((1u << rank) | (1u << colPartner));
+
+  if (warp == 0) {
+    for (u32 kc = 0; kc < numChunks; ++kc) {
+      const u32 s = kc % kStagesT;
+      if (lane == 0) {
+        if (kc >= kStagesT) {
+          const u32 par = ((kc / kStagesT) - 1) & 1u;
+          mbar_wait_bounded(&emptyBar[s], par);      // my MMA is done with stage s ...
+          mbar_arrive_remote(&peerBar[s], rowPartner);  // ... tell the CTAs that write into it ...
+          mbar_arrive_remote(&peerBar[s], colPartner);
+          mbar_wait_cluster_bounded(&peerBar[s], par);  // ... and wait until theirs are free for my halves
+        }
+        const u32 bar = smem_u32(&fullBar[s]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kTlStageBytes) : "memory");
+        const u32 dst = smem_u32(stages + s * kTlStageBytes);
+        tma_load_3d_mc(dst + dc * 8192u, &mapA64, bar, kc * kDnKChunk, tr * 128u + dc * 64u, blockIdx.y, maskRow);
+        tma_load_3d_mc(dst + 16384u + dr * 8192u, &mapB64, bar, kc * kDnKChunk, tc * 128u + dr * 64u, blockIdx.y,
+                       maskCol);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    for (u32 kc = 0; kc < numChunks; ++kc) {
+      const u32 s = kc % kStagesT;
+      if (lane == 0) {
+        mbar_wait_bounded(&fullBar[s], (kc / kStagesT) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const u32 base = smem_u32(stages + s * kTlStageBytes);
+        const u64 dA = umma_desc_sw128(base);
+        const u64 dB = umma_desc_sw128(base + 128u * 128u);
+#pragma unroll
+        for (u32 k = 0; k < kDnKChunk / 8; ++k) {
+          const u32 acc = (kc | k) ? 1u : 0u;
+          asm volatile(
+              "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem),
+              "l"(dA + 2ull * k), "l"(dB + 2ull * k), "r"(idesc), "r"(acc)
+              : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         smem_u32(&emptyBar[s]))
+                     : "memory");
+        if (kc + 1 == numChunks)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                           smem_u32(&accBar))
+                       : "memory");
+      }
+      __syncwarp();
+    }
+  }
+  mbar_wait_bounded(&accBar, 0u);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  __syncthreads();
+
+  float* sOut = reinterpret_cast<float*>(stages);
+  if (tileIdx != kNull) {
+    const u32 q4 = warp & 3u, half = warp >> 2;
+    const u32 r = q4 * 32u + lane;
+    const u32* meta = rowMeta + (size_t)tileIdx * 640u + r * 5u;
+    const u32 m0 = meta[0], m1 = meta[1], m2 = meta[2], m3 = meta[3];
+    u32 off = meta[4] - tile.z;
+    if (half) off += __popc(m0) + __popc(m1);
+#pragma unroll
+    for (u32 qq = 0; qq < 2; ++qq) {
+      const u32 q = half * 2u + qq;
+      u32 acc[32];
+      const u32 taddr = tmem + ((q4 * 32u) << 16) + q * 32u;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]),
+            "=r"(acc[7]), "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]),
+            "=r"(acc[14]), "=r"(acc[15]), "=r"(acc[16]), "=r"(acc[17]), "=r"(acc[18]), "=r"(acc[19]), "=r"(acc[20]),
+            "=r"(acc[21]), "=r"(acc[22]), "=r"(acc[23]), "=r"(acc[24]), "=r"(acc[25]), "=r"(acc[26]), "=r"(acc[27]),
+            "=r"(acc[28]), "=r"(acc[29]), "=r"(acc[30]), "=r"(acc[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const u32 mw = q == 0 ? m0 : q == 1 ? m1 : q == 2 ? m2 : m3;
+#pragma unroll
+      for (u32 b = 0; b < 32; ++b) {
+        if ((mw >> b) & 1u) {
+          sOut[off] = __uint_as_float(acc[b]);
+          ++off;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tileIdx != kNull) {
+    const u32 cnt = tile.w;
+    const u32* __restrict__ idx = entIdx + tile.z;
+    u32 e = tid;
+    for (; e + 3u * kTlThreads < cnt; e += 4u * kTlThreads) {
+      const u32 i0 = __ldg(idx + e), i1 = __ldg(idx + e + kTlThreads), i2 = __ldg(idx + e + 2u * kTlThreads),
+                i3 = __ldg(idx + e + 3u * kTlThreads);
+      P[i0] = sOut[e];
+      P[i1] = sOut[e + kTlThreads];
+      P[i2] = sOut[e + 2u * kTlThreads];
+      P[i3] = sOut[e + 3u * kTlThreads];
+    }
+    for (; e < cnt; e += kTlThreads) P[__ldg(idx + e)] = sOut[e];
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTlTmemCols) : "memory");
+  }
+  cluster_sync_all();  // nobody leaves while a partner could still signal one of its barriers
+}
+
+// host side of K9: workspaces + tensor maps (cached in the layout per K / batch count)
+static void encode_map(void* out, const float* base, u32 K, u32 rows, u32 numBatch, u32 boxRows) {
+  using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeFn>(p);
+  }();
+  if (!fn) fail(SDDMM_E_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[3] = {K, rows, numBatch};
+  const cuuint64_t strides[2] = {(cuuint64_t)K * 4u, (cuuint64_t)rows * K * 4u};
+  const cuuint32_t box[3] = {kDnKChunk, boxRows, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult rc = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                         const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) fail(SDDMM_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
+}
+
+static const bsmr_layout::TileTma* ensure_tile_tma(const bsmr_layout* L, u32 K, u32 numBatch) {
+  if (L->tma && L->tma->K == K && L->tma->numBatch == numBatch) return L->tma.get();
+  auto t = std::make_unique<bsmr_layout::TileTma>();
+  const bsmr_layout_info& I = L->info;
+  const u32 nR = I.numRows ? I.numRows : 1u;
+  t->K = K;
+  t->numBatch = numBatch;
+  t->rA.alloc((size_t)numBatch * nR * K);
+  t->rB.alloc((size_t)numBatch * I.N * K);
+  encode_map(t->mapA, t->rA.get(), K, nR, numBatch, 128u);
+  encode_map(t->mapB, t->rB.get(), K, I.N, numBatch, 128u);
+  encode_map(t->mapA64, t->rA.get(), K, nR, numBatch, 64u);
+  encode_map(t->mapB64, t->rB.get(), K, I.N, numBatch, 64u);
+  L->tma = std::move(t);
+  return L->tma.get();
+}
+
+// =============================================================================================
 // launcher
 // =============================================================================================
 void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB, float* dP, cudaStream_t denseStream,
@@ -642,7 +1071,59 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
     const double covered = (double)I.numDenseValues + (double)I.numSparseValues;  // this shard's entries
     const double bsmrCost = covered * (0.03 * K + 1.5);
     if (plan == 2 || (plan == 1 && tileCost < bsmrCost)) {
-      if (which & kLaunchDense) {
+      // 0: register-staged tiles; 1: TMA, one CTA per tile (default for K >= 128; below that the rounding pre-pass
+      // costs more than it saves); 2: TMA + 2x2 clusters with multicast -- halves the L2 -> SM operand traffic but
+      // measured SLOWER (64 vs 39 us at 4096^2, K=256): with one tile per CTA and two stages the per-stage handshake
+      // between the four CTAs is exposed; kept opt-in as the base of a persistent, deeper-pipelined version.
+      static const int tileCfg = [] { const char* e = getenv("SDDMM_B200_TILE"); return !e ? -1 : !strcmp(e, "reg") ? 0 : !strcmp(e, "tma4") ? 2 : 1; }();
+      const int tileMode = tileCfg >= 0 ? tileCfg : (K >= 128 ? 1 : 0);
+      if ((which & kLaunchDense) && tileMode == 2 && L->tl->numQuads) {
+        static const u32 nStages = [] { const char* e = getenv("SDDMM_B200_TILE_STAGES"); const int v = e ? atoi(e) : 2; return (u32)(v == 3 || v == 4 ? v : 2); }();
+        const size_t smem = (size_t)nStages * kTlStageBytes + 1024;
+        auto kq = nStages == 2 ? k_sddmm_tile_tma4<2> : nStages == 3 ? k_sddmm_tile_tma4<3> : k_sddmm_tile_tma4<4>;
+        SB_CUDA(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const bsmr_layout::TileTma* t = ensure_tile_tma(L, K, numBatch);
+        const u32 K4 = K / 4;
+        const size_t work = ((size_t)I.numRows + I.N) * K4;
+        k_round_operands<<<dim3((unsigned)std::min<size_t>((work + 255) / 256, 148 * 16), numBatch), 256, 0, denseStream>>>(
+            I.M, I.N, K4, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB),
+            arr(BSMR_REORDERED_ROWS), I.numRows, reinterpret_cast<float4*>(t->rA.get()),
+            reinterpret_cast<float4*>(t->rB.get()), bst);
+        SB_LAUNCH_CHECK();
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(L->tl->numQuads * 4u, numBatch);
+        cfg.blockDim = dim3(kTlThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = denseStream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        SB_CUDA(cudaLaunchKernelEx(&cfg, kq, *reinterpret_cast<const CUtensorMap*>(t->mapA64),
+                                   *reinterpret_cast<const CUtensorMap*>(t->mapB64), K,
+                                   (const uint2*)L->tl->quads.get(), (const u32*)L->tl->quadTiles.get(),
+                                   (const uint4*)L->tl->tiles.get(), (const u32*)L->tl->rowMeta.get(),
+                                   (const u32*)L->tl->idx.get(), dP, bst.p));
+        SB_LAUNCH_CHECK();
+      } else if ((which & kLaunchDense) && tileMode >= 1) {
+        static const u32 nStages = [] { const char* e = getenv("SDDMM_B200_TILE_STAGES"); const int v = e ? atoi(e) : 2; return (u32)(v == 3 || v == 4 ? v : 2); }();
+        const size_t smem = (size_t)nStages * kTlStageBytes + 1024;
+        auto kt = nStages == 2 ? k_sddmm_tile_tma<2> : nStages == 3 ? k_sddmm_tile_tma<3> : k_sddmm_tile_tma<4>;
+        SB_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const bsmr_layout::TileTma* t = ensure_tile_tma(L, K, numBatch);
+        const u32 K4 = K / 4;
+        const size_t work = ((size_t)I.numRows + I.N) * K4;
+        k_round_operands<<<dim3((unsigned)std::min<size_t>((work + 255) / 256, 148 * 16), numBatch), 256, 0, denseStream>>>(
+            I.M, I.N, K4, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB),
+            arr(BSMR_REORDERED_ROWS), I.numRows, reinterpret_cast<float4*>(t->rA.get()),
+            reinterpret_cast<float4*>(t->rB.get()), bst);
+        SB_LAUNCH_CHECK();
+        kt<<<dim3(L->tl->numTiles, numBatch), kTlThreads, smem, denseStream>>>(
+            *reinterpret_cast<const CUtensorMap*>(t->mapA), *reinterpret_cast<const CUtensorMap*>(t->mapB), K,
+            L->tl->tiles.get(), L->tl->rowMeta.get(), L->tl->idx.get(), dP, bst.p);
+        SB_LAUNCH_CHECK();
+      } else if (which & kLaunchDense) {
         const size_t smem = (size_t)kTlStages * kTlStageBytes + 1024;
         static bool attrSet = false;
         if (!attrSet) {
