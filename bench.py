@@ -316,7 +316,7 @@ def run_ours(args, w):
         if dense_dominant:
             # tensor-core kernel (128x128 tcgen05 tiles or 16x16 BSMR blocks): padded flops vs the tf32 peak,
             # taken as half of the measured dense bf16 peak (tf32 runs at half the bf16 rate)
-            kname, kms = "k_sddmm_tile / k_sddmm_dense (tcgen05 kind::tf32)", kt["dense_ms"]
+            kname, kms = "k_round_operands + k_sddmm_tile_tma / k_sddmm_tile / k_sddmm_dense (tcgen05 kind::tf32)", kt["dense_ms"]
             tiles = (-(-S.M // 128)) * (-(-S.N // 128))
             padded = 2.0 * 16384.0 * tiles * K if info.numDenseBlocks == 0 or True else 0.0
             padded_blocks = 2.0 * 256.0 * info.numDenseBlocks * K
