@@ -197,6 +197,15 @@ def write_mtx(path, S: CSRPattern, order="col", values=True):
             np.savetxt(f, np.stack([r + 1, c + 1], 1), fmt="%d")
 
 
+def write_smtx(path, S: CSRPattern):
+    """DLMC `.smtx` file (the reference's second loader, src/Matrix.cpp:296-371): `M, N, nnz`, then one line
+    of row offsets, then one line of column indices (0-based); values are implicitly 1."""
+    with open(path, "w") as f:
+        f.write("%d, %d, %d\n" % (S.M, S.N, S.nnz))
+        f.write(" ".join(str(int(x)) for x in S.row_off) + "\n")
+        f.write(" ".join(str(int(x)) for x in S.col_idx) + "\n")
+
+
 def write_case_bin(path, S: CSRPattern, A, B):
     """Case file consumed by oracle/_ref/ref_dump (oracle/ref_dump_main.cu)."""
     K = A.shape[1]

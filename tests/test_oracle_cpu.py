@@ -237,3 +237,78 @@ def test_evaluation_reordering_equals_reference_host_code(delta):
                 assert a[k] == pytest.approx(b[k], rel=1e-6, abs=1e-7), (S.name, k, a[k], b[k])
             else:
                 assert a[k] == b[k], (S.name, k, a[k], b[k])
+
+
+@needs_ref
+def test_cpp_host_smtx_loader_matches_reference(tmp_path):
+    """csrc/host/Matrix.cpp's `.smtx` loader (DLMC format) against the reference's own (src/Matrix.cpp:296-371)
+    through `BSMR-sddmm -x 1`; duplicates inside a row are rejected by both."""
+    import subprocess
+    from cases import ROOT
+    exe = os.path.join(ROOT, "sddmm-gpu_b200", "BSMR-sddmm")
+    if not os.access(exe, os.X_OK):
+        pytest.skip("CLI not built")
+    S = gen.shuffle_within_rows(gen.with_empty_rows(gen.dlmc_magnitude_mask(96, 200, 0.8, 5), 3), 2)
+    p = str(tmp_path / "m.smtx")
+    gen.write_smtx(p, S)
+    rc, (M, N, ro, ci, va) = O.ref_load_mtx(p)
+    assert rc == 0 and M == S.M and N == S.N and np.array_equal(ci, S.col_idx) and np.all(va == 1.0)
+    out = subprocess.run([exe, "-f", p, "-x", "1"], capture_output=True, text=True, timeout=60).stdout
+    tok = [l for l in out.splitlines() if l.startswith("[loader")][0].strip("[]").split()
+    got = dict(zip(tok[2::2], tok[3::2]))
+    assert int(got["M"]) == M and int(got["N"]) == N and int(got["nnz"]) == len(ci)
+    assert int(got["rowOff"], 16) == _fnv(ro) and int(got["colIdx"], 16) == _fnv(ci) and int(got["values"], 16) == _fnv(va)
+    bad = str(tmp_path / "dup.smtx")
+    open(bad, "w").write("2, 4, 3\n0 2 3\n1 1 2\n")
+    assert O.ref_load_mtx(bad)[0] != 0
+    r = subprocess.run([exe, "-f", bad, "-x", "1"], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "duplicate" in r.stderr
+
+
+_MTX_QUIRKS = {
+    "crlf": "%%MatrixMarket matrix coordinate real general\r\n3 4 4\r\n1 1 1.5\r\n2 3 -2\r\n3 4 1e-3\r\n1 2 7\r\n",
+    "blank_lines": "%%MatrixMarket x\n% c\n3 4 4\n\n1 1 1.5\n\n2 3 -2\n3 4 1e-3\n1 2 7\n\n",
+    "tabs": "%%MatrixMarket x\n3\t4\t4\n1\t1\t1.5\n2\t3\t-2\n3\t4\t1e-3\n1\t2\t7\n",
+    "pattern": "%%MatrixMarket matrix coordinate pattern general\n3 4 4\n1 1\n2 3\n3 4\n1 2\n",
+    "no_trailing_newline": "%%MatrixMarket x\n3 4 4\n1 1 1.5\n2 3 -2\n3 4 1e-3\n1 2 7",
+    "trailing_spaces": "%%MatrixMarket x\n3 4 4 \n1 1 1.5 \n2 3 -2  \n3 4 1e-3\n1 2 7 \n",
+    "int_values": "%%MatrixMarket matrix coordinate integer general\n3 4 4\n1 1 2\n2 3 -2\n3 4 5\n1 2 7\n",
+    "too_few": "%%MatrixMarket x\n3 4 5\n1 1 1.5\n2 3 -2\n3 4 1e-3\n1 2 7\n",
+    "too_many": "%%MatrixMarket x\n3 4 3\n1 1 1.5\n2 3 -2\n3 4 1e-3\n1 2 7\n",
+    "row_oob": "%%MatrixMarket x\n3 4 4\n1 1 1.5\n4 3 -2\n3 4 1e-3\n1 2 7\n",
+    "col_oob": "%%MatrixMarket x\n3 4 4\n1 1 1.5\n2 5 -2\n3 4 1e-3\n1 2 7\n",
+    "zero_index": "%%MatrixMarket x\n3 4 4\n0 1 1.5\n2 3 -2\n3 4 1e-3\n1 2 7\n",
+    "dup": "%%MatrixMarket x\n3 4 4\n1 1 1.5\n2 3 -2\n1 1 1e-3\n1 2 7\n",
+    "nnz1": "%%MatrixMarket x\n3 4 1\n1 1 1.5\n",
+}
+
+
+@needs_ref
+@pytest.mark.parametrize("name", sorted(_MTX_QUIRKS))
+def test_cpp_host_loader_quirks_match_reference(tmp_path, name):
+    """accept / reject decisions and the loaded arrays of csrc/host/Matrix.cpp against the reference's loader
+    (src/Matrix.cpp:398-480) on line-ending, separator, value-format and error cases.  (Leading blanks and
+    comments between entries make the reference throw from std::stoi; those are outside its contract.)"""
+    import subprocess
+    from cases import ROOT
+    exe = os.path.join(ROOT, "sddmm-gpu_b200", "BSMR-sddmm")
+    if not os.access(exe, os.X_OK):
+        pytest.skip("CLI not built")
+    p = str(tmp_path / (name + ".mtx"))
+    with open(p, "w", newline="") as f:
+        f.write(_MTX_QUIRKS[name])
+    rc, res = O.ref_load_mtx(p)
+    r = subprocess.run([exe, "-f", p, "-x", "1"], capture_output=True, text=True, timeout=60)
+    line = [l for l in r.stdout.splitlines() if l.startswith("[loader")]
+    if rc != 0:
+        assert r.returncode != 0 and not line
+        return
+    M, N, ro, ci, va = res
+    assert r.returncode == 0 and line
+    tok = line[0].strip("[]").split()
+    got = dict(zip(tok[2::2], tok[3::2]))
+    assert int(got["M"]) == M and int(got["N"]) == N and int(got["nnz"]) == len(ci)
+    assert int(got["rowOff"], 16) == _fnv(ro) and int(got["colIdx"], 16) == _fnv(ci) and int(got["values"], 16) == _fnv(va)
+    # the oracle's restatement agrees as well
+    rc2, res2 = O.load_mtx(p)
+    assert rc2 == 0 and np.array_equal(res2[2], ro) and np.array_equal(res2[3], ci) and np.array_equal(res2[4], va)
