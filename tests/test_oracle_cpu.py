@@ -312,3 +312,28 @@ def test_cpp_host_loader_quirks_match_reference(tmp_path, name):
     # the oracle's restatement agrees as well
     rc2, res2 = O.load_mtx(p)
     assert rc2 == 0 and np.array_equal(res2[2], ro) and np.array_equal(res2[3], ci) and np.array_equal(res2[4], va)
+
+
+@needs_ref
+def test_col_reorder_and_evaluation_random_matrices_vs_reference():
+    """randomised sweep (fixed seeds): tiny ragged shapes, any row order (not just the clustering's), every delta
+    regime -- oracle column reordering + statistics against the reference host code."""
+    rng = np.random.default_rng(20240)
+    for trial in range(40):
+        M, N = int(rng.integers(1, 90)), int(rng.integers(1, 140))
+        dens = float(rng.choice([0.02, 0.1, 0.35, 0.8]))
+        S = gen.uniform_random(M, N, dens, int(rng.integers(1, 1 << 30)))
+        if S.nnz < 2:
+            continue
+        nz = np.nonzero(np.diff(S.row_off.astype(np.int64)))[0].astype(np.uint32)
+        R = rng.permutation(nz).astype(np.uint32)
+        delta = float(rng.choice([0.0, 0.05, 0.3, 0.5, 0.99, 1.1]))
+        a, b = O.col_reorder(S, R, delta), O.ref_col_reorder(S, R, delta)
+        for k in ("denseCols", "denseColOffsets", "sparseCols", "sparseColOffsets", "sparseValueOffsets"):
+            assert np.array_equal(a[k], b[k]), (trial, M, N, dens, delta, k)
+        ea, eb = O.evaluation_reordering(S, R, a, delta), O.ref_evaluation_reordering(S, R, delta)
+        for k in eb:
+            if isinstance(eb[k], float):
+                assert ea[k] == pytest.approx(eb[k], rel=1e-6, abs=1e-7), (trial, k)
+            else:
+                assert ea[k] == eb[k], (trial, M, N, dens, delta, k, ea[k], eb[k])
