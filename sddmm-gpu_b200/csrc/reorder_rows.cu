@@ -418,7 +418,6 @@ struct ClusterBatchArgs {
   u32* cid;
   unsigned long long* slots;  // [3] earliest (pos << 8 | cluster-in-batch) that joins, per rotating window
   u32* accepts;               // [3] number of accepting candidates seen in the window (same rotation)
-  u32* pend;                  // [M] assignments made in sequential mode, flushed into cid by block 0 afterwards
   u32* seeds;                 // [0] count, [1..8] positions of the next batch's seeds (written by block 0)
   u32* stats;                 // [0] exact evaluations, [1] clusters created, [2] windows, [3] batches
 };
@@ -904,14 +903,13 @@ void row_reorder_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32
   u32 exactEvals = 0;
   static const bool legacy = [] { const char* e = getenv("SDDMM_B200_CLUSTER"); return e && !strcmp(e, "legacy"); }();
   DevBuf<unsigned long long> slots(4);
-  DevBuf<u32> seedsBuf(16), statsBuf(8), acceptsBuf(4), pendBuf(legacy ? 1 : M);
+  DevBuf<u32> seedsBuf(16), statsBuf(8), acceptsBuf(4);
   if (zeroRows < M && !legacy) {
     ClusterBatchArgs a;
     a.M = M; a.start0 = zeroRows; a.nbpr = nbpr; a.B = B; a.keptMask = keptMask; a.alpha = alpha;
     a.enc = enc.get(); a.meta = meta.get(); a.cid = cid.get(); a.slots = slots.get(); a.seeds = seedsBuf.get();
     a.stats = statsBuf.get();
     a.accepts = acceptsBuf.get();
-    a.pend = pendBuf.get();
     // short-row matrices (graphs): evaluate one candidate per lane (SDDMM_B200_CLUSTER_LANE=0 turns it off)
     {
       static const int laneCfg = [] { const char* e = getenv("SDDMM_B200_CLUSTER_LANE"); return e ? atoi(e) : -1; }();
@@ -919,7 +917,6 @@ void row_reorder_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32
       a.laneRows = laneCfg == 0 ? 0u : laneCfg > 0 ? (u32)laneCfg : (avgEnt <= 24.0 ? 64u : 0u);
     }
     SB_CUDA(cudaMemsetAsync(acceptsBuf.get(), 0, 16, s));
-    SB_CUDA(cudaMemsetAsync(pendBuf.get(), 0xFF, (size_t)M * 4, s));
     u32 G = (u32)((200u * 1024u) / ((size_t)nbpr * 4));
     if (const char* e = getenv("SDDMM_B200_CLUSTER_G")) { const int v = atoi(e); if (v >= 1 && (u32)v < G) G = (u32)v; }
     G = G >= 8 ? 8u : G >= 4 ? 4u : G >= 2 ? 2u : 1u;  // template instances
