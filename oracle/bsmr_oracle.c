@@ -242,6 +242,233 @@ int oracle_row_reorder(const u32* rowOff, const u32* colIdx, u32 M, u32 N,
 }
 
 /* ------------------------------------------------------------------------- */
+/* The same clustering with CANDIDATE PRUNING (validation of the round-2 device
+ * design; also what lets the oracle reach matrices whose dense M x nbpr encoding
+ * does not fit).  For alpha >= 0 a row that shares no non-zero block with the
+ * representative has min_sum == 0, hence sim == 0, and can never join; the only
+ * other way to join is the "both norms are zero" rule (:263-268).  So for every
+ * cluster only the rows on the posting lists of the representative's non-zero
+ * blocks (lists of the blocks a joiner adds are merged in from its position on)
+ * and the rows with a zero norm are evaluated -- in ascending position, with the
+ * literal reduction tree restricted to the blocks that are non-zero on either
+ * side (adding +0.0f to a partial sum does not change it, and every thread still
+ * sees its blocks in ascending order).  Must return exactly what
+ * oracle_row_reorder returns; tests/test_oracle_cpu.py checks that.            */
+typedef struct { u32 blk, cnt; } ent_t;
+
+static float similarity_sparse(const u32* rep, const u32* repNz, u32 nRepNz, const ent_t* cmp, u32 nCmp,
+                               u32 B, u32* ur, u32* uc, float* fmn, float* fmx, u32* mark /* nbpr, zero */) {
+  /* integer norms: per-thread partials over the non-zero blocks (order irrelevant, wrapping adds) */
+  memset(ur, 0, sizeof(u32) * B);
+  memset(uc, 0, sizeof(u32) * B);
+  for (u32 k = 0; k < nRepNz; ++k) { const u32 i = repNz[k]; ur[i % B] += rep[i] * rep[i]; }
+  for (u32 k = 0; k < nCmp; ++k) uc[cmp[k].blk % B] += cmp[k].cnt * cmp[k].cnt;
+  const u32 ss_rep = reduce_u32(ur, B), ss_cmp = reduce_u32(uc, B);
+  if (ss_rep == 0 && ss_cmp == 0) return 1.0f;
+  if (ss_rep == 0 || ss_cmp == 0) return 0.0f;
+  const float norm_rep = sqrtf((float)ss_rep), norm_cmp = sqrtf((float)ss_cmp);
+  for (u32 t = 0; t < B; ++t) fmn[t] = 0.0f, fmx[t] = 0.0f;
+  /* union of the two sorted block lists, ascending */
+  for (u32 k = 0; k < nCmp; ++k) mark[cmp[k].blk] = cmp[k].cnt;
+  u32 a = 0, b = 0;
+  while (a < nRepNz || b < nCmp) {
+    u32 i;
+    if (b >= nCmp || (a < nRepNz && repNz[a] <= cmp[b].blk)) { i = repNz[a]; if (b < nCmp && cmp[b].blk == i) ++b; ++a; }
+    else i = cmp[b++].blk;
+    const u32 t = i % B;
+    const float x = ((float)rep[i]) / norm_rep, y = ((float)mark[i]) / norm_cmp;
+    fmn[t] = fmn[t] + fminf(x, y);
+    fmx[t] = fmx[t] + fmaxf(x, y);
+  }
+  for (u32 k = 0; k < nCmp; ++k) mark[cmp[k].blk] = 0;
+  const float min_sum = reduce_f32(fmn, B), max_sum = reduce_f32(fmx, B);
+  return min_sum / max_sum;
+}
+
+static int cmp_u32_asc(const void* x, const void* y) {
+  const u32 a = *(const u32*)x, b = *(const u32*)y;
+  return a < b ? -1 : a > b;
+}
+
+int oracle_row_reorder_pruned(const u32* rowOff, const u32* colIdx, u32 M, u32 N, float alpha, u32 block_size,
+                              u32* reorderedRows, u32* numRows, int32_t* clusterCnt, u32* clusterOfRow,
+                              u32* ascending_out, uint64_t* evaluations, int flags) {
+  if (!(alpha >= 0.0f)) return -2; /* the pruning argument needs alpha >= 0 */
+  const int prefixFilter = flags & 1;
+  const u32 nbpr = oracle_num_blocks_per_row(N, block_size);
+  const u32 B = oracle_cluster_blockdim(nbpr);
+  u32* disp = (u32*)malloc(sizeof(u32) * (M ? M : 1));
+  oracle_encode_dispersion(rowOff, colIdx, M, N, block_size, NULL, disp);
+  u32* keys = (u32*)malloc(sizeof(u32) * (M ? M : 1));
+  u32* asc = (u32*)malloc(sizeof(u32) * (M ? M : 1));
+  for (u32 i = 0; i < M; ++i) keys[i] = disp[i], asc[i] = i;
+  stable_sort_by_key(keys, asc, M);
+  u32* cid = (u32*)malloc(sizeof(u32) * (M ? M : 1));
+  for (u32 i = 0; i < M; ++i) cid[i] = ORACLE_NULL_VALUE;
+  u32 zero_row_idx = 0;
+  while (zero_row_idx < M && disp[asc[zero_row_idx]] == 0) cid[zero_row_idx++] = 0;
+
+  /* sparse encodings by POSITION (blocks ascending), posting lists by block (positions ascending) */
+  size_t* eOff = (size_t*)malloc(sizeof(size_t) * ((size_t)M + 1));
+  u32* h = (u32*)calloc(nbpr ? nbpr : 1, sizeof(u32));
+  u32* tb = (u32*)malloc(sizeof(u32) * (nbpr ? nbpr : 1));
+  size_t total = 0;
+  for (u32 p = 0; p < M; ++p) { /* count distinct blocks per row */
+    const u32 r = asc[p];
+    u32 nt = 0;
+    for (u32 i = rowOff[r]; i < rowOff[r + 1]; ++i) { const u32 b = colIdx[i] / block_size; if (h[b]++ == 0) tb[nt++] = b; }
+    for (u32 k = 0; k < nt; ++k) h[tb[k]] = 0;
+    eOff[p] = total;
+    total += nt;
+  }
+  eOff[M] = total;
+  ent_t* ent = (ent_t*)malloc(sizeof(ent_t) * (total ? total : 1));
+  size_t* pOff = (size_t*)calloc((size_t)nbpr + 1, sizeof(size_t));
+  for (u32 p = 0; p < M; ++p) {
+    const u32 r = asc[p];
+    u32 nt = 0;
+    for (u32 i = rowOff[r]; i < rowOff[r + 1]; ++i) { const u32 b = colIdx[i] / block_size; if (h[b]++ == 0) tb[nt++] = b; }
+    qsort(tb, nt, sizeof(u32), cmp_u32_asc);
+    for (u32 k = 0; k < nt; ++k) { ent[eOff[p] + k].blk = tb[k]; ent[eOff[p] + k].cnt = h[tb[k]]; pOff[tb[k] + 1]++; h[tb[k]] = 0; }
+  }
+  for (u32 b = 0; b < nbpr; ++b) pOff[b + 1] += pOff[b];
+  u32* post = (u32*)malloc(sizeof(u32) * (total ? total : 1));
+  size_t* fill = (size_t*)malloc(sizeof(size_t) * ((size_t)nbpr + 1));
+  memcpy(fill, pOff, sizeof(size_t) * ((size_t)nbpr + 1));
+  for (u32 p = 0; p < M; ++p)
+    for (size_t k = eOff[p]; k < eOff[p + 1]; ++k) post[fill[ent[k].blk]++] = p; /* ascending p */
+
+  u32 ur[1024], uc[1024];
+  float fmn[1024], fmx[1024];
+  u32* mark = (u32*)calloc(nbpr ? nbpr : 1, sizeof(u32));
+  /* rows whose integer norm reduces to zero (all their blocks in dropped warps, or a wrap) */
+  u32* zeroNorm = (u32*)malloc(sizeof(u32) * (M ? M : 1));
+  u32 nZeroNorm = 0;
+  for (u32 p = zero_row_idx; p < M; ++p) {
+    memset(uc, 0, sizeof(u32) * B);
+    for (size_t k = eOff[p]; k < eOff[p + 1]; ++k) uc[ent[k].blk % B] += ent[k].cnt * ent[k].cnt;
+    if (reduce_u32(uc, B) == 0) zeroNorm[nZeroNorm++] = p;
+  }
+
+  /* PREFIX FILTER (flags & 1).  sim = min_sum / max_sum <= (rep mass on the shared blocks) / (rep mass), both over
+   * the blocks the reduction keeps, so a row that shares only blocks of a set F with mass(F) <= alpha * mass can
+   * never join.  F = the most frequent (longest posting list) blocks of the representative while that holds, with a
+   * 1e-3 relative margin for the fp32 tree sums; blocks in dropped warps carry no mass and are always in F.
+   * Candidates then come from the posting lists of the OTHER blocks only.                                       */
+  uint8_t keptWarp[32];
+  oracle_kept_warps(B, keptWarp);
+  uint8_t* hasIt = (uint8_t*)calloc(nbpr ? nbpr : 1, 1); /* block already feeds the candidate stream */
+  u32* byFreq = (u32*)malloc(sizeof(u32) * (nbpr ? nbpr : 1));
+  u32* rep = (u32*)calloc(nbpr ? nbpr : 1, sizeof(u32));
+  u32* repNz = (u32*)malloc(sizeof(u32) * (nbpr ? nbpr : 1));
+  /* candidate iterators: one per non-zero block of the representative (+ the zero-norm list); a plain array
+   * scanned for its minimum is enough for a CPU checker */
+  size_t* itCur = (size_t*)malloc(sizeof(size_t) * ((size_t)nbpr + 2));
+  size_t* itEnd = (size_t*)malloc(sizeof(size_t) * ((size_t)nbpr + 2));
+  const u32** itArr = (const u32**)malloc(sizeof(u32*) * ((size_t)nbpr + 2));
+  uint64_t evals = 0;
+  u32 cluster = 1, start = zero_row_idx;
+  while (start < M) {
+    cid[start] = cluster;
+    u32 nRepNz = 0, nIt = 0;
+    for (size_t k = eOff[start]; k < eOff[start + 1]; ++k) {
+      const u32 b = ent[k].blk;
+      rep[b] = ent[k].cnt;
+      repNz[nRepNz++] = b;
+    }
+    itArr[nIt] = zeroNorm; itCur[nIt] = 0; itEnd[nIt] = nZeroNorm; ++nIt;
+    u32 last = start; /* candidates must lie strictly behind this position */
+#define ADD_SOURCES()                                                                                         \
+    do {                                                                                                        \
+      if (!prefixFilter) {                                                                                      \
+        for (u32 k_ = 0; k_ < nRepNz; ++k_) {                                                                   \
+          const u32 b_ = repNz[k_];                                                                             \
+          if (!hasIt[b_]) { hasIt[b_] = 1; itArr[nIt] = post; itCur[nIt] = pOff[b_]; itEnd[nIt] = pOff[b_ + 1]; ++nIt; } \
+        }                                                                                                       \
+      } else {                                                                                                  \
+        uint64_t mass_ = 0;                                                                                     \
+        u32 nk_ = 0;                                                                                            \
+        for (u32 k_ = 0; k_ < nRepNz; ++k_) {                                                                   \
+          const u32 b_ = repNz[k_];                                                                             \
+          if (keptWarp[(b_ % B) / 32]) { mass_ += rep[b_]; byFreq[nk_++] = b_; }                                \
+        }                                                                                                       \
+        /* most frequent first (insertion sort: the lists are short) */                                         \
+        for (u32 i_ = 1; i_ < nk_; ++i_) {                                                                      \
+          const u32 v_ = byFreq[i_];                                                                            \
+          const size_t lv_ = pOff[v_ + 1] - pOff[v_];                                                           \
+          u32 j_ = i_;                                                                                          \
+          while (j_ > 0 && (pOff[byFreq[j_ - 1] + 1] - pOff[byFreq[j_ - 1]]) < lv_) { byFreq[j_] = byFreq[j_ - 1]; --j_; } \
+          byFreq[j_] = v_;                                                                                      \
+        }                                                                                                       \
+        const double budget_ = ((double)alpha * (1.0 - 1e-3) - 1e-6) * (double)mass_;                           \
+        uint64_t acc_ = 0;                                                                                      \
+        u32 skip_ = 0;                                                                                          \
+        while (skip_ < nk_ && (double)(acc_ + rep[byFreq[skip_]]) <= budget_) { acc_ += rep[byFreq[skip_]]; ++skip_; } \
+        for (u32 k_ = skip_; k_ < nk_; ++k_) {                                                                  \
+          const u32 b_ = byFreq[k_];                                                                            \
+          if (!hasIt[b_]) { hasIt[b_] = 1; itArr[nIt] = post; itCur[nIt] = pOff[b_]; itEnd[nIt] = pOff[b_ + 1]; ++nIt; } \
+        }                                                                                                       \
+      }                                                                                                         \
+    } while (0)
+    ADD_SOURCES();
+    for (;;) {
+      u32 best = ORACLE_NULL_VALUE;
+      for (u32 t = 0; t < nIt; ++t) {
+        while (itCur[t] < itEnd[t] && itArr[t][itCur[t]] <= last) ++itCur[t];
+        if (itCur[t] < itEnd[t] && itArr[t][itCur[t]] < best) best = itArr[t][itCur[t]];
+      }
+      if (best == ORACLE_NULL_VALUE) break;
+      last = best;
+      if (cid[best] != ORACLE_NULL_VALUE) continue;
+      ++evals;
+      const float sim = similarity_sparse(rep, repNz, nRepNz, ent + eOff[best], (u32)(eOff[best + 1] - eOff[best]), B,
+                                          ur, uc, fmn, fmx, mark);
+      if (sim > alpha) {
+        cid[best] = cluster;
+        for (size_t k = eOff[best]; k < eOff[best + 1]; ++k) {
+          const u32 b = ent[k].blk;
+          if (rep[b] == 0) { /* a new block of the representative */
+            u32 at = nRepNz++;
+            while (at > 0 && repNz[at - 1] > b) { repNz[at] = repNz[at - 1]; --at; }
+            repNz[at] = b;
+          }
+          rep[b] += ent[k].cnt;
+        }
+        ADD_SOURCES(); /* new blocks (and blocks that left F) feed the stream from `last` on */
+      }
+    }
+    for (u32 k = 0; k < nRepNz; ++k) rep[repNz[k]] = 0, hasIt[repNz[k]] = 0;
+#undef ADD_SOURCES
+    u32 next_start = start + 1;
+    while (next_start < M && cid[next_start] != ORACLE_NULL_VALUE) ++next_start;
+    if (next_start >= M) break;
+    start = next_start;
+    cluster++;
+  }
+  if (evaluations) *evaluations = evals;
+
+  u32* skey = (u32*)malloc(sizeof(u32) * (M ? M : 1));
+  u32* ind = (u32*)malloc(sizeof(u32) * (M ? M : 1));
+  for (u32 i = 0; i < M; ++i) skey[i] = cid[i], ind[i] = i;
+  stable_sort_by_key(skey, ind, M);
+  u32* perm = (u32*)malloc(sizeof(u32) * (M ? M : 1));
+  for (u32 i = 0; i < M; ++i) perm[i] = asc[ind[i]];
+  if (clusterCnt) *clusterCnt = M ? (int32_t)(skey[ind[M - 1]] + (u32)(zero_row_idx != 0)) : 0;
+  if (clusterOfRow)
+    for (u32 i = 0; i < M; ++i) clusterOfRow[asc[i]] = cid[i];
+  if (ascending_out) memcpy(ascending_out, asc, sizeof(u32) * M);
+  u32 s0 = 0;
+  while (s0 < M && rowOff[perm[s0] + 1] - rowOff[perm[s0]] == 0) ++s0;
+  *numRows = M - s0;
+  memcpy(reorderedRows, perm + s0, sizeof(u32) * (M - s0));
+  free(perm); free(ind); free(skey); free(itArr); free(itEnd); free(itCur); free(repNz); free(rep); free(zeroNorm);
+  free(byFreq); free(hasIt);
+  free(mark); free(fill); free(post); free(pOff); free(ent); free(tb); free(h); free(eOff); free(cid); free(asc);
+  free(keys); free(disp);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------- */
 /* BSMR.cpp:48 (float ceil; exact for numRows <= 2^24, which bounds every case
  * the reference can run; integer form used beyond that) */
 u32 oracle_num_panels(u32 numRows) { return (numRows + ORACLE_PANEL - 1) / ORACLE_PANEL; }

@@ -89,6 +89,12 @@ int oracle_rphm_build(const uint32_t* rowOff, const uint32_t* colIdx,
                       uint32_t* sparseColIndices);
 
 /* BSMR.cpp:99-119 and :221-246 work lists.  Pass NULL outputs to get counts. */
+/* oracle_row_reorder with candidate pruning through an inverted index over the non-zero blocks (alpha >= 0 only,
+ * returns -2 otherwise).  Same outputs; *evaluations receives the number of similarity evaluations made. */
+int oracle_row_reorder_pruned(const uint32_t* rowOff, const uint32_t* colIdx, uint32_t M, uint32_t N, float alpha,
+                              uint32_t block_size, uint32_t* reorderedRows, uint32_t* numRows, int32_t* clusterCnt,
+                              uint32_t* clusterOfRow, uint32_t* ascending_out, uint64_t* evaluations,
+                              int flags /* bit 0: prefix filter on the representative's block masses */);
 /* BSMR.cpp:953-994 and :826-925 (the statistics the reference logs after every run) */
 void oracle_original_block_stats(const uint32_t* rowOff, const uint32_t* colIdx, uint32_t M, uint32_t N,
                                  float delta, uint32_t* numDenseBlocks, float* averageDensity);

@@ -149,6 +149,24 @@ def row_reorder(S, alpha, bs):
     return dict(reorderedRows=out[: n.value].copy(), numClusters=cc.value, clusterOfRow=cof, ascending=asc)
 
 
+def row_reorder_pruned(S, alpha, bs, prefix_filter=False):
+    """oracle_row_reorder_pruned: the same clustering through an inverted index (alpha >= 0); adds `evaluations`."""
+    L = lib()
+    L.oracle_row_reorder_pruned.restype = C.c_int
+    L.oracle_row_reorder_pruned.argtypes = [_u32p, _u32p, C.c_uint32, C.c_uint32, C.c_float, C.c_uint32, _u32p,
+                                            C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
+                                            C.POINTER(C.c_uint64), C.c_int]
+    out = np.zeros(max(1, S.M), dtype=np.uint32)
+    n, cc, ev = C.c_uint32(0), C.c_int32(0), C.c_uint64(0)
+    cof = np.zeros(max(1, S.M), dtype=np.uint32)
+    asc = np.zeros(max(1, S.M), dtype=np.uint32)
+    rc = L.oracle_row_reorder_pruned(S.row_off, S.col_idx, S.M, S.N, float(alpha), bs, out, C.byref(n), C.byref(cc),
+                                     cof.ctypes.data, asc.ctypes.data, C.byref(ev), 1 if prefix_filter else 0)
+    assert rc == 0, rc
+    return dict(reorderedRows=out[: n.value].copy(), numClusters=cc.value, clusterOfRow=cof[: S.M],
+                ascending=asc[: S.M], evaluations=int(ev.value))
+
+
 def col_reorder(S, reordered_rows, delta):
     R = np.ascontiguousarray(reordered_rows, dtype=np.uint32)
     P = int(lib().oracle_num_panels(R.shape[0]))
