@@ -6,6 +6,7 @@
 #include "Matrix.hpp"
 
 #include <omp.h>
+#include <parallel/algorithm>
 
 #include <algorithm>
 #include <cstdio>
@@ -140,14 +141,17 @@ bool CSR<T>::initializeFromMtxFile(const std::string& file) {
     }
   }
   std::vector<uint64_t> keys(nnz_);
-  for (UIN i = 0; i < nnz_; ++i) {
-    if (ri[i] >= row_ || ci[i] >= col_) {
-      std::cerr << "Error, file " << file << " row or col is too big!" << std::endl;
-      return false;
-    }
+  bool tooBig = false;
+#pragma omp parallel for reduction(|| : tooBig)
+  for (long i = 0; i < static_cast<long>(nnz_); ++i) {
+    tooBig = tooBig || ri[i] >= row_ || ci[i] >= col_;
     keys[i] = (static_cast<uint64_t>(ri[i]) << 32) | ci[i];
   }
-  std::sort(keys.begin(), keys.end());
+  if (tooBig) {
+    std::cerr << "Error, file " << file << " row or col is too big!" << std::endl;
+    return false;
+  }
+  __gnu_parallel::sort(keys.begin(), keys.end());
   if (std::adjacent_find(keys.begin(), keys.end()) != keys.end()) {
     std::cerr << "Error, matrix has duplicate data!" << std::endl;
     return false;
