@@ -364,3 +364,15 @@ def test_pruned_clustering_random_and_edge_cases():
         a, b = O.row_reorder(S, alpha, bs), O.row_reorder_pruned(S, alpha, bs, bool(trial & 1))
         assert np.array_equal(a["reorderedRows"], b["reorderedRows"]), (trial, M, N, alpha, bs)
         assert a["numClusters"] == b["numClusters"]
+
+
+@pytest.mark.skipif(not os.environ.get("SDDMM_SLOW_TESTS"), reason="8 minutes of CPU; set SDDMM_SLOW_TESTS=1")
+def test_pruned_oracle_reproduces_reference_gpu_at_65k_rows():
+    """R-MAT scale 16 (65 536 rows, 24 047 clusters): the pruned oracle against the permutation the UNMODIFIED
+    reference GPU pipeline produced on a B200 (tests/golden/ref_gpu/rmat16_k32.npz).  The literal oracle cannot
+    reach this size (dense M x nbpr encoding, all-pairs evaluation).  Last run: equal, 137 384 802 evaluations."""
+    import make_ref_goldens as m
+    S = [c for c in m.cases(big=True) if c[0] == "rmat16_k32"][0][1]
+    z = np.load(os.path.join(REF_GPU, "rmat16_k32.npz"))
+    r = O.row_reorder_pruned(S, 0.3, int(z["block_size"]))
+    assert np.array_equal(r["reorderedRows"], z["reorderedRows"]) and r["numClusters"] == int(z["num_clusters"])
