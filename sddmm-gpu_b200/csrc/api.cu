@@ -407,9 +407,9 @@ int sddmm_run_host(const bsmr_layout* L, uint32_t K, const float* h_A, const flo
   Timer t(s);
   t.start();
   const size_t nA = (size_t)I.M * K, nB = (size_t)I.N * K, nP = I.nnz ? I.nnz : 1;
-  if (L->wsA.size() < nA) L->wsA.alloc(nA);
-  if (L->wsB.size() < nB) L->wsB.alloc(nB);
-  if (L->wsP.size() < nP) L->wsP.alloc(nP);
+  if (L->wsA.size() < nA) L->wsA.alloc(nA, true);
+  if (L->wsB.size() < nB) L->wsB.alloc(nB, true);
+  if (L->wsP.size() < nP) L->wsP.alloc(nP, true);
   float *dA = L->wsA.get(), *dB = L->wsB.get(), *dP = L->wsP.get();
   SB_CUDA(cudaMemcpyAsync(dA, h_A, nA * 4, cudaMemcpyHostToDevice, s));
   SB_CUDA(cudaMemcpyAsync(dB, h_B, nB * 4, cudaMemcpyHostToDevice, s));
@@ -442,9 +442,9 @@ int sddmm_run_host_async(const bsmr_layout* L, uint32_t K, const float* h_A, con
   const size_t nA = (size_t)I.M * K, nB = (size_t)I.N * K, nP = I.nnz ? I.nnz : 1;
   if (P.A[slot].size() < nA || P.B[slot].size() < nB || P.P[slot].size() < nP) {
     SB_CUDA(cudaDeviceSynchronize());  // growing a slot: nothing may still be using it
-    if (P.A[slot].size() < nA) P.A[slot].alloc(nA);
-    if (P.B[slot].size() < nB) P.B[slot].alloc(nB);
-    if (P.P[slot].size() < nP) P.P[slot].alloc(nP);
+    if (P.A[slot].size() < nA) P.A[slot].alloc(nA, true);
+    if (P.B[slot].size() < nB) P.B[slot].alloc(nB, true);
+    if (P.P[slot].size() < nP) P.P[slot].alloc(nP, true);
   }
   // H2D of this batch may start once the previous pass on this slot has consumed A/B
   SB_CUDA(cudaStreamWaitEvent(P.h2d, P.evComp[slot], 0));

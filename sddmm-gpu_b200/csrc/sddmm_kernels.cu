@@ -1036,8 +1036,8 @@ static const bsmr_layout::TileTma* ensure_tile_tma(const bsmr_layout* L, u32 K, 
   const u32 nR = I.numRows ? I.numRows : 1u;
   t->K = K;
   t->numBatch = numBatch;
-  t->rA.alloc((size_t)numBatch * nR * K);
-  t->rB.alloc((size_t)numBatch * I.N * K);
+  t->rA.alloc((size_t)numBatch * nR * K, true);  // outlives any scratch scope
+  t->rB.alloc((size_t)numBatch * I.N * K, true);
   encode_map(t->mapA, t->rA.get(), K, nR, numBatch, 128u);
   encode_map(t->mapB, t->rB.get(), K, I.N, numBatch, 128u);
   encode_map(t->mapA64, t->rA.get(), K, nR, numBatch, 64u);
