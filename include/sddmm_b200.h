@@ -20,6 +20,11 @@
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
  *   - There is NO CPU fallback: without a CUDA device every compute entry point fails with
  *     SDDMM_E_CUDA.
+ *   - Threading: the library keeps its streams, scratch arena, launch counter and error string per
+ *     host thread, so different threads may work on DIFFERENT layouts concurrently.  One
+ *     bsmr_layout must not be used by two threads at once: it caches K-dependent private layouts
+ *     and staging buffers inside the object (the reference is not re-entrant at all).
+ *   - A layout belongs to the CUDA device that was current when it was built.
  */
 #ifndef SDDMM_B200_H
 #define SDDMM_B200_H
