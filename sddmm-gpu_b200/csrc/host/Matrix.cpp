@@ -15,6 +15,7 @@
 #include <fstream>
 #include <iostream>
 #include <random>
+#include <unordered_map>
 
 template <typename T>
 void Matrix<T>::makeData(uint64_t seed) {
@@ -64,6 +65,7 @@ bool CSR<T>::initializeFromMatrixFile(const std::string& file) {
   const std::string s = suffix_of(file);
   if (s == ".mtx" || s == ".mmio") return initializeFromMtxFile(file);
   if (s == ".smtx") return initializeFromSmtxFile(file);
+  if (s == ".txt") return initializeFromGraphDataset(file);
   std::cerr << "Error, file format is not supported : " << file << std::endl;
   return false;
 }
@@ -212,6 +214,90 @@ bool CSR<T>::initializeFromSmtxFile(const std::string& file) {
       std::cerr << "Error, matrix has duplicate data!" << std::endl;
       return false;
     }
+  }
+  return true;
+}
+
+// SNAP edge list (src/Matrix.cpp:483-580): '#' header lines carry "Nodes: n" and "Edges: e"; every other line is
+// "from to [value]"; node ids are renumbered in order of first appearance (from before to); duplicates and
+// counts that disagree with the header are errors; rows end up stably sorted, columns in file order.
+template <typename T>
+bool CSR<T>::initializeFromGraphDataset(const std::string& file) {
+  std::vector<char> buf;
+  if (!read_file(file, buf)) {
+    std::cerr << "Error, file cannot be opened : " << file << std::endl;
+    return false;
+  }
+  std::cout << "sparseMatrix::CSR initialize from file : " << file << std::endl;
+  const char* p = buf.data();
+  row_ = col_ = nnz_ = 0;
+  while (*p == '#') {
+    const char* eol = p;
+    while (*eol && *eol != '\n') ++eol;
+    const std::string line(p, eol);
+    size_t at;
+    if ((at = line.find("Nodes: ")) != std::string::npos) row_ = col_ = static_cast<UIN>(std::strtol(line.c_str() + at + 7, nullptr, 10));
+    if ((at = line.find("Edges: ")) != std::string::npos) nnz_ = static_cast<UIN>(std::strtol(line.c_str() + at + 7, nullptr, 10));
+    p = next_line(p);
+  }
+  if (!row_ || !col_ || !nnz_) {
+    std::cerr << "Error, file " << file << " row or col or nnz not initialized!" << std::endl;
+    return false;
+  }
+  std::vector<UIN> ri, ci;
+  std::vector<T> va;
+  ri.reserve(nnz_); ci.reserve(nnz_); va.reserve(nnz_);
+  std::unordered_map<UIN, UIN> id;
+  id.reserve(static_cast<size_t>(row_) * 2);
+  auto renumber = [&](UIN node) {
+    auto it = id.find(node);
+    if (it != id.end()) return it->second;
+    const UIN n = static_cast<UIN>(id.size());
+    id.emplace(node, n);
+    return n;
+  };
+  char* e = nullptr;
+  while (*p) {
+    if (at_eol(p)) { p = next_line(p); continue; }  // empty line
+    const char* w = p;
+    const UIN a = static_cast<UIN>(std::strtol(w, &e, 10)); w = skip_blank(e);
+    const UIN b = static_cast<UIN>(std::strtol(w, &e, 10)); w = skip_blank(e);
+    const T v = at_eol(w) ? static_cast<T>(0) : static_cast<T>(std::strtod(w, &e));
+    const UIN ra = renumber(a), rb = renumber(b);
+    if (ri.size() >= nnz_) {
+      std::cerr << "Error, file " << file << " too many elements, exceeding the number nnz!" << std::endl;
+      return false;
+    }
+    ri.push_back(ra); ci.push_back(rb); va.push_back(v);
+    p = next_line(p);
+  }
+  if (ri.size() < nnz_) {
+    std::cerr << "Error, file " << file << " elements is not enough!" << std::endl;
+    return false;
+  }
+  std::vector<uint64_t> keys(nnz_);
+  for (UIN i = 0; i < nnz_; ++i) {
+    if (ri[i] >= row_ || ci[i] >= col_) {
+      std::cerr << "Error, file " << file << " row or col is too big!" << std::endl;
+      return false;
+    }
+    keys[i] = (static_cast<uint64_t>(ri[i]) << 32) | ci[i];
+  }
+  __gnu_parallel::sort(keys.begin(), keys.end());
+  if (std::adjacent_find(keys.begin(), keys.end()) != keys.end()) {
+    std::cerr << "Error, matrix has duplicate data!" << std::endl;
+    return false;
+  }
+  rowOffsets_.assign(static_cast<size_t>(row_) + 1, 0);
+  for (UIN i = 0; i < nnz_; ++i) rowOffsets_[ri[i] + 1]++;
+  for (UIN r = 0; r < row_; ++r) rowOffsets_[r + 1] += rowOffsets_[r];
+  std::vector<UIN> pos(rowOffsets_.begin(), rowOffsets_.end() - 1);
+  colIndices_.resize(nnz_);
+  values_.resize(nnz_);
+  for (UIN i = 0; i < nnz_; ++i) {
+    const UIN d = pos[ri[i]]++;
+    colIndices_[d] = ci[i];
+    values_[d] = va[i];
   }
   return true;
 }

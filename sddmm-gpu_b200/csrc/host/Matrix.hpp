@@ -76,6 +76,7 @@ class CSR : public DataBase {
   bool initializeFromMatrixFile(const std::string& file);  // suffix dispatch, src/Matrix.cpp:280-294
   bool initializeFromMtxFile(const std::string& file);     // src/Matrix.cpp:398-480
   bool initializeFromSmtxFile(const std::string& file);    // src/Matrix.cpp:296-371 (DLMC native format)
+  bool initializeFromGraphDataset(const std::string& file);  // SNAP-style .txt edge list, src/Matrix.cpp:483-580
   bool outputToMarketMatrixFile(const std::string& fileName) const;
 
   const std::vector<UIN>& rowOffsets() const { return rowOffsets_; }

@@ -206,6 +206,21 @@ def write_smtx(path, S: CSRPattern):
         f.write(" ".join(str(int(x)) for x in S.col_idx) + "\n")
 
 
+def write_snap_txt(path, S: CSRPattern, seed=0):
+    """SNAP-style edge list (the reference's `.txt` loader, src/Matrix.cpp:483-580): '#' header with
+    `Nodes: n Edges: e`, then `from<TAB>to` lines.  Node ids are scrambled (the loader renumbers them in order of
+    first appearance) and the edge order is shuffled; S must be square."""
+    assert S.M == S.N
+    rng = np.random.default_rng(seed)
+    label = rng.permutation(10 * S.M)[: S.M]  # non-contiguous ids
+    r, c = S.rows().astype(np.int64), S.col_idx.astype(np.int64)
+    o = rng.permutation(S.nnz)
+    with open(path, "w") as f:
+        f.write("# Directed graph: synthetic\n# generated by sddmm-gpu_b200.generators\n")
+        f.write("# Nodes: %d Edges: %d\n# FromNodeId\tToNodeId\n" % (S.M, S.nnz))
+        np.savetxt(f, np.stack([label[r[o]], label[c[o]]], 1), fmt="%d", delimiter="\t")
+
+
 def write_case_bin(path, S: CSRPattern, A, B):
     """Case file consumed by oracle/_ref/ref_dump (oracle/ref_dump_main.cu)."""
     K = A.shape[1]

@@ -376,3 +376,32 @@ def test_pruned_oracle_reproduces_reference_gpu_at_65k_rows():
     z = np.load(os.path.join(REF_GPU, "rmat16_k32.npz"))
     r = O.row_reorder_pruned(S, 0.3, int(z["block_size"]))
     assert np.array_equal(r["reorderedRows"], z["reorderedRows"]) and r["numClusters"] == int(z["num_clusters"])
+
+
+@needs_ref
+def test_cpp_host_graph_txt_loader_matches_reference(tmp_path):
+    """SNAP-style `.txt` edge lists (src/Matrix.cpp:483-580: '# Nodes: n Edges: e' header, node ids renumbered
+    in order of first appearance, shuffled edges): csrc/host/Matrix.cpp against the reference's own loader."""
+    import subprocess
+    from cases import ROOT
+    exe = os.path.join(ROOT, "sddmm-gpu_b200", "BSMR-sddmm")
+    if not os.access(exe, os.X_OK):
+        pytest.skip("CLI not built")
+    S = gen.rmat(9, 6, 12)
+    p = str(tmp_path / "g.txt")
+    gen.write_snap_txt(p, S, seed=3)
+    rc, (M, N, ro, ci, va) = O.ref_load_mtx(p)
+    assert rc == 0 and M == S.M and len(ci) == S.nnz
+    out = subprocess.run([exe, "-f", p, "-x", "1"], capture_output=True, text=True, timeout=60).stdout
+    tok = [l for l in out.splitlines() if l.startswith("[loader")][0].strip("[]").split()
+    got = dict(zip(tok[2::2], tok[3::2]))
+    assert int(got["M"]) == M and int(got["N"]) == N and int(got["nnz"]) == len(ci)
+    assert int(got["rowOff"], 16) == _fnv(ro) and int(got["colIdx"], 16) == _fnv(ci) and int(got["values"], 16) == _fnv(va)
+    for name, text in (("dup", "# Nodes: 3 Edges: 3\n5\t7\n7\t9\n5\t7\n"), ("few", "# Nodes: 3 Edges: 4\n5\t7\n7\t9\n9\t5\n"),
+                       ("many", "# Nodes: 3 Edges: 2\n5\t7\n7\t9\n9\t5\n"), ("nodes", "# Nodes: 2 Edges: 3\n5\t7\n7\t9\n9\t5\n"),
+                       ("nohdr", "5\t7\n7\t9\n")):
+        q = str(tmp_path / (name + ".txt"))
+        open(q, "w").write(text)
+        assert O.ref_load_mtx(q)[0] != 0, name
+        r = subprocess.run([exe, "-f", q, "-x", "1"], capture_output=True, text=True, timeout=60)
+        assert r.returncode != 0, name
