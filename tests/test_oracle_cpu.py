@@ -405,3 +405,32 @@ def test_cpp_host_graph_txt_loader_matches_reference(tmp_path):
         assert O.ref_load_mtx(q)[0] != 0, name
         r = subprocess.run([exe, "-f", q, "-x", "1"], capture_output=True, text=True, timeout=60)
         assert r.returncode != 0, name
+
+
+def test_cli_log_is_readable_by_the_reference_analyser(tmp_path):
+    """`scripts/analyze_results.cpp` of the reference (compiled unmodified into oracle/_ref/analyze_results) must
+    parse the [key : value] record our CLI writes: file, M, N, NNZ, sparsity, K and bsmr_gflops end up in its CSV.
+    (`-x 2` prints the record with a nominal 1 ms pass and needs no GPU.)"""
+    import subprocess
+    from cases import ROOT
+    exe = os.path.join(ROOT, "sddmm-gpu_b200", "BSMR-sddmm")
+    ana = os.path.join(ROOT, "oracle", "_ref", "analyze_results")
+    if not (os.access(exe, os.X_OK) and os.access(ana, os.X_OK)):
+        pytest.skip("CLI or oracle/_ref/analyze_results not built")
+    S = gen.rmat(9, 8, 3)
+    mtx = str(tmp_path / "m.mtx")
+    gen.write_mtx(mtx, S, order="col")
+    log = str(tmp_path / "results.log")
+    with open(log, "w") as f:
+        for K in (64,):
+            out = subprocess.run([exe, "-f", mtx, "-k", str(K), "-x", "2"], capture_output=True, text=True, timeout=60)
+            assert out.returncode == 0
+            f.write(out.stdout[out.stdout.index("---New data---"):])
+    r = subprocess.run([ana, log], capture_output=True, text=True, timeout=120, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-300:]
+    csv = [l for l in open(str(tmp_path / "results_64.csv")).read().splitlines() if l]
+    assert csv[0].startswith("file,M,N,NNZ,Sparsity,K,BSMR")
+    row = csv[1].split(",")
+    assert row[0] == mtx and int(row[1]) == S.M and int(row[2]) == S.N and int(row[3]) == S.nnz and int(row[5]) == 64
+    # gflops at 1 ms; two decimals, as in the reference's log (std::fixed/setprecision(2) stay set after "sparsity")
+    assert float(row[6]) == pytest.approx(2.0 * S.nnz * 64 / 1e6, abs=0.006)
