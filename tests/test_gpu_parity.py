@@ -461,3 +461,27 @@ def test_tiny_and_ragged_shapes(shape):
     for k in RPHM_KEYS:
         assert np.array_equal(res[k], rp[k]), k
     assert O.check_data(O.sddmm_cpu(S, A, B), res["P"]) == 0
+
+
+def _golden_cases():
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    import make_ref_goldens as m
+    have = {f[:-4] for f in os.listdir(os.path.join(GOLDEN, "ref_gpu")) if f.endswith(".npz")}
+    # one entry per distinct (matrix, alpha): the *_k256 / *_k128 twins share the permutation of their *_k64 / *_k32 case
+    return {c[0]: c for c in m.cases(big=True) if c[0] in have and not c[0].endswith(("_k256", "_k128"))}
+
+
+_GOLDEN_CASES = _golden_cases()
+
+
+@pytest.mark.parametrize("name", sorted(_GOLDEN_CASES))
+def test_row_reorder_matches_reference_gpu_goldens(name):
+    """our row reordering against the permutation the UNMODIFIED reference GPU pipeline produced on a B200
+    (tests/golden/ref_gpu, tests/make_ref_goldens.py) -- directly, without the oracle in between; includes the
+    4096 x 4096 masks, the nips surrogate and R-MAT scale 16 (65 536 rows, one-candidate-per-lane sweep)."""
+    _, S, _K, alpha, _delta, _ = _GOLDEN_CASES[name]
+    g = np.load(os.path.join(GOLDEN, "ref_gpu", name + ".npz"))
+    b = pkg.BSMR().rowReordering(alpha, S, block_size=int(g["block_size"]))
+    assert np.array_equal(b.reorderedRows(), g["reorderedRows"])
+    assert b.numClusters() == int(g["num_clusters"])

@@ -434,3 +434,13 @@ def test_cli_log_is_readable_by_the_reference_analyser(tmp_path):
     assert row[0] == mtx and int(row[1]) == S.M and int(row[2]) == S.N and int(row[3]) == S.nnz and int(row[5]) == 64
     # gflops at 1 ms; two decimals, as in the reference's log (std::fixed/setprecision(2) stay set after "sparsity")
     assert float(row[6]) == pytest.approx(2.0 * S.nnz * 64 / 1e6, abs=0.006)
+
+
+@pytest.mark.parametrize("name", ["bern4096s70_k64", "dlmc4096s90_k64"])
+def test_pruned_oracle_matches_reference_gpu_golden_4096(name):
+    """the 4096 x 4096 config-3 masks: permutation of the unmodified reference GPU pipeline (golden) == pruned oracle."""
+    import make_ref_goldens as m
+    S, alpha = [(c[1], c[3]) for c in m.cases(big=True) if c[0] == name][0]
+    z = np.load(os.path.join(REF_GPU, name + ".npz"))
+    r = O.row_reorder_pruned(S, alpha, int(z["block_size"]))
+    assert np.array_equal(r["reorderedRows"], z["reorderedRows"]) and r["numClusters"] == int(z["num_clusters"])
