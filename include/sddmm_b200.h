@@ -21,10 +21,17 @@
  *   - There is NO CPU fallback: without a CUDA device every compute entry point fails with
  *     SDDMM_E_CUDA.
  *   - Threading: the library keeps its streams, scratch arena, launch counter and error string per
- *     host thread, so different threads may work on DIFFERENT layouts concurrently.  One
- *     bsmr_layout must not be used by two threads at once: it caches K-dependent private layouts
- *     and staging buffers inside the object (the reference is not re-entrant at all).
- *   - A layout belongs to the CUDA device that was current when it was built.
+ *     host thread (streams additionally per device), so different threads may work on DIFFERENT
+ *     layouts concurrently.  One bsmr_layout must not be used by two threads at once: it caches
+ *     K-dependent private layouts and staging buffers inside the object (the reference is not
+ *     re-entrant at all).  Passes on ONE layout may be enqueued on different streams;
+ *     the tile-TMA plan's rounded-operand workspace is shared per (K, numBatch), so such passes are
+ *     serialised on the device by an event inside the layout (they never corrupt each other).
+ *   - A layout belongs to the CUDA device that was current when it was built; every entry point
+ *     that takes a layout fails with SDDMM_E_ARG when another device is current.
+ *   - Run calls are enqueue-only once sddmm_prepare() has been called for the (K, numBatch, plan)
+ *     in use; without it the first run for a new K builds the K-dependent private layouts
+ *     (allocations, sorts, one stream synchronisation) and is NOT capturable in a CUDA graph.
  */
 #ifndef SDDMM_B200_H
 #define SDDMM_B200_H
@@ -79,6 +86,25 @@ int bsmr_row_reorder_dev(const uint32_t* d_rowOff, const uint32_t* d_colIdx, uin
 int bsmr_row_reorder(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, uint32_t N,
                      uint32_t nnz, float alpha, uint32_t block_size, uint32_t* h_reorderedRows,
                      uint32_t* numRows, int32_t* numClusters, float* ms);
+/* Same result (the permutation is the reference's, bit for bit, whatever the options); the options only choose
+ * HOW the clustering kernel gets there, so that every variant can be parity-tested on its own.
+ * A zero-initialised struct = defaults (= the environment variables of DESIGN.md section 9, else automatic). */
+enum { BSMR_CLUSTER_AUTO = 0, BSMR_CLUSTER_LEGACY = 1, BSMR_CLUSTER_BATCHED = 2 };
+enum { BSMR_TRISTATE_AUTO = 0, BSMR_TRISTATE_OFF = 1, BSMR_TRISTATE_ON = 2 };
+typedef struct {
+  uint32_t kernel;     /* BSMR_CLUSTER_*: one cluster per sweep (k_cluster) / up to `batch` clusters per sweep */
+  uint32_t batch;      /* 0 = as many as fit shared memory, else 1, 2, 4 or 8 (template instances)            */
+  uint32_t laneRows;   /* BSMR_TRISTATE_*: one candidate row per LANE for short-row matrices                    */
+  uint32_t signature;  /* BSMR_TRISTATE_*: bitmap-signature upper bound that rejects candidates early          */
+  uint32_t reserved[4];
+} bsmr_reorder_opts;
+int bsmr_row_reorder_dev_ex(const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N,
+                            uint32_t nnz, float alpha, uint32_t block_size, const bsmr_reorder_opts* opts,
+                            uint32_t* d_reorderedRows, uint32_t* numRows, int32_t* numClusters, float* ms,
+                            void* stream);
+int bsmr_row_reorder_ex(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, uint32_t N,
+                        uint32_t nnz, float alpha, uint32_t block_size, const bsmr_reorder_opts* opts,
+                        uint32_t* h_reorderedRows, uint32_t* numRows, int32_t* numClusters, float* ms);
 
 /* optional introspection used by the parity tests (K1 encode / dispersion, a3):
  * d_dispersion[M]; returns nbpr in *numBlocksPerRow. */
@@ -103,6 +129,16 @@ int bsmr_layout_build_dev(const uint32_t* d_rowOff, const uint32_t* d_colIdx, ui
 int bsmr_layout_build(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, uint32_t N,
                       uint32_t nnz, const uint32_t* h_reorderedRows, uint32_t numRows, float delta,
                       bsmr_layout** out, float* msColReorder, float* msRphm);
+/* flags: whether the private 128x128 full-tile layout of the tile plan is built next to the BSMR/RPHM arrays
+ * (AUTO: when at least ~1 % of the tile slots are stored; the BSMR/RPHM arrays are identical either way). */
+enum { BSMR_BUILD_TILES_AUTO = 0, BSMR_BUILD_TILES_ALWAYS = 1, BSMR_BUILD_TILES_NEVER = 2 };
+int bsmr_layout_build_dev_ex(const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N,
+                             uint32_t nnz, const uint32_t* d_reorderedRows, uint32_t numRows, float delta,
+                             uint32_t panelBegin, uint32_t panelEnd, uint32_t flags, bsmr_layout** out,
+                             float* msColReorder, float* msRphm, void* stream);
+int bsmr_layout_build_ex(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, uint32_t N,
+                         uint32_t nnz, const uint32_t* h_reorderedRows, uint32_t numRows, float delta,
+                         uint32_t flags, bsmr_layout** out, float* msColReorder, float* msRphm);
 void bsmr_layout_destroy(bsmr_layout*);
 /* On-disk cache of a layout (no reference counterpart; SURVEY.md 8f rank 4: reordering costs 10^4 x one
  * SDDMM pass, so deployments persist it keyed by (matrix, alpha, delta, block_size)).  Versioned file. */
@@ -180,6 +216,38 @@ int bsmr_layout_array_to_host(const bsmr_layout*, bsmr_array_id which, uint32_t*
  * Entries of d_P not covered by this layout (other shards) are left untouched. */
 int sddmm_run_dev(const bsmr_layout*, uint32_t K, const float* d_A, const float* d_B, float* d_P,
                   void* stream);
+/* ---- kernel plan, chosen PER CALL ---------------------------------------------------------------
+ * The reference picks its kernels at compile time (commented-out launch sites, src/sddmmKernel.cu:2583-2646).
+ * Here every kernel that can serve a pass is selectable per call, so each one is parity-tested by name:
+ *   plan     BSMR  = dense 16x16 blocks (tcgen05) || residual (CUDA cores): the reference's split  (:2575, :2617)
+ *            TILE  = every stored entry through whole 128x128 tcgen05 tiles with a sampled epilogue
+ *   dense    REG   = k_sddmm_dense      (operands staged through registers, cvt.rna.tf32 on the way)
+ *            TMA   = k_sddmm_dense_tma  (TMA tile::gather4 of the denseCols rows from TF32-rounded copies)
+ *   residual PANEL = k_sddmm_residual   (one 16-row panel per CTA; any K % 4 == 0)
+ *            SUPERPANEL = k_sddmm_residual_sp (K in {32, 64, 128, 256, 512})
+ *   tile     REG / TMA / TMA_CLUSTER = k_sddmm_tile / k_sddmm_tile_tma / k_sddmm_tile_tma4
+ * AUTO everywhere = the library's cost model (the defaults of sddmm_run_dev).  A choice that cannot serve the
+ * call (SUPERPANEL with K = 36, TILE on a layout built with BSMR_BUILD_TILES_NEVER ...) fails with
+ * SDDMM_E_UNSUPPORTED instead of silently running something else. */
+enum { SDDMM_PLAN_AUTO = 0, SDDMM_PLAN_BSMR = 1, SDDMM_PLAN_TILE = 2 };
+enum { SDDMM_DENSE_AUTO = 0, SDDMM_DENSE_REG = 1, SDDMM_DENSE_TMA = 2 };
+enum { SDDMM_RESIDUAL_AUTO = 0, SDDMM_RESIDUAL_PANEL = 1, SDDMM_RESIDUAL_SUPERPANEL = 2 };
+enum { SDDMM_TILE_AUTO = 0, SDDMM_TILE_REG = 1, SDDMM_TILE_TMA = 2, SDDMM_TILE_TMA_CLUSTER = 3 };
+typedef struct {
+  uint32_t plan, dense, residual, tile;
+  uint32_t tileStages;   /* 0 = default, else 2..4 operand stages of the TMA tile kernels                      */
+  uint32_t reserved[3];
+} sddmm_plan;
+/* fills *out with the defaults: AUTO unless an SDDMM_B200_* environment variable says otherwise */
+void sddmm_plan_default(sddmm_plan* out);
+/* resolves every AUTO of `in` (NULL = defaults) for this layout / K / numBatch: *out names the kernels a run
+ * with `in` WILL launch (dense / residual are AUTO in *out when that part has no work) */
+int sddmm_plan_resolve(const bsmr_layout*, uint32_t K, uint32_t numBatch, const sddmm_plan* in, sddmm_plan* out);
+/* builds (and keeps, keyed by K / numBatch) every K-dependent private layout and workspace the plan needs, so
+ * that later runs with the same arguments only enqueue work (CUDA-graph capturable). */
+int sddmm_prepare(const bsmr_layout*, uint32_t K, uint32_t numBatch, const sddmm_plan* plan);
+int sddmm_run_dev_ex(const bsmr_layout*, uint32_t K, uint32_t numBatch, const float* d_A, const float* d_B,
+                     float* d_P, const sddmm_plan* plan, void* stream);
 /* replaces sddmm_gpu_batch(numBatch, M, N, K, nnz, dA, dB, rphm, dP, time)   src/sddmmKernel.cu:2764-2850
  * One layout, numBatch independent (A, B, P) triples stored back to back: batch b uses
  * d_A + b*M*K, d_B + b*N*K, d_P + b*nnz (the reference's blockIdx.z indexing, :1280-1283).

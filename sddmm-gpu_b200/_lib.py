@@ -36,6 +36,27 @@ class Stats(C.Structure):
                 ("sddmmMs", C.c_float), ("numClusters", C.c_int32), ("blockSize", C.c_uint32)]
 
 
+class Plan(C.Structure):
+    """sddmm_plan (include/sddmm_b200.h): which kernels serve a pass; 0 = AUTO everywhere."""
+    _fields_ = [("plan", C.c_uint32), ("dense", C.c_uint32), ("residual", C.c_uint32), ("tile", C.c_uint32),
+                ("tileStages", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+
+
+class ReorderOpts(C.Structure):
+    """bsmr_reorder_opts: how the clustering kernel gets to the (always identical) permutation."""
+    _fields_ = [("kernel", C.c_uint32), ("batch", C.c_uint32), ("laneRows", C.c_uint32), ("signature", C.c_uint32),
+                ("reserved", C.c_uint32 * 4)]
+
+
+PLAN = dict(auto=0, bsmr=1, tile=2)
+DENSE = dict(auto=0, reg=1, tma=2)
+RESIDUAL = dict(auto=0, panel=1, superpanel=2)
+TILE = dict(auto=0, reg=1, tma=2, tma_cluster=3)
+CLUSTER = dict(auto=0, legacy=1, batched=2)
+TRISTATE = dict(auto=0, off=1, on=2)
+BUILD_TILES = dict(auto=0, always=1, never=2)
+
+
 class SddmmError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libsddmm_b200 error {code}: {msg}")
@@ -75,6 +96,15 @@ def lib():
     L.bsmr_dispersion_dev.argtypes = [vp, vp, u32, u32, u32, u32, vp, pu32, vp]
     L.bsmr_layout_build_dev.argtypes = [vp, vp, u32, u32, u32, vp, u32, f32, u32, u32, C.POINTER(vp), pf32, pf32, vp]
     L.bsmr_layout_build.argtypes = [vp, vp, u32, u32, u32, vp, u32, f32, C.POINTER(vp), pf32, pf32]
+    L.bsmr_row_reorder_dev_ex.argtypes = [vp, vp, u32, u32, u32, f32, u32, C.POINTER(ReorderOpts), vp, pu32, pi32, pf32, vp]
+    L.bsmr_row_reorder_ex.argtypes = [vp, vp, u32, u32, u32, f32, u32, C.POINTER(ReorderOpts), vp, pu32, pi32, pf32]
+    L.bsmr_layout_build_dev_ex.argtypes = [vp, vp, u32, u32, u32, vp, u32, f32, u32, u32, u32, C.POINTER(vp), pf32, pf32, vp]
+    L.bsmr_layout_build_ex.argtypes = [vp, vp, u32, u32, u32, vp, u32, f32, u32, C.POINTER(vp), pf32, pf32]
+    L.sddmm_plan_default.argtypes = [C.POINTER(Plan)]
+    L.sddmm_plan_default.restype = None
+    L.sddmm_plan_resolve.argtypes = [vp, u32, u32, C.POINTER(Plan), C.POINTER(Plan)]
+    L.sddmm_prepare.argtypes = [vp, u32, u32, C.POINTER(Plan)]
+    L.sddmm_run_dev_ex.argtypes = [vp, u32, u32, vp, vp, vp, C.POINTER(Plan), vp]
     L.bsmr_layout_destroy.argtypes = [vp]
     L.bsmr_layout_destroy.restype = None
     L.bsmr_layout_get_info.argtypes = [vp, C.POINTER(LayoutInfo)]

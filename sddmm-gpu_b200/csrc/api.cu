@@ -2,6 +2,7 @@
 // forms, exception -> error code translation.  No CPU compute path exists behind any entry point.
 #include <algorithm>
 #include <chrono>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <vector>
@@ -150,10 +151,17 @@ static void require_device() {
     fail(SDDMM_E_CUDA, "no CUDA device available (%s): libsddmm_b200 has no CPU fallback",
          e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
 }
+// a layout's arrays, cached private layouts and workspaces live on the device it was built on
+static void require_layout_device(const bsmr_layout* L) {
+  int dev = -1;
+  SB_CUDA(cudaGetDevice(&dev));
+  if (dev != L->device)
+    fail(SDDMM_E_ARG, "layout belongs to CUDA device %d but device %d is current", L->device, dev);
+}
 
 extern "C" {
 
-int sddmm_b200_abi_version(void) { return 1; }
+int sddmm_b200_abi_version(void) { return 2; }
 const char* sddmm_last_error(void) { return sb::g_err.c_str(); }
 uint64_t sddmm_launch_count(void) { return sb::g_launches; }
 void sddmm_launch_count_reset(void) { sb::g_launches = 0; }
@@ -170,37 +178,55 @@ uint32_t bsmr_calc_block_size(uint32_t M, uint32_t N, uint64_t free_mem_bytes) {
   return calc_block_size(M, N, free_mem_bytes);
 }
 
-int bsmr_row_reorder_dev(const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N, uint32_t nnz,
-                         float alpha, uint32_t block_size, uint32_t* d_reorderedRows, uint32_t* numRows,
-                         int32_t* numClusters, float* ms, void* stream) {
+int bsmr_row_reorder_dev_ex(const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N, uint32_t nnz,
+                            float alpha, uint32_t block_size, const bsmr_reorder_opts* opts, uint32_t* d_reorderedRows,
+                            uint32_t* numRows, int32_t* numClusters, float* ms, void* stream) {
   API_BEGIN
   require_device();
   require(d_rowOff && d_colIdx && d_reorderedRows && numRows, "null pointer");
   if (block_size == 0) block_size = bsmr_calc_block_size(M, N, 0);
   require(block_size > 0, "block_size");
+  if (opts)
+    require(opts->kernel <= BSMR_CLUSTER_BATCHED && opts->laneRows <= BSMR_TRISTATE_ON &&
+                opts->signature <= BSMR_TRISTATE_ON &&
+                (opts->batch == 0 || opts->batch == 1 || opts->batch == 2 || opts->batch == 4 || opts->batch == 8),
+            "bsmr_reorder_opts holds an unknown selector");
   cudaStream_t s = (cudaStream_t)stream;
   Timer t(s);
   t.start();
-  row_reorder_dev(d_rowOff, d_colIdx, M, N, nnz, alpha, block_size, d_reorderedRows, numRows, numClusters, nullptr, s);
+  row_reorder_dev(d_rowOff, d_colIdx, M, N, nnz, alpha, block_size, opts, d_reorderedRows, numRows, numClusters, nullptr,
+                  s);
   const float el = t.stop();
   if (ms) *ms = el;
   API_END
 }
+int bsmr_row_reorder_dev(const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N, uint32_t nnz,
+                         float alpha, uint32_t block_size, uint32_t* d_reorderedRows, uint32_t* numRows,
+                         int32_t* numClusters, float* ms, void* stream) {
+  return bsmr_row_reorder_dev_ex(d_rowOff, d_colIdx, M, N, nnz, alpha, block_size, nullptr, d_reorderedRows, numRows,
+                                 numClusters, ms, stream);
+}
 
-int bsmr_row_reorder(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, uint32_t N, uint32_t nnz,
-                     float alpha, uint32_t block_size, uint32_t* h_reorderedRows, uint32_t* numRows,
-                     int32_t* numClusters, float* ms) {
+int bsmr_row_reorder_ex(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, uint32_t N, uint32_t nnz,
+                        float alpha, uint32_t block_size, const bsmr_reorder_opts* opts, uint32_t* h_reorderedRows,
+                        uint32_t* numRows, int32_t* numClusters, float* ms) {
   API_BEGIN
   require_device();
   require(h_rowOff && h_colIdx && h_reorderedRows && numRows, "null pointer");
   DevBuf<u32> ro((size_t)M + 1), ci(nnz ? nnz : 1), out(M ? M : 1);
   SB_CUDA(cudaMemcpy(ro.get(), h_rowOff, ((size_t)M + 1) * 4, cudaMemcpyHostToDevice));
   SB_CUDA(cudaMemcpy(ci.get(), h_colIdx, (size_t)nnz * 4, cudaMemcpyHostToDevice));
-  const int rc = bsmr_row_reorder_dev(ro.get(), ci.get(), M, N, nnz, alpha, block_size, out.get(), numRows, numClusters,
-                                      ms, nullptr);
+  const int rc = bsmr_row_reorder_dev_ex(ro.get(), ci.get(), M, N, nnz, alpha, block_size, opts, out.get(), numRows,
+                                         numClusters, ms, nullptr);
   if (rc) return rc;
   SB_CUDA(cudaMemcpy(h_reorderedRows, out.get(), (size_t)(*numRows) * 4, cudaMemcpyDeviceToHost));
   API_END
+}
+int bsmr_row_reorder(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, uint32_t N, uint32_t nnz,
+                     float alpha, uint32_t block_size, uint32_t* h_reorderedRows, uint32_t* numRows,
+                     int32_t* numClusters, float* ms) {
+  return bsmr_row_reorder_ex(h_rowOff, h_colIdx, M, N, nnz, alpha, block_size, nullptr, h_reorderedRows, numRows,
+                             numClusters, ms);
 }
 
 int bsmr_dispersion_dev(const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N, uint32_t nnz,
@@ -213,30 +239,45 @@ int bsmr_dispersion_dev(const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint
   API_END
 }
 
-int bsmr_layout_build_dev(const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N, uint32_t nnz,
-                          const uint32_t* d_reorderedRows, uint32_t numRows, float delta, uint32_t panelBegin,
-                          uint32_t panelEnd, bsmr_layout** out, float* msColReorder, float* msRphm, void* stream) {
+int bsmr_layout_build_dev_ex(const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N, uint32_t nnz,
+                             const uint32_t* d_reorderedRows, uint32_t numRows, float delta, uint32_t panelBegin,
+                             uint32_t panelEnd, uint32_t flags, bsmr_layout** out, float* msColReorder, float* msRphm,
+                             void* stream) {
   API_BEGIN
   require_device();
   require(d_rowOff && d_colIdx && out && (d_reorderedRows || numRows == 0), "null pointer");
-  *out = layout_build_dev(d_rowOff, d_colIdx, M, N, nnz, d_reorderedRows, numRows, delta, panelBegin, panelEnd,
+  require(flags <= BSMR_BUILD_TILES_NEVER, "flags");
+  *out = layout_build_dev(d_rowOff, d_colIdx, M, N, nnz, d_reorderedRows, numRows, delta, panelBegin, panelEnd, flags,
                           msColReorder, msRphm, (cudaStream_t)stream);
   API_END
 }
+int bsmr_layout_build_dev(const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N, uint32_t nnz,
+                          const uint32_t* d_reorderedRows, uint32_t numRows, float delta, uint32_t panelBegin,
+                          uint32_t panelEnd, bsmr_layout** out, float* msColReorder, float* msRphm, void* stream) {
+  return bsmr_layout_build_dev_ex(d_rowOff, d_colIdx, M, N, nnz, d_reorderedRows, numRows, delta, panelBegin, panelEnd,
+                                  BSMR_BUILD_TILES_AUTO, out, msColReorder, msRphm, stream);
+}
 
-int bsmr_layout_build(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, uint32_t N, uint32_t nnz,
-                      const uint32_t* h_reorderedRows, uint32_t numRows, float delta, bsmr_layout** out,
-                      float* msColReorder, float* msRphm) {
+int bsmr_layout_build_ex(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, uint32_t N, uint32_t nnz,
+                         const uint32_t* h_reorderedRows, uint32_t numRows, float delta, uint32_t flags,
+                         bsmr_layout** out, float* msColReorder, float* msRphm) {
   API_BEGIN
   require_device();
   require(h_rowOff && h_colIdx && out && (h_reorderedRows || numRows == 0), "null pointer");
+  require(flags <= BSMR_BUILD_TILES_NEVER, "flags");
   DevBuf<u32> ro((size_t)M + 1), ci(nnz ? nnz : 1), rr(numRows ? numRows : 1);
   SB_CUDA(cudaMemcpy(ro.get(), h_rowOff, ((size_t)M + 1) * 4, cudaMemcpyHostToDevice));
   SB_CUDA(cudaMemcpy(ci.get(), h_colIdx, (size_t)nnz * 4, cudaMemcpyHostToDevice));
   SB_CUDA(cudaMemcpy(rr.get(), h_reorderedRows, (size_t)numRows * 4, cudaMemcpyHostToDevice));
-  *out = layout_build_dev(ro.get(), ci.get(), M, N, nnz, rr.get(), numRows, delta, 0, 0xFFFFFFFFu, msColReorder,
+  *out = layout_build_dev(ro.get(), ci.get(), M, N, nnz, rr.get(), numRows, delta, 0, 0xFFFFFFFFu, flags, msColReorder,
                           msRphm, nullptr);
   API_END
+}
+int bsmr_layout_build(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, uint32_t N, uint32_t nnz,
+                      const uint32_t* h_reorderedRows, uint32_t numRows, float delta, bsmr_layout** out,
+                      float* msColReorder, float* msRphm) {
+  return bsmr_layout_build_ex(h_rowOff, h_colIdx, M, N, nnz, h_reorderedRows, numRows, delta, BSMR_BUILD_TILES_AUTO, out,
+                              msColReorder, msRphm);
 }
 
 void bsmr_layout_destroy(bsmr_layout* L) { delete L; }
@@ -322,28 +363,68 @@ struct Streams {
   }
 };
 Streams& streams() {
-  static thread_local Streams* s = nullptr;  // per host thread, per process; leaked at exit on purpose
+  // per host thread AND per device (streams and events belong to the device that was current at creation);
+  // leaked at exit on purpose
+  static thread_local std::map<int, Streams*>* byDev = nullptr;
+  if (!byDev) byDev = new std::map<int, Streams*>();
+  int dev = 0;
+  SB_CUDA(cudaGetDevice(&dev));
+  Streams*& s = (*byDev)[dev];
   if (!s) s = new Streams();
   return *s;
 }
 // dense || residual, forked from and joined back into `s`
 void run_once(const bsmr_layout* L, u32 K, const float* dA, const float* dB, float* dP, cudaStream_t s,
-              u32 numBatch = 1) {
-  Streams& st = streams();
-  if (L->numDenseWork && L->numSparseWork) {
+              u32 numBatch = 1, const sddmm_plan* plan = nullptr) {
+  require_layout_device(L);
+  sddmm_plan p;
+  plan_resolve(L, K, numBatch ? numBatch : 1, plan, &p);
+  if (p.plan == SDDMM_PLAN_BSMR && L->numDenseWork && L->numSparseWork) {
+    Streams& st = streams();
+    plan_prepare(L, K, numBatch, p, s);  // no-op when everything is cached; never inside the fork
     SB_CUDA(cudaEventRecord(st.fork, s));
     SB_CUDA(cudaStreamWaitEvent(st.dense, st.fork, 0));
     SB_CUDA(cudaStreamWaitEvent(st.sparse, st.fork, 0));
-    sddmm_launch(L, K, dA, dB, dP, st.dense, st.sparse, kLaunchBoth, numBatch);
+    sddmm_launch(L, K, dA, dB, dP, st.dense, st.sparse, kLaunchBoth, numBatch, &p);
     SB_CUDA(cudaEventRecord(st.joinD, st.dense));
     SB_CUDA(cudaEventRecord(st.joinS, st.sparse));
     SB_CUDA(cudaStreamWaitEvent(s, st.joinD, 0));
     SB_CUDA(cudaStreamWaitEvent(s, st.joinS, 0));
   } else {
-    sddmm_launch(L, K, dA, dB, dP, s, s, kLaunchBoth, numBatch);
+    sddmm_launch(L, K, dA, dB, dP, s, s, kLaunchBoth, numBatch, &p);
   }
 }
 }  // namespace
+
+void sddmm_plan_default(sddmm_plan* out) {
+  if (out) plan_default(out);
+}
+int sddmm_plan_resolve(const bsmr_layout* L, uint32_t K, uint32_t numBatch, const sddmm_plan* in, sddmm_plan* out) {
+  API_BEGIN
+  require(L && out, "null pointer");
+  plan_resolve(L, K, numBatch ? numBatch : 1, in, out);
+  API_END
+}
+int sddmm_prepare(const bsmr_layout* L, uint32_t K, uint32_t numBatch, const sddmm_plan* plan) {
+  API_BEGIN
+  require_device();
+  require(L && numBatch > 0, "arguments");
+  require_layout_device(L);
+  sddmm_plan p;
+  plan_resolve(L, K, numBatch, plan, &p);
+  cudaStream_t s = streams().dense;
+  plan_prepare(L, K, numBatch, p, s);
+  SB_CUDA(cudaStreamSynchronize(s));
+  API_END
+}
+int sddmm_run_dev_ex(const bsmr_layout* L, uint32_t K, uint32_t numBatch, const float* d_A, const float* d_B, float* d_P,
+                     const sddmm_plan* plan, void* stream) {
+  API_BEGIN
+  require_device();
+  require(L && d_A && d_B && d_P && numBatch > 0, "arguments");
+  run_once(L, K, d_A, d_B, d_P, (cudaStream_t)stream, numBatch, plan);
+  API_END
+}
 
 int sddmm_run_dev(const bsmr_layout* L, uint32_t K, const float* d_A, const float* d_B, float* d_P, void* stream) {
   API_BEGIN
@@ -367,6 +448,7 @@ int sddmm_run_timed_dev(const bsmr_layout* L, uint32_t K, const float* d_A, cons
   API_BEGIN
   require_device();
   require(L && d_A && d_B && d_P && iters > 0 && warmup >= 0, "arguments");
+  require_layout_device(L);
   Streams& st = streams();
   cudaStream_t s = st.dense;  // the launching stream of the combined pass
   for (int i = 0; i < warmup; ++i) run_once(L, K, d_A, d_B, d_P, s);
@@ -402,6 +484,7 @@ int sddmm_run_host(const bsmr_layout* L, uint32_t K, const float* h_A, const flo
   API_BEGIN
   require_device();
   require(L && h_A && h_B && h_P, "null pointer");
+  require_layout_device(L);
   const bsmr_layout_info& I = L->info;
   cudaStream_t s = streams().dense;
   Timer t(s);
@@ -409,11 +492,16 @@ int sddmm_run_host(const bsmr_layout* L, uint32_t K, const float* h_A, const flo
   const size_t nA = (size_t)I.M * K, nB = (size_t)I.N * K, nP = I.nnz ? I.nnz : 1;
   if (L->wsA.size() < nA) L->wsA.alloc(nA, true);
   if (L->wsB.size() < nB) L->wsB.alloc(nB, true);
-  if (L->wsP.size() < nP) L->wsP.alloc(nP, true);
+  if (L->wsP.size() < nP) {
+    L->wsP.alloc(nP, true);
+    SB_CUDA(cudaMemsetAsync(L->wsP.get(), 0, nP * 4, s));
+  }
   float *dA = L->wsA.get(), *dB = L->wsB.get(), *dP = L->wsP.get();
   SB_CUDA(cudaMemcpyAsync(dA, h_A, nA * 4, cudaMemcpyHostToDevice, s));
   SB_CUDA(cudaMemcpyAsync(dB, h_B, nB * 4, cudaMemcpyHostToDevice, s));
-  SB_CUDA(cudaMemsetAsync(dP, 0, (size_t)I.nnz * 4, s));  // dev::vector<float> P(nnz, 0)  sddmmKernel.cu:2525
+  // (the reference zero-fills P, sddmmKernel.cu:2525; every entry this layout covers is overwritten by the pass --
+  //  the NaN-canary test proves it -- so a full layout needs no memset; a row-panel shard leaves foreign entries
+  //  as they were, hence the one-time zeroing when the staging buffer is created)
   run_once(L, K, dA, dB, dP, s);
   SB_CUDA(cudaMemcpyAsync(h_P, dP, (size_t)I.nnz * 4, cudaMemcpyDeviceToHost, s));
   const float el = t.stop();
@@ -425,6 +513,7 @@ int sddmm_run_host_async(const bsmr_layout* L, uint32_t K, const float* h_A, con
   API_BEGIN
   require_device();
   require(L && h_A && h_B && h_P && (slot == 0 || slot == 1), "arguments");
+  require_layout_device(L);
   const bsmr_layout_info& I = L->info;
   if (!L->pipe) {
     auto pp = std::make_unique<bsmr_layout::HostPipe>();
@@ -444,7 +533,10 @@ int sddmm_run_host_async(const bsmr_layout* L, uint32_t K, const float* h_A, con
     SB_CUDA(cudaDeviceSynchronize());  // growing a slot: nothing may still be using it
     if (P.A[slot].size() < nA) P.A[slot].alloc(nA, true);
     if (P.B[slot].size() < nB) P.B[slot].alloc(nB, true);
-    if (P.P[slot].size() < nP) P.P[slot].alloc(nP, true);
+    if (P.P[slot].size() < nP) {
+      P.P[slot].alloc(nP, true);
+      SB_CUDA(cudaMemset(P.P[slot].get(), 0, nP * 4));  // once; see sddmm_run_host
+    }
   }
   // H2D of this batch may start once the previous pass on this slot has consumed A/B
   SB_CUDA(cudaStreamWaitEvent(P.h2d, P.evComp[slot], 0));
@@ -454,7 +546,6 @@ int sddmm_run_host_async(const bsmr_layout* L, uint32_t K, const float* h_A, con
   // the pass needs the operands and a P buffer whose previous contents have left for the host
   SB_CUDA(cudaStreamWaitEvent(P.comp, P.evH2D[slot], 0));
   SB_CUDA(cudaStreamWaitEvent(P.comp, P.evD2H[slot], 0));
-  SB_CUDA(cudaMemsetAsync(P.P[slot].get(), 0, (size_t)I.nnz * 4, P.comp));
   run_once(L, K, P.A[slot].get(), P.B[slot].get(), P.P[slot].get(), P.comp);
   SB_CUDA(cudaEventRecord(P.evComp[slot], P.comp));
   SB_CUDA(cudaStreamWaitEvent(P.d2h, P.evComp[slot], 0));

@@ -398,8 +398,8 @@ static void build_tiles(bsmr_layout* L, const u32* d_rowOff, const u32* d_colIdx
                         const u32* eOff, u32 nSel, cudaStream_t s);
 
 bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32 nnz, const u32* d_R,
-                              u32 numRows, float delta, u32 panelBegin, u32 panelEnd, float* msCol, float* msRphm,
-                              cudaStream_t s) {
+                              u32 numRows, float delta, u32 panelBegin, u32 panelEnd, u32 tileFlags, float* msCol,
+                              float* msRphm, cudaStream_t s) {
   const u32 Pall = (numRows + kPanel - 1) / kPanel;  // BSMR.cpp:48
   if (panelEnd > Pall) panelEnd = Pall;
   if (panelBegin > panelEnd) panelBegin = panelEnd;
@@ -450,7 +450,10 @@ bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u
     // dense enough for whole 128x128 tensor-core tiles to be worth considering? (>= ~1% of the slots)
     {
       const u64 slots = (u64)((nR + 127u) / 128u) * ((N + 127u) / 128u) * 16384ull;
-      static const int plan = [] { const char* e = getenv("SDDMM_B200_PLAN"); return e ? (!strcmp(e, "full") ? 2 : !strcmp(e, "bsmr") ? 0 : 1) : 1; }();
+      int plan = 1;  // 0 never, 1 auto, 2 always; the environment variable only fills in for AUTO
+      if (tileFlags == BSMR_BUILD_TILES_ALWAYS) plan = 2;
+      else if (tileFlags == BSMR_BUILD_TILES_NEVER) plan = 0;
+      else if (const char* e = getenv("SDDMM_B200_PLAN")) plan = !strcmp(e, "full") ? 2 : !strcmp(e, "bsmr") ? 0 : 1;
       if (plan == 2 || (plan == 1 && (u64)nSel * 100ull >= slots)) build_tiles(L, d_rowOff, d_colIdx, d_R, r0, nR, eOff.get(), nSel, s);
     }
     const int colBits = bits_for(N);  // sentinel-free here: real columns are < N
@@ -669,7 +672,10 @@ void build_quads(TileLayout& T) {
 }
 
 const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStream_t s) {
-  if (L->sp && L->sp->G == G) return L->sp.get();
+  {
+    auto it = L->sp.find(G);
+    if (it != L->sp.end()) return it->second.get();
+  }
   TempScope tempScope(s);
   const bsmr_layout_info& I = L->info;
   auto sp = std::make_unique<SuperPanelLayout>();
@@ -681,8 +687,7 @@ const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStre
   const u32 n = I.numSparseValues;
   if (n == 0 || P == 0) {
     sp->numWork = 0;
-    L->sp = std::move(sp);
-    return L->sp.get();
+    return (L->sp[G] = std::move(sp)).get();
   }
   const int rowBits = bits_for(sp->rows - 1), colBits = bits_for(I.N), spBits = bits_for(sp->numSp);
   const u32* vOff = L->arr[BSMR_SPARSE_VALUE_OFFSETS].get();
@@ -737,8 +742,7 @@ const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStre
     sp->work = std::move(sorted);
   }
   SB_CUDA(cudaStreamSynchronize(s));
-  L->sp = std::move(sp);
-  return L->sp.get();
+  return (L->sp[G] = std::move(sp)).get();
 }
 
 // ---- on-disk layout cache: reordering costs orders of magnitude more than one SDDMM pass,

@@ -1,5 +1,6 @@
 // layout.cuh -- the device-resident BSMR + RPHM layout object behind `bsmr_layout` (C ABI).
 #pragma once
+#include <map>
 #include <memory>
 
 #include "common.cuh"
@@ -48,16 +49,40 @@ struct bsmr_layout {
   // device staging buffers of the host-buffer entry point (sddmm_run_host), grown on demand and kept
   // so that repeated calls do not pay cudaMalloc/cudaFree
   mutable sb::DevBuf<float> wsA, wsB, wsP;
-  // TMA form of the tile plan: TF32-rounded, row-gathered copies of the operands (rewritten every pass) and the
-  // tensor maps describing them; (re)built when K or the batch count changes
+  // TMA forms (tile plan and BSMR dense blocks): TF32-rounded, row-gathered copies of the operands (rewritten every
+  // pass) and the tensor maps describing them.  One workspace per (K, numBatch), kept for the layout's lifetime
+  // (sddmm_prepare builds it ahead of the first run).  `busy` serialises passes that share the workspace from
+  // different streams: a pass waits for it before rounding and records it after its last reader.
   struct TileTma {
     sb::u32 K = 0, numBatch = 0;
     sb::DevBuf<float> rA, rB;                  // [numBatch][numRows][K], [numBatch][N][K]
     alignas(64) unsigned char mapA[128], mapB[128];      // CUtensorMap (box 128 rows), kept opaque here
     alignas(64) unsigned char mapA64[128], mapB64[128];  // box 64 rows: the halves a cluster member multicasts
+    cudaEvent_t busy = nullptr;
+    ~TileTma() { if (busy) cudaEventDestroy(busy); }
   };
-  mutable std::unique_ptr<TileTma> tma;
-  mutable std::unique_ptr<sb::SuperPanelLayout> sp;  // built lazily for the K in use
+  mutable std::map<sb::u64, std::unique_ptr<TileTma>> tma;              // key = K << 32 | numBatch
+  // TMA form of the BSMR dense-block kernel.  K-independent index (built once): the distinct columns that
+  // appear in denseCols and the panels that own dense blocks, each numbered compactly, so that the rounded
+  // copies hold ONLY the rows dense blocks touch (a graph's dense part uses a sliver of B).
+  struct DenseIndex {
+    sb::u32 numCols = 0, numPanels = 0;
+    sb::DevBuf<sb::u32> colList;      // [numCols]   distinct dense columns, ascending
+    sb::DevBuf<sb::u32> colCompact;   // [|denseCols|] compact id of denseCols[i] (sentinel N -> 0)
+    sb::DevBuf<sb::u32> panelList;    // [numPanels] local panels with >= 1 dense block, ascending
+    sb::DevBuf<sb::u32> workRowA;     // [numDenseWork] first compact A row of the work item's panel
+  };
+  mutable std::unique_ptr<DenseIndex> dix;
+  struct DenseTma {
+    sb::u32 K = 0, numBatch = 0;
+    sb::DevBuf<float> rA, rB;             // [numBatch][16*numPanels][K], [numBatch][numCols][K], TF32-rounded
+    alignas(64) unsigned char mapA16[128];  // 3D, box 32 floats x 16 rows: one row panel
+    alignas(64) unsigned char mapBg[128];   // 2D, box 32 floats x 1 row: tile::gather4 of four rows per instruction
+    cudaEvent_t busy = nullptr;
+    ~DenseTma() { if (busy) cudaEventDestroy(busy); }
+  };
+  mutable std::map<sb::u64, std::unique_ptr<DenseTma>> dtma;            // key = K << 32 | numBatch
+  mutable std::map<sb::u32, std::unique_ptr<sb::SuperPanelLayout>> sp;  // key = G (panels per super-panel)
   std::unique_ptr<sb::TileLayout> tl;                // built with the layout when S is dense enough to consider it
   // two-slot pipeline of sddmm_run_host_async
   struct HostPipe {
@@ -85,12 +110,12 @@ constexpr u32 kSparseChunkDefault = 2048;  // residual entries per CTA work item
 
 bsmr_layout* layout_build_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32 nnz,
                               const u32* d_reorderedRows, u32 numRows, float delta, u32 panelBegin, u32 panelEnd,
-                              float* msCol, float* msRphm, cudaStream_t s);
+                              u32 tileFlags, float* msCol, float* msRphm, cudaStream_t s);
 
 void layout_save(const bsmr_layout* L, const char* path);
 bsmr_layout* layout_load(const char* path);
 
-// (re)builds L->sp for G panels per super-panel if needed; returns it
+// builds (once, then cached) the super-panel layout for G panels per super-panel; returns it
 const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStream_t s);
 
 }  // namespace sb

@@ -846,7 +846,21 @@ void dispersion_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32 
 }
 
 void row_reorder_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32 nnz, float alpha, u32 bs,
-                     u32* d_reorderedRows, u32* numRows, int32_t* numClusters, RowReorderStats* st, cudaStream_t s) {
+                     const bsmr_reorder_opts* opts, u32* d_reorderedRows, u32* numRows, int32_t* numClusters,
+                     RowReorderStats* st, cudaStream_t s) {
+  // options: explicit > environment > automatic
+  bsmr_reorder_opts o{};
+  if (opts) o = *opts;
+  if (o.kernel == BSMR_CLUSTER_AUTO) {
+    const char* e = getenv("SDDMM_B200_CLUSTER");
+    o.kernel = (e && !strcmp(e, "legacy")) ? BSMR_CLUSTER_LEGACY : BSMR_CLUSTER_BATCHED;
+  }
+  if (o.batch == 0)
+    if (const char* e = getenv("SDDMM_B200_CLUSTER_G")) { const int v = atoi(e); if (v >= 1 && v <= 8) o.batch = (u32)v; }
+  int laneCfg = -1;  // -1 auto, 0 off, > 0 row-length threshold
+  if (o.laneRows == BSMR_TRISTATE_OFF) laneCfg = 0;
+  else if (o.laneRows == BSMR_TRISTATE_ON) laneCfg = 64;
+  else if (const char* e = getenv("SDDMM_B200_CLUSTER_LANE")) laneCfg = atoi(e);
   if (M == 0) { *numRows = 0; if (numClusters) *numClusters = 0; return; }
   TempScope tempScope(s);
   const u32 nbpr = num_blocks_per_row(N, bs);
@@ -901,7 +915,7 @@ void row_reorder_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32
   SB_CUDA(cudaMemsetAsync(ctrl.get() + 6, 0, 2 * 4, s));
   SB_CUDA(cudaMemsetAsync(ncl.get(), 0, 4, s));
   u32 exactEvals = 0;
-  static const bool legacy = [] { const char* e = getenv("SDDMM_B200_CLUSTER"); return e && !strcmp(e, "legacy"); }();
+  const bool legacy = o.kernel == BSMR_CLUSTER_LEGACY;
   DevBuf<unsigned long long> slots(4);
   DevBuf<u32> seedsBuf(16), statsBuf(8), acceptsBuf(4);
   if (zeroRows < M && !legacy) {
@@ -912,13 +926,12 @@ void row_reorder_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32
     a.accepts = acceptsBuf.get();
     // short-row matrices (graphs): evaluate one candidate per lane (SDDMM_B200_CLUSTER_LANE=0 turns it off)
     {
-      static const int laneCfg = [] { const char* e = getenv("SDDMM_B200_CLUSTER_LANE"); return e ? atoi(e) : -1; }();
       const double avgEnt = (double)totalEnt / (double)(M - zeroRows);
       a.laneRows = laneCfg == 0 ? 0u : laneCfg > 0 ? (u32)laneCfg : (avgEnt <= 24.0 ? 64u : 0u);
     }
     SB_CUDA(cudaMemsetAsync(acceptsBuf.get(), 0, 16, s));
     u32 G = (u32)((200u * 1024u) / ((size_t)nbpr * 4));
-    if (const char* e = getenv("SDDMM_B200_CLUSTER_G")) { const int v = atoi(e); if (v >= 1 && (u32)v < G) G = (u32)v; }
+    if (o.batch && o.batch < G) G = o.batch;
     G = G >= 8 ? 8u : G >= 4 ? 4u : G >= 2 ? 2u : 1u;  // template instances
     a.G = G;
     SB_CUDA(cudaMemsetAsync(slots.get(), 0xFF, 4 * 8, s));

@@ -17,6 +17,6 @@ void dispersion_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32 
                     u32* nbprOut, cudaStream_t s);
 
 void row_reorder_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32 nnz, float alpha, u32 bs,
-                     u32* d_reorderedRows, u32* numRows, int32_t* numClusters, RowReorderStats* st, cudaStream_t s);
+                     const bsmr_reorder_opts* opts, u32* d_reorderedRows, u32* numRows, int32_t* numClusters, RowReorderStats* st, cudaStream_t s);
 
 }  // namespace sb

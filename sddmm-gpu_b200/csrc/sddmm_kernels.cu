@@ -15,7 +15,12 @@
 
 #include <cuda.h>  // CUtensorMap and its enums only; the encoder is fetched through cudaGetDriverEntryPoint
 
+#include <cstring>
+#include <initializer_list>
+#include <utility>
+
 #include "layout.cuh"
+#include "primitives.cuh"
 #include "sddmm_kernels.cuh"
 
 namespace sb {
@@ -100,9 +105,11 @@ k_sddmm_residual(u32 M, u32 K4, const float4* __restrict__ A4, const float4* __r
       acc0 = fmaf(a0.z, b0.z, acc0); acc0 = fmaf(a0.w, b0.w, acc0);
     }
     float acc = acc0 + acc1;
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    // the four 8-lane groups of a warp run different trip counts: name only this group's lanes
+    const unsigned gmask = 0xFFu << (threadIdx.x & 24u);
+    acc += __shfl_xor_sync(gmask, acc, 4);
+    acc += __shfl_xor_sync(gmask, acc, 2);
+    acc += __shfl_xor_sync(gmask, acc, 1);
     if (gl == 0) P[sVals[e]] = acc;
   }
 }
@@ -240,7 +247,8 @@ static u32 superpanel_G(u32 K) {
   if (K % 32u || K > 512u) return 0;
   const u32 NB = K / 32u;
   if (NB != 1 && NB != 2 && NB != 4 && NB != 8 && NB != 16) return 0;
-  static const u32 tileKB = [] { const char* e = getenv("SDDMM_B200_SP_SMEM_KB"); return e ? (u32)atoi(e) : 192u; }();
+  u32 tileKB = 192u;
+  if (const char* e = getenv("SDDMM_B200_SP_SMEM_KB")) { const int v = atoi(e); if (v >= 16 && v <= 216) tileKB = (u32)v; }
   u32 rows = (tileKB * 1024u) / (K * 4u);
   u32 G = rows / 16u;
   if (G > 64u) G = 64u;
@@ -1004,8 +1012,264 @@ k_sddmm_tile_tma4(const __grid_constant__ CUtensorMap mapA64, const __grid_const
   cluster_sync_all();  // nobody leaves while a partner could still signal one of its barriers
 }
 
-// host side of K9: workspaces + tensor maps (cached in the layout per K / batch count)
-static void encode_map(void* out, const float* base, u32 K, u32 rows, u32 numBatch, u32 boxRows) {
+// =============================================================================================
+// dense-block kernel, TMA form (K6t): the kernel that consumes the BSMR dense blocks (replaces
+// src/sddmmKernel.cu:213-351, whose gather is the scalar __ldg loop at :279-306) with both operands staged by
+// the TMA unit.  Operands come from TF32-rounded copies (k_round_dense_rows: tcgen05 kind::tf32 truncates, the
+// reference rounds) that hold ONLY the rows dense blocks touch:
+//   * the 16 A rows of the panel: one ordinary box load (32 floats x 16 rows, SWIZZLE_128B);
+//   * the 128 gathered B^T rows: 32 x cp.async.bulk.tensor.2d ... tile::gather4 -- four row indices (compact ids
+//     of denseCols) plus the K coordinate per instruction, one instruction per lane of the producer warp, each
+//     landing 4 x 128 B at its slot of the swizzled stage;
+//   * full / empty mbarriers per stage, one MMA-issuing thread, accumulator 128 lanes x 16 TMEM columns, the same
+//     blockValues epilogue as k_sddmm_dense.
+// =============================================================================================
+constexpr u32 kDtStages = 4;
+
+__device__ __forceinline__ void tma_gather4_2d(u32 dstSmem, const void* map, u32 barSmem, u32 c0, u32 r0, u32 r1, u32 r2,
+                                               u32 r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dstSmem), "l"(map), "r"(barSmem), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+
+// rounds the rows the dense blocks touch into the compact copies: one warp per row
+static __global__ void __launch_bounds__(256) k_round_dense_rows(u32 M, u32 K4, const float4* __restrict__ A,
+                                                                 const float4* __restrict__ B, const u32* __restrict__ R,
+                                                                 u32 nR, const u32* __restrict__ panelList, u32 numPanels,
+                                                                 const u32* __restrict__ colList, u32 numCols,
+                                                                 float4* __restrict__ Ar, float4* __restrict__ Br,
+                                                                 BatchStrides bs) {
+  A += (bs.a >> 2) * blockIdx.y;
+  B += (bs.b >> 2) * blockIdx.y;
+  Ar += (size_t)numPanels * 16u * K4 * blockIdx.y;
+  Br += (size_t)numCols * K4 * blockIdx.y;
+  const u32 lane = threadIdx.x & 31u;
+  const u32 nA = numPanels * 16u;
+  const size_t nw = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < (size_t)nA + numCols; w += nw) {
+    const float4* src = nullptr;
+    float4* dst;
+    if (w < nA) {
+      const u32 ri = panelList[w >> 4] * 16u + ((u32)w & 15u);
+      if (ri < nR) {
+        const u32 row = R[ri];
+        if (row < M) src = A + (size_t)row * K4;
+      }
+      dst = Ar + w * K4;
+    } else {
+      src = B + (size_t)colList[w - nA] * K4;
+      dst = Br + (w - nA) * K4;
+    }
+    for (u32 j = lane; j < K4; j += 32) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (src) v = __ldg(src + j);
+      v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w);
+      dst[j] = v;
+    }
+  }
+}
+
+static __global__ void __launch_bounds__(kDnThreads)
+k_sddmm_dense_tma(const __grid_constant__ CUtensorMap mapA16, const __grid_constant__ CUtensorMap mapBg, u32 K,
+                  u32 numCompactCols, const u32* __restrict__ colCompact, const u32* __restrict__ blockOffsets,
+                  const u32* __restrict__ blockValues, const uint2* __restrict__ work,
+                  const u32* __restrict__ workRowA, float* __restrict__ P, size_t pStride) {
+  extern __shared__ __align__(1024) unsigned char smemRaw[];
+  P += pStride * blockIdx.y;
+  unsigned char* stages = smemRaw + ((1024u - (smem_u32(smemRaw) & 1023u)) & 1023u);
+  __shared__ u64 fullBar[kDtStages], emptyBar[kDtStages], accBar;
+  __shared__ u32 tmemBase;
+
+  const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const uint2 w = work[blockIdx.x];
+  const u32 p = w.x, firstBlk = w.y;
+  const u32 blkBeg = blockOffsets[p], blkEnd = blockOffsets[p + 1];
+  const u32 nBlk = min(kDenseGroupBlocks, blkEnd - blkBeg - firstBlk);
+  const u32 colBase = (blkBeg + firstBlk) * 16u;  // denseColOffsets[p] == blockOffsets[p] * 16
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmemBase)),
+                 "r"(kDnTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (u32 s = 0; s < kDtStages; ++s) {
+      mbar_init(&fullBar[s], 1);
+      mbar_init(&emptyBar[s], 1);
+    }
+    mbar_init(&accBar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const u32 tmem = tmemBase;
+  const u32 numChunks = (K + kDnKChunk - 1) / kDnKChunk;
+  constexpr u32 idesc = umma_idesc_tf32(128, 16);
+
+  if (warp == 0) {
+    // ---- producer: lane l owns gathered rows 4l .. 4l+3 of the stage.  Slots past the group's last block and
+    // sentinel columns read compact row 0: their accumulator lanes are never stored (blockValues holds NULL
+    // there) and every TMEM lane depends on its own row only.
+    u32 rows[4];
+    const u32 rowBase = blockIdx.y * numCompactCols;  // batch b's copy starts at row b * numCompactCols
+#pragma unroll
+    for (u32 i = 0; i < 4; ++i) {
+      const u32 slot = lane * 4u + i;
+      rows[i] = rowBase + (slot < nBlk * 16u ? __ldg(colCompact + colBase + slot) : 0u);
+    }
+    const u32 aRow = workRowA[blockIdx.x];
+    for (u32 kc = 0; kc < numChunks; ++kc) {
+      const u32 s = kc % kDtStages;
+      const u32 bar = smem_u32(&fullBar[s]);
+      const u32 dst = smem_u32(stages + s * kDnStageBytes);
+      if (lane == 0) {
+        if (kc >= kDtStages) mbar_wait_bounded(&emptyBar[s], ((kc / kDtStages) - 1) & 1u);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kDnStageBytes) : "memory");
+      }
+      __syncwarp();
+      tma_gather4_2d(dst + lane * 512u, &mapBg, bar, kc * kDnKChunk, rows[0], rows[1], rows[2], rows[3]);
+      if (lane == 0) tma_load_3d(dst + kDnRowsB * 128u, &mapA16, bar, kc * kDnKChunk, aRow, blockIdx.y);
+    }
+  } else if (warp == 1) {
+    for (u32 kc = 0; kc < numChunks; ++kc) {
+      const u32 s = kc % kDtStages;
+      if (lane == 0) {
+        mbar_wait_bounded(&fullBar[s], (kc / kDtStages) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const u32 base = smem_u32(stages + s * kDnStageBytes);
+        const u64 dB = umma_desc_sw128(base);                   // 128 gathered B^T rows: MMA "A" operand
+        const u64 dA = umma_desc_sw128(base + kDnRowsB * 128u);  // 16 panel rows: MMA "B" operand
+#pragma unroll
+        for (u32 k = 0; k < kDnKChunk / 8; ++k) {
+          const u32 acc = (kc | k) ? 1u : 0u;
+          asm volatile(
+              "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem),
+              "l"(dB + 2ull * k), "l"(dA + 2ull * k), "r"(idesc), "r"(acc)
+              : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         smem_u32(&emptyBar[s]))
+                     : "memory");
+        if (kc + 1 == numChunks)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                           smem_u32(&accBar))
+                       : "memory");
+      }
+      __syncwarp();
+    }
+  }
+  mbar_wait_bounded(&accBar, 0u);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // ---- epilogue: TMEM lane = gathered column slot j, register n = panel row
+  u32 acc[16];
+  const u32 taddr = tmem + ((warp * 32u) << 16);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]), "=r"(acc[7]),
+        "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]), "=r"(acc[14]),
+        "=r"(acc[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (tid < nBlk * 16u) {
+    const u32* bv = blockValues + ((size_t)(blkBeg + firstBlk) + (tid >> 4)) * 256u + (tid & 15u);
+#pragma unroll
+    for (u32 r = 0; r < 16; ++r) {
+      const u32 idx = __ldg(bv + r * 16u);
+      if (idx != kNull) P[idx] = __uint_as_float(acc[r]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kDnTmemCols) : "memory");
+  }
+}
+
+// ---- K-independent index of the dense part (distinct columns, panels with dense blocks), built once per layout
+static __global__ void k_mark_dense_cols(const u32* __restrict__ denseCols, size_t n, u32 N, u32* __restrict__ flag) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const u32 c = denseCols[i];
+    if (c < N) flag[c] = 1u;
+  }
+}
+static __global__ void k_mark_dense_panels(const u32* __restrict__ blockOffsets, u32 P, u32* __restrict__ flag) {
+  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x)
+    flag[p] = blockOffsets[p + 1] > blockOffsets[p] ? 1u : 0u;
+}
+static __global__ void k_compact_ids(const u32* __restrict__ flag, const u32* __restrict__ ex, size_t n,
+                                     u32* __restrict__ list) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    if (flag[i]) list[ex[i]] = (u32)i;
+}
+static __global__ void k_dense_col_compact(const u32* __restrict__ denseCols, size_t n, u32 N,
+                                           const u32* __restrict__ ex, u32* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const u32 c = denseCols[i];
+    out[i] = c < N ? ex[c] : 0u;
+  }
+}
+static __global__ void k_dense_work_rows(const uint2* __restrict__ work, u32 n, const u32* __restrict__ exPanel,
+                                         u32* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = exPanel[work[i].x] * 16u;
+}
+
+static u32 read_back_u32(const u32* d, cudaStream_t s) {
+  u32 h = 0;
+  SB_CUDA(cudaMemcpyAsync(&h, d, 4, cudaMemcpyDeviceToHost, s));
+  SB_CUDA(cudaStreamSynchronize(s));
+  return h;
+}
+
+static const bsmr_layout::DenseIndex* ensure_dense_index(const bsmr_layout* L, cudaStream_t s) {
+  if (L->dix) return L->dix.get();
+  auto d = std::make_unique<bsmr_layout::DenseIndex>();
+  const bsmr_layout_info& I = L->info;
+  const size_t nDc = L->arr[BSMR_DENSE_COLS].size();
+  const u32 P = I.numRowPanels;
+  if (nDc && P) {
+    TempScope scope(s);
+    DevBuf<u32> flagC((size_t)I.N + 1), exC((size_t)I.N + 1), flagP((size_t)P + 1), exP((size_t)P + 1);
+    SB_CUDA(cudaMemsetAsync(flagC.get(), 0, ((size_t)I.N + 1) * 4, s));
+    SB_CUDA(cudaMemsetAsync(flagP.get(), 0, ((size_t)P + 1) * 4, s));
+    k_mark_dense_cols<<<grid_for(nDc), 256, 0, s>>>(L->arr[BSMR_DENSE_COLS].get(), nDc, I.N, flagC.get());
+    SB_LAUNCH_CHECK();
+    k_mark_dense_panels<<<grid_for(P), 256, 0, s>>>(L->arr[RPHM_BLOCK_OFFSETS].get(), P, flagP.get());
+    SB_LAUNCH_CHECK();
+    exclusive_scan_u32(flagC.get(), exC.get(), (size_t)I.N + 1, s);
+    exclusive_scan_u32(flagP.get(), exP.get(), (size_t)P + 1, s);
+    d->numCols = read_back_u32(exC.get() + I.N, s);
+    d->numPanels = read_back_u32(exP.get() + P, s);
+    d->colList.alloc(d->numCols ? d->numCols : 1, true);
+    d->panelList.alloc(d->numPanels ? d->numPanels : 1, true);
+    d->colCompact.alloc(nDc, true);
+    d->workRowA.alloc(L->numDenseWork ? L->numDenseWork : 1, true);
+    k_compact_ids<<<grid_for(I.N), 256, 0, s>>>(flagC.get(), exC.get(), I.N, d->colList.get());
+    SB_LAUNCH_CHECK();
+    k_compact_ids<<<grid_for(P), 256, 0, s>>>(flagP.get(), exP.get(), P, d->panelList.get());
+    SB_LAUNCH_CHECK();
+    k_dense_col_compact<<<grid_for(nDc), 256, 0, s>>>(L->arr[BSMR_DENSE_COLS].get(), nDc, I.N, exC.get(), d->colCompact.get());
+    SB_LAUNCH_CHECK();
+    if (L->numDenseWork) {
+      k_dense_work_rows<<<grid_for(L->numDenseWork), 256, 0, s>>>(L->denseWork.get(), L->numDenseWork, exP.get(),
+                                                                 d->workRowA.get());
+      SB_LAUNCH_CHECK();
+    }
+    SB_CUDA(cudaStreamSynchronize(s));
+  }
+  L->dix = std::move(d);
+  return L->dix.get();
+}
+
+// host side of the TMA kernels: workspaces + tensor maps (cached in the layout per K / batch count)
+static void encode_map(void* out, const float* base, int rank, u32 K, u64 rows, u32 numBatch, u32 boxRows) {
   using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1022,7 +1286,7 @@ static void encode_map(void* out, const float* base, u32 K, u32 rows, u32 numBat
   const cuuint64_t strides[2] = {(cuuint64_t)K * 4u, (cuuint64_t)rows * K * 4u};
   const cuuint32_t box[3] = {kDnKChunk, boxRows, 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
-  const CUresult rc = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+  const CUresult rc = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
                          const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1030,7 +1294,11 @@ static void encode_map(void* out, const float* base, u32 K, u32 rows, u32 numBat
 }
 
 static const bsmr_layout::TileTma* ensure_tile_tma(const bsmr_layout* L, u32 K, u32 numBatch) {
-  if (L->tma && L->tma->K == K && L->tma->numBatch == numBatch) return L->tma.get();
+  const u64 key = ((u64)K << 32) | numBatch;
+  {
+    auto it = L->tma.find(key);
+    if (it != L->tma.end()) return it->second.get();
+  }
   auto t = std::make_unique<bsmr_layout::TileTma>();
   const bsmr_layout_info& I = L->info;
   const u32 nR = I.numRows ? I.numRows : 1u;
@@ -1038,22 +1306,126 @@ static const bsmr_layout::TileTma* ensure_tile_tma(const bsmr_layout* L, u32 K, 
   t->numBatch = numBatch;
   t->rA.alloc((size_t)numBatch * nR * K, true);  // outlives any scratch scope
   t->rB.alloc((size_t)numBatch * I.N * K, true);
-  encode_map(t->mapA, t->rA.get(), K, nR, numBatch, 128u);
-  encode_map(t->mapB, t->rB.get(), K, I.N, numBatch, 128u);
-  encode_map(t->mapA64, t->rA.get(), K, nR, numBatch, 64u);
-  encode_map(t->mapB64, t->rB.get(), K, I.N, numBatch, 64u);
-  L->tma = std::move(t);
-  return L->tma.get();
+  encode_map(t->mapA, t->rA.get(), 3, K, nR, numBatch, 128u);
+  encode_map(t->mapB, t->rB.get(), 3, K, I.N, numBatch, 128u);
+  encode_map(t->mapA64, t->rA.get(), 3, K, nR, numBatch, 64u);
+  encode_map(t->mapB64, t->rB.get(), 3, K, I.N, numBatch, 64u);
+  SB_CUDA(cudaEventCreateWithFlags(&t->busy, cudaEventDisableTiming));
+  return (L->tma[key] = std::move(t)).get();
+}
+
+static const bsmr_layout::DenseTma* ensure_dense_tma(const bsmr_layout* L, u32 K, u32 numBatch, cudaStream_t s) {
+  const u64 key = ((u64)K << 32) | numBatch;
+  {
+    auto it = L->dtma.find(key);
+    if (it != L->dtma.end()) return it->second.get();
+  }
+  const bsmr_layout::DenseIndex* d = ensure_dense_index(L, s);
+  auto t = std::make_unique<bsmr_layout::DenseTma>();
+  t->K = K;
+  t->numBatch = numBatch;
+  const u64 rowsA = (u64)(d->numPanels ? d->numPanels : 1u) * 16u, rowsB = d->numCols ? d->numCols : 1u;
+  t->rA.alloc((size_t)numBatch * rowsA * K, true);
+  t->rB.alloc((size_t)numBatch * rowsB * K, true);
+  encode_map(t->mapA16, t->rA.get(), 3, K, rowsA, numBatch, 16u);
+  encode_map(t->mapBg, t->rB.get(), 2, K, rowsB * numBatch, 1u, 1u);
+  SB_CUDA(cudaEventCreateWithFlags(&t->busy, cudaEventDisableTiming));
+  return (L->dtma[key] = std::move(t)).get();
 }
 
 // =============================================================================================
-// launcher
+// plan resolution + launcher
 // =============================================================================================
-void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB, float* dP, cudaStream_t denseStream,
-                  cudaStream_t sparseStream, int which, u32 numBatch) {
-  if (numBatch == 0) return;
+static u32 env_choice(const char* name, std::initializer_list<std::pair<const char*, u32>> table) {
+  const char* e = getenv(name);
+  if (!e) return 0u;
+  for (const auto& kv : table)
+    if (!strcmp(e, kv.first)) return kv.second;
+  return 0u;
+}
+
+void plan_default(sddmm_plan* out) {
+  std::memset(out, 0, sizeof *out);
+  out->plan = env_choice("SDDMM_B200_PLAN", {{"bsmr", SDDMM_PLAN_BSMR}, {"full", SDDMM_PLAN_TILE}, {"tile", SDDMM_PLAN_TILE}});
+  out->dense = env_choice("SDDMM_B200_DENSE", {{"reg", SDDMM_DENSE_REG}, {"tma", SDDMM_DENSE_TMA}});
+  out->residual = env_choice("SDDMM_B200_RESIDUAL", {{"0", SDDMM_RESIDUAL_PANEL}, {"panel", SDDMM_RESIDUAL_PANEL},
+                                                     {"1", SDDMM_RESIDUAL_SUPERPANEL}, {"sp", SDDMM_RESIDUAL_SUPERPANEL}});
+  out->tile = env_choice("SDDMM_B200_TILE", {{"reg", SDDMM_TILE_REG}, {"tma1", SDDMM_TILE_TMA}, {"tma", SDDMM_TILE_TMA},
+                                             {"tma4", SDDMM_TILE_TMA_CLUSTER}});
+  if (const char* e = getenv("SDDMM_B200_TILE_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 4) out->tileStages = (u32)v; }
+}
+
+// Resolves every AUTO.  Cost model (cycles per SM, calibrated on B200): a tile moves 2*128*K*4 bytes from L2
+// (~54 B/clk/SM) and its stores cost ~1 clk each; the BSMR kernels cost about 0.03*K + 1.5 clk per non-zero.
+void plan_resolve(const bsmr_layout* L, u32 K, u32 numBatch, const sddmm_plan* in, sddmm_plan* out) {
   if (numBatch > 65535u) fail(SDDMM_E_ARG, "numBatch=%u exceeds the grid's y extent", numBatch);
   if (K == 0 || (K & 3u)) fail(SDDMM_E_ARG, "K=%u must be a positive multiple of 4", K);
+  sddmm_plan p;
+  if (in) p = *in; else plan_default(&p);
+  if (p.plan > SDDMM_PLAN_TILE || p.dense > SDDMM_DENSE_TMA || p.residual > SDDMM_RESIDUAL_SUPERPANEL ||
+      p.tile > SDDMM_TILE_TMA_CLUSTER || (p.tileStages && (p.tileStages < 2 || p.tileStages > 4)))
+    fail(SDDMM_E_ARG, "sddmm_plan holds an unknown selector");
+  const bsmr_layout_info& I = L->info;
+  const bool haveTiles = L->tl && L->tl->numTiles;
+  if (p.plan == SDDMM_PLAN_TILE && !haveTiles) {
+    if (L->tl || (u64)I.numDenseValues + I.numSparseValues == 0) p.plan = SDDMM_PLAN_BSMR;  // nothing stored: nothing to launch
+    else fail(SDDMM_E_UNSUPPORTED, "SDDMM_PLAN_TILE: this layout was built without the full-tile layout (BSMR_BUILD_TILES_*)");
+  }
+  if (p.plan == SDDMM_PLAN_AUTO) {
+    p.plan = SDDMM_PLAN_BSMR;
+    if (haveTiles) {
+      const double tileCost = (double)L->tl->numTiles * (1024.0 * K / 54.0 + 600.0) + (double)L->tl->numEntries;
+      const double covered = (double)I.numDenseValues + (double)I.numSparseValues;  // this shard's entries
+      if (tileCost < covered * (0.03 * K + 1.5)) p.plan = SDDMM_PLAN_TILE;
+    }
+  }
+  if (p.plan == SDDMM_PLAN_TILE) {
+    // REG: register-staged tiles; TMA: one CTA per tile fed by TMA (default for K >= 128; below that the rounding
+    // pre-pass costs more than it saves); TMA_CLUSTER: 2x2 clusters with multicast (opt-in: measured slower)
+    if (p.tile == SDDMM_TILE_AUTO) p.tile = K >= 128 ? SDDMM_TILE_TMA : SDDMM_TILE_REG;
+    if (p.tile == SDDMM_TILE_TMA_CLUSTER && !L->tl->numQuads) p.tile = SDDMM_TILE_TMA;
+    if (!p.tileStages) p.tileStages = 2;
+    p.dense = SDDMM_DENSE_AUTO;
+    p.residual = SDDMM_RESIDUAL_AUTO;
+  } else {
+    p.tile = SDDMM_TILE_AUTO;
+    p.tileStages = 0;
+    if (!L->numDenseWork) p.dense = SDDMM_DENSE_AUTO;
+    else if (p.dense == SDDMM_DENSE_AUTO) p.dense = SDDMM_DENSE_REG;
+    if (!L->numSparseWork) p.residual = SDDMM_RESIDUAL_AUTO;
+    else {
+      const u32 G = superpanel_G(K);
+      if (p.residual == SDDMM_RESIDUAL_SUPERPANEL && !G)
+        fail(SDDMM_E_UNSUPPORTED, "SDDMM_RESIDUAL_SUPERPANEL needs K in {32, 64, 128, 256, 512} (K=%u)", K);
+      if (p.residual == SDDMM_RESIDUAL_AUTO) p.residual = G ? SDDMM_RESIDUAL_SUPERPANEL : SDDMM_RESIDUAL_PANEL;
+      if (p.residual == SDDMM_RESIDUAL_PANEL && (size_t)16 * K * sizeof(float) > 200 * 1024)
+        fail(SDDMM_E_UNSUPPORTED, "K=%u too large for the residual kernel's A tile", K);
+    }
+  }
+  *out = p;
+}
+
+// builds everything a run with this (resolved) plan needs; after it a run only enqueues
+void plan_prepare(const bsmr_layout* L, u32 K, u32 numBatch, const sddmm_plan& p, cudaStream_t s) {
+  if (p.plan == SDDMM_PLAN_TILE) {
+    if (p.tile != SDDMM_TILE_REG) ensure_tile_tma(L, K, numBatch);
+    return;
+  }
+  if (p.dense == SDDMM_DENSE_TMA) ensure_dense_tma(L, K, numBatch, s);
+  if (p.residual == SDDMM_RESIDUAL_SUPERPANEL) ensure_superpanels(L, superpanel_G(K), s);
+}
+
+template <typename Kern>
+static void set_smem(Kern kern, size_t smem) {
+  // per device and cheap: set on every launch path instead of caching a per-process flag
+  SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+}
+
+void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB, float* dP, cudaStream_t denseStream,
+                  cudaStream_t sparseStream, int which, u32 numBatch, const sddmm_plan* plan) {
+  if (numBatch == 0) return;
+  sddmm_plan p;
+  plan_resolve(L, K, numBatch, plan, &p);
   const bsmr_layout_info& I = L->info;
   auto arr = [&](bsmr_array_id id) { return L->arr[id].get(); };
   BatchStrides bst;
@@ -1062,108 +1434,92 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
     bst.b = (size_t)I.N * K;
     bst.p = I.nnz;
   }
-  // ---- plan selection: whole 128x128 tensor-core tiles (K8) vs BSMR dense blocks + residual.
-  // Cost model (cycles per SM, calibrated on B200): a tile moves 2*128*K*4 bytes from L2 (~54 B/clk/SM)
-  // and its stores cost ~1 clk each; the BSMR kernels cost about 0.03*K + 1.5 clk per non-zero.
-  if (L->tl && L->tl->numTiles) {
-    static const int plan = [] { const char* e = getenv("SDDMM_B200_PLAN"); return e ? (!strcmp(e, "full") ? 2 : !strcmp(e, "bsmr") ? 0 : 1) : 1; }();
-    const double tileCost = (double)L->tl->numTiles * (1024.0 * K / 54.0 + 600.0) + (double)L->tl->numEntries;
-    const double covered = (double)I.numDenseValues + (double)I.numSparseValues;  // this shard's entries
-    const double bsmrCost = covered * (0.03 * K + 1.5);
-    if (plan == 2 || (plan == 1 && tileCost < bsmrCost)) {
-      // 0: register-staged tiles; 1: TMA, one CTA per tile (default for K >= 128; below that the rounding pre-pass
-      // costs more than it saves); 2: TMA + 2x2 clusters with multicast -- halves the L2 -> SM operand traffic but
-      // measured SLOWER (64 vs 39 us at 4096^2, K=256): with one tile per CTA and two stages the per-stage handshake
-      // between the four CTAs is exposed; kept opt-in as the base of a persistent, deeper-pipelined version.
-      static const int tileCfg = [] { const char* e = getenv("SDDMM_B200_TILE"); return !e ? -1 : !strcmp(e, "reg") ? 0 : !strcmp(e, "tma4") ? 2 : 1; }();
-      const int tileMode = tileCfg >= 0 ? tileCfg : (K >= 128 ? 1 : 0);
-      if ((which & kLaunchDense) && tileMode == 2 && L->tl->numQuads) {
-        static const u32 nStages = [] { const char* e = getenv("SDDMM_B200_TILE_STAGES"); const int v = e ? atoi(e) : 2; return (u32)(v == 3 || v == 4 ? v : 2); }();
-        const size_t smem = (size_t)nStages * kTlStageBytes + 1024;
-        auto kq = nStages == 2 ? k_sddmm_tile_tma4<2> : nStages == 3 ? k_sddmm_tile_tma4<3> : k_sddmm_tile_tma4<4>;
-        SB_CUDA(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const bsmr_layout::TileTma* t = ensure_tile_tma(L, K, numBatch);
-        const u32 K4 = K / 4;
-        const size_t work = ((size_t)I.numRows + I.N) * K4;
-        k_round_operands<<<dim3((unsigned)std::min<size_t>((work + 255) / 256, 148 * 16), numBatch), 256, 0, denseStream>>>(
-            I.M, I.N, K4, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB),
-            arr(BSMR_REORDERED_ROWS), I.numRows, reinterpret_cast<float4*>(t->rA.get()),
-            reinterpret_cast<float4*>(t->rB.get()), bst);
-        SB_LAUNCH_CHECK();
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(L->tl->numQuads * 4u, numBatch);
-        cfg.blockDim = dim3(kTlThreads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = denseStream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        SB_CUDA(cudaLaunchKernelEx(&cfg, kq, *reinterpret_cast<const CUtensorMap*>(t->mapA64),
-                                   *reinterpret_cast<const CUtensorMap*>(t->mapB64), K,
-                                   (const uint2*)L->tl->quads.get(), (const u32*)L->tl->quadTiles.get(),
-                                   (const uint4*)L->tl->tiles.get(), (const u32*)L->tl->rowMeta.get(),
-                                   (const u32*)L->tl->idx.get(), dP, bst.p));
-        SB_LAUNCH_CHECK();
-      } else if ((which & kLaunchDense) && tileMode >= 1) {
-        static const u32 nStages = [] { const char* e = getenv("SDDMM_B200_TILE_STAGES"); const int v = e ? atoi(e) : 2; return (u32)(v == 3 || v == 4 ? v : 2); }();
-        const size_t smem = (size_t)nStages * kTlStageBytes + 1024;
-        auto kt = nStages == 2 ? k_sddmm_tile_tma<2> : nStages == 3 ? k_sddmm_tile_tma<3> : k_sddmm_tile_tma<4>;
-        SB_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const bsmr_layout::TileTma* t = ensure_tile_tma(L, K, numBatch);
-        const u32 K4 = K / 4;
-        const size_t work = ((size_t)I.numRows + I.N) * K4;
-        k_round_operands<<<dim3((unsigned)std::min<size_t>((work + 255) / 256, 148 * 16), numBatch), 256, 0, denseStream>>>(
-            I.M, I.N, K4, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB),
-            arr(BSMR_REORDERED_ROWS), I.numRows, reinterpret_cast<float4*>(t->rA.get()),
-            reinterpret_cast<float4*>(t->rB.get()), bst);
-        SB_LAUNCH_CHECK();
-        kt<<<dim3(L->tl->numTiles, numBatch), kTlThreads, smem, denseStream>>>(
-            *reinterpret_cast<const CUtensorMap*>(t->mapA), *reinterpret_cast<const CUtensorMap*>(t->mapB), K,
-            L->tl->tiles.get(), L->tl->rowMeta.get(), L->tl->idx.get(), dP, bst.p);
-        SB_LAUNCH_CHECK();
-      } else if (which & kLaunchDense) {
-        const size_t smem = (size_t)kTlStages * kTlStageBytes + 1024;
-        static bool attrSet = false;
-        if (!attrSet) {
-          SB_CUDA(cudaFuncSetAttribute(k_sddmm_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          attrSet = true;
-        }
-        k_sddmm_tile<<<dim3(L->tl->numTiles, numBatch), kTlThreads, smem, denseStream>>>(
-            I.M, I.N, K, dA, dB, arr(BSMR_REORDERED_ROWS), I.numRows, L->tl->tiles.get(), L->tl->rowMeta.get(),
-            L->tl->idx.get(), dP, bst);
-        SB_LAUNCH_CHECK();
-      }
-      return;  // every stored entry lives in exactly one tile
+  const u32 K4 = K / 4;
+  if (p.plan == SDDMM_PLAN_TILE) {
+    if (!(which & kLaunchDense)) return;  // every stored entry lives in exactly one tile: the "dense" side does it all
+    if (p.tile == SDDMM_TILE_REG) {
+      const size_t smem = (size_t)kTlStages * kTlStageBytes + 1024;
+      set_smem(k_sddmm_tile, smem);
+      k_sddmm_tile<<<dim3(L->tl->numTiles, numBatch), kTlThreads, smem, denseStream>>>(
+          I.M, I.N, K, dA, dB, arr(BSMR_REORDERED_ROWS), I.numRows, L->tl->tiles.get(), L->tl->rowMeta.get(),
+          L->tl->idx.get(), dP, bst);
+      SB_LAUNCH_CHECK();
+      return;
     }
+    const bsmr_layout::TileTma* t = ensure_tile_tma(L, K, numBatch);
+    const size_t smem = (size_t)p.tileStages * kTlStageBytes + 1024;
+    SB_CUDA(cudaStreamWaitEvent(denseStream, t->busy, 0));  // an earlier pass on another stream may still read rA / rB
+    const size_t work = ((size_t)I.numRows + I.N) * K4;
+    k_round_operands<<<dim3((unsigned)std::min<size_t>((work + 255) / 256, 148 * 16), numBatch), 256, 0, denseStream>>>(
+        I.M, I.N, K4, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB),
+        arr(BSMR_REORDERED_ROWS), I.numRows, reinterpret_cast<float4*>(t->rA.get()),
+        reinterpret_cast<float4*>(t->rB.get()), bst);
+    SB_LAUNCH_CHECK();
+    if (p.tile == SDDMM_TILE_TMA_CLUSTER) {
+      auto kq = p.tileStages == 2 ? k_sddmm_tile_tma4<2> : p.tileStages == 3 ? k_sddmm_tile_tma4<3> : k_sddmm_tile_tma4<4>;
+      set_smem(kq, smem);
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(L->tl->numQuads * 4u, numBatch);
+      cfg.blockDim = dim3(kTlThreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = denseStream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      SB_CUDA(cudaLaunchKernelEx(&cfg, kq, *reinterpret_cast<const CUtensorMap*>(t->mapA64),
+                                 *reinterpret_cast<const CUtensorMap*>(t->mapB64), K,
+                                 (const uint2*)L->tl->quads.get(), (const u32*)L->tl->quadTiles.get(),
+                                 (const uint4*)L->tl->tiles.get(), (const u32*)L->tl->rowMeta.get(),
+                                 (const u32*)L->tl->idx.get(), dP, bst.p));
+      SB_LAUNCH_CHECK();
+    } else {
+      auto kt = p.tileStages == 2 ? k_sddmm_tile_tma<2> : p.tileStages == 3 ? k_sddmm_tile_tma<3> : k_sddmm_tile_tma<4>;
+      set_smem(kt, smem);
+      kt<<<dim3(L->tl->numTiles, numBatch), kTlThreads, smem, denseStream>>>(
+          *reinterpret_cast<const CUtensorMap*>(t->mapA), *reinterpret_cast<const CUtensorMap*>(t->mapB), K,
+          L->tl->tiles.get(), L->tl->rowMeta.get(), L->tl->idx.get(), dP, bst.p);
+      SB_LAUNCH_CHECK();
+    }
+    SB_CUDA(cudaEventRecord(t->busy, denseStream));
+    return;
   }
   if (L->numDenseWork && (which & kLaunchDense)) {
-    const size_t smem = (size_t)kDnStages * kDnStageBytes + 1024;
-    static bool attrSet = false;
-    if (!attrSet) {
-      SB_CUDA(cudaFuncSetAttribute(k_sddmm_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attrSet = true;
+    if (p.dense == SDDMM_DENSE_TMA) {
+      const bsmr_layout::DenseTma* t = ensure_dense_tma(L, K, numBatch, denseStream);
+      const bsmr_layout::DenseIndex* d = L->dix.get();
+      SB_CUDA(cudaStreamWaitEvent(denseStream, t->busy, 0));
+      const size_t rows = (size_t)d->numPanels * 16u + d->numCols;
+      k_round_dense_rows<<<dim3((unsigned)std::min<size_t>((rows + 7) / 8, 148 * 16), numBatch), 256, 0, denseStream>>>(
+          I.M, K4, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB), arr(BSMR_REORDERED_ROWS),
+          I.numRows, d->panelList.get(), d->numPanels, d->colList.get(), d->numCols,
+          reinterpret_cast<float4*>(t->rA.get()), reinterpret_cast<float4*>(t->rB.get()), bst);
+      SB_LAUNCH_CHECK();
+      const size_t smem = (size_t)kDtStages * kDnStageBytes + 1024;
+      set_smem(k_sddmm_dense_tma, smem);
+      k_sddmm_dense_tma<<<dim3(L->numDenseWork, numBatch), kDnThreads, smem, denseStream>>>(
+          *reinterpret_cast<const CUtensorMap*>(t->mapA16), *reinterpret_cast<const CUtensorMap*>(t->mapBg), K,
+          d->numCols ? d->numCols : 1u, d->colCompact.get(), arr(RPHM_BLOCK_OFFSETS), arr(RPHM_BLOCK_VALUES),
+          L->denseWork.get(), d->workRowA.get(), dP, bst.p);
+      SB_LAUNCH_CHECK();
+      SB_CUDA(cudaEventRecord(t->busy, denseStream));
+    } else {
+      const size_t smem = (size_t)kDnStages * kDnStageBytes + 1024;
+      set_smem(k_sddmm_dense, smem);
+      k_sddmm_dense<<<dim3(L->numDenseWork, numBatch), kDnThreads, smem, denseStream>>>(
+          I.M, I.N, K, dA, dB, arr(BSMR_REORDERED_ROWS), I.numRows, arr(BSMR_DENSE_COLS), arr(RPHM_BLOCK_OFFSETS),
+          arr(RPHM_BLOCK_VALUES), L->denseWork.get(), dP, bst);
+      SB_LAUNCH_CHECK();
     }
-    k_sddmm_dense<<<dim3(L->numDenseWork, numBatch), kDnThreads, smem, denseStream>>>(
-        I.M, I.N, K, dA, dB, arr(BSMR_REORDERED_ROWS), I.numRows, arr(BSMR_DENSE_COLS), arr(RPHM_BLOCK_OFFSETS),
-        arr(RPHM_BLOCK_VALUES), L->denseWork.get(), dP, bst);
-    SB_LAUNCH_CHECK();
   }
   if (L->numSparseWork && (which & kLaunchSparse)) {
-    const u32 K4 = K / 4;
-    static const int mode = [] { const char* e = getenv("SDDMM_B200_RESIDUAL"); return e ? atoi(e) : 1; }();
-    const u32 G = mode == 1 ? superpanel_G(K) : 0;
-    if (G) {
-      const SuperPanelLayout* sp = ensure_superpanels(L, G, sparseStream);
-      // worth it only if a fetched B^T row is reused (entries per (super-panel, column) run)
-      static const float minReuse = [] { const char* e = getenv("SDDMM_B200_SP_MIN_REUSE"); return e ? (float)atof(e) : 0.0f; }();
-      const bool useSp = sp->numRuns && (float)sp->numEntries >= minReuse * (float)sp->numRuns;
-      if (!useSp) goto panel_kernel;
+    if (p.residual == SDDMM_RESIDUAL_SUPERPANEL) {
+      const SuperPanelLayout* sp = ensure_superpanels(L, superpanel_G(K), sparseStream);
       if (sp->numWork) {
         const size_t smem = (size_t)sp->rows * K * sizeof(float);
         auto launch = [&](auto kern, int threads) {
-          SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          set_smem(kern, smem);
           kern<<<dim3(sp->numWork, numBatch), threads, smem, sparseStream>>>(
               I.M, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB), arr(BSMR_REORDERED_ROWS),
               I.numRows, sp->rows, sp->segLen, sp->off.get(), sp->col.get(), sp->row.get(), sp->idx.get(),
@@ -1179,12 +1535,10 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
         SB_LAUNCH_CHECK();
       }
     } else {
-    panel_kernel:
       const size_t smem = (size_t)16 * K * sizeof(float);
-      if (smem > 200 * 1024) fail(SDDMM_E_UNSUPPORTED, "K=%u too large for the residual kernel's A tile", K);
       static const bool useL1 = [] { const char* e = getenv("SDDMM_B200_L1"); return !e || atoi(e) != 0; }();
       auto kern = useL1 ? k_sddmm_residual<true> : k_sddmm_residual<false>;
-      if (smem > 48 * 1024) SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (smem > 48 * 1024) set_smem(kern, smem);
       kern<<<dim3(L->numSparseWork, numBatch), kResThreads, smem, sparseStream>>>(
           I.M, K4, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB), arr(BSMR_REORDERED_ROWS),
           I.numRows, arr(BSMR_SPARSE_VALUE_OFFSETS), arr(RPHM_SPARSE_VALUES), arr(RPHM_SPARSE_RELATIVE_ROWS),

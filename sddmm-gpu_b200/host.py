@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import ARRAY_IDS, LayoutInfo, Stats, check
+from ._lib import ARRAY_IDS, LayoutInfo, Plan, ReorderOpts, Stats, check
 
 NULL_VALUE = 0xFFFFFFFF
 ROW_PANEL_SIZE = 16
@@ -32,6 +32,36 @@ def _ptr(a):
     if isinstance(a, np.ndarray):
         return a.ctypes.data
     return a.data_ptr()
+
+
+def make_plan(plan="auto", dense="auto", residual="auto", tile="auto", tile_stages=0):
+    """sddmm_plan by name: plan auto|bsmr|tile, dense auto|reg|tma, residual auto|panel|superpanel,
+    tile auto|reg|tma|tma_cluster.  None where the library's defaults (environment, cost model) should decide."""
+    return Plan(_lib.PLAN[plan], _lib.DENSE[dense], _lib.RESIDUAL[residual], _lib.TILE[tile], int(tile_stages))
+
+
+def make_reorder_opts(kernel="auto", batch=0, lane_rows="auto", signature="auto"):
+    return ReorderOpts(_lib.CLUSTER[kernel], int(batch), _lib.TRISTATE[lane_rows], _lib.TRISTATE[signature])
+
+
+def _plan_ptr(plan):
+    return C.byref(plan) if plan is not None else None
+
+
+def plan_resolve(layout, K, numBatch=1, plan=None):
+    """The kernels a pass with `plan` will launch on this layout, as a dict of names."""
+    lay = layout.layout() if hasattr(layout, "layout") else layout
+    out = Plan()
+    check(_lib.lib().sddmm_plan_resolve(lay.handle, int(K), int(numBatch), _plan_ptr(plan), C.byref(out)))
+    inv = lambda d, v: next(k for k, x in d.items() if x == v)
+    return dict(plan=inv(_lib.PLAN, out.plan), dense=inv(_lib.DENSE, out.dense), residual=inv(_lib.RESIDUAL, out.residual),
+                tile=inv(_lib.TILE, out.tile), tile_stages=int(out.tileStages))
+
+
+def sddmm_prepare(layout, K, numBatch=1, plan=None):
+    """Front-loads every K-dependent private layout / workspace so that later passes only enqueue kernels."""
+    lay = layout.layout() if hasattr(layout, "layout") else layout
+    check(_lib.lib().sddmm_prepare(lay.handle, int(K), int(numBatch), _plan_ptr(plan)))
 
 
 def calculateBlockSize(S, free_mem_bytes=0):
@@ -109,15 +139,16 @@ class BSMR:
             self.colReordering(delta, S)
 
     # BSMR::rowReordering  src/BSMR.cpp:27-50
-    def rowReordering(self, alpha, S, numIterations=1, block_size=0):
+    def rowReordering(self, alpha, S, numIterations=1, block_size=0, opts=None):
         L = _lib.lib()
         bs = block_size or self.blockSize_ or calculateBlockSize(S)
         out = np.zeros(max(1, S.M), dtype=np.uint32)
         n, ncl, ms = C.c_uint32(0), C.c_int32(0), C.c_float(0)
         tot = 0.0
         for _ in range(numIterations):
-            check(L.bsmr_row_reorder(S.row_off.ctypes.data, S.col_idx.ctypes.data, S.M, S.N, S.nnz, float(alpha), bs,
-                                     out.ctypes.data, C.byref(n), C.byref(ncl), C.byref(ms)))
+            check(L.bsmr_row_reorder_ex(S.row_off.ctypes.data, S.col_idx.ctypes.data, S.M, S.N, S.nnz, float(alpha), bs,
+                                        C.byref(opts) if opts is not None else None, out.ctypes.data, C.byref(n),
+                                        C.byref(ncl), C.byref(ms)))
             tot += ms.value
         self.reorderedRows_ = out[: n.value].copy()
         self.numClusters_ = ncl.value
@@ -127,16 +158,16 @@ class BSMR:
         return self
 
     # BSMR::colReordering  src/BSMR.cpp:52-81  (+ the RPHM arrays, built by the same device pass)
-    def colReordering(self, delta, S, reorderedRows=None, numIterations=1):
+    def colReordering(self, delta, S, reorderedRows=None, numIterations=1, tiles="auto"):
         L = _lib.lib()
         if reorderedRows is not None and len(reorderedRows):
             self.reorderedRows_ = _np_u32(reorderedRows)
         R = self.reorderedRows_
         h = C.c_void_p()
         msC, msR = C.c_float(0), C.c_float(0)
-        check(L.bsmr_layout_build(S.row_off.ctypes.data, S.col_idx.ctypes.data, S.M, S.N, S.nnz,
-                                  R.ctypes.data if R.size else None, R.size, float(delta), C.byref(h), C.byref(msC),
-                                  C.byref(msR)))
+        check(L.bsmr_layout_build_ex(S.row_off.ctypes.data, S.col_idx.ctypes.data, S.M, S.N, S.nnz,
+                                     R.ctypes.data if R.size else None, R.size, float(delta), _lib.BUILD_TILES[tiles],
+                                     C.byref(h), C.byref(msC), C.byref(msR)))
         self._layout = Layout(h.value)
         self.colReorderingTime_ = msC.value
         self.rphmTime_ = msR.value
@@ -187,7 +218,7 @@ class RPHM:
 
 
 # ------------------------------------------------------------------------------------------------
-def sddmm_gpu(A, B, rphm_or_layout, P=None):
+def sddmm_gpu(A, B, rphm_or_layout, P=None, plan=None):
     """sddmm_gpu(matrixA, matrixB, rphm, matrixP, logger)  src/sddmmKernel.cu:2518-2537 (host buffers:
     H2D of A and B, one pass, D2H of P)  -- or the raw device-pointer overload :2539-2663 when A, B, P
     are torch CUDA tensors.  Returns (P, ms)."""
@@ -207,11 +238,12 @@ def sddmm_gpu(A, B, rphm_or_layout, P=None):
     if P is None:
         P = torch.zeros(max(1, lay.info.nnz), dtype=torch.float32, device=A.device)
     stream = torch.cuda.current_stream().cuda_stream
-    check(L.sddmm_run_dev(lay.handle, K, A.data_ptr(), B.data_ptr(), P.data_ptr(), C.c_void_p(stream)))
+    check(L.sddmm_run_dev_ex(lay.handle, K, 1, A.data_ptr(), B.data_ptr(), P.data_ptr(), _plan_ptr(plan),
+                             C.c_void_p(stream)))
     return P, None
 
 
-def sddmm_gpu_batch(A, B, layout, P=None):
+def sddmm_gpu_batch(A, B, layout, P=None, plan=None):
     """sddmm_gpu_batch(numBatch, M, N, K, nnz, dA, dB, rphm, dP, time)  src/sddmmKernel.cu:2764-2850:
     A [numBatch, M, K], B [numBatch, N, K], P [numBatch, nnz] torch CUDA tensors; one layout for all."""
     import torch
@@ -221,8 +253,8 @@ def sddmm_gpu_batch(A, B, layout, P=None):
     if P is None:
         P = torch.zeros((nb, max(1, lay.info.nnz)), dtype=torch.float32, device=A.device)
     stream = torch.cuda.current_stream().cuda_stream
-    check(_lib.lib().sddmm_run_batch_dev(lay.handle, K, nb, A.data_ptr(), B.data_ptr(), P.data_ptr(),
-                                         C.c_void_p(stream)))
+    check(_lib.lib().sddmm_run_dev_ex(lay.handle, K, nb, A.data_ptr(), B.data_ptr(), P.data_ptr(), _plan_ptr(plan),
+                                      C.c_void_p(stream)))
     return P
 
 
@@ -276,29 +308,31 @@ def sddmm(S, A, B, alpha=0.3, delta=0.3, block_size=0, keep_layout=True):
 
 # ------------------------------------------------------------------------------------------------
 # device-resident forms (torch CUDA tensors)
-def row_reorder_dev(row_off_t, col_idx_t, M, N, alpha, block_size=0):
+def row_reorder_dev(row_off_t, col_idx_t, M, N, alpha, block_size=0, opts=None):
     import torch
 
     L = _lib.lib()
     out = torch.empty(max(1, M), dtype=torch.int32, device=row_off_t.device)
     n, ncl, ms = C.c_uint32(0), C.c_int32(0), C.c_float(0)
     stream = torch.cuda.current_stream().cuda_stream
-    check(L.bsmr_row_reorder_dev(row_off_t.data_ptr(), col_idx_t.data_ptr(), M, N, col_idx_t.numel(), float(alpha),
-                                 int(block_size), out.data_ptr(), C.byref(n), C.byref(ncl), C.byref(ms),
-                                 C.c_void_p(stream)))
+    check(L.bsmr_row_reorder_dev_ex(row_off_t.data_ptr(), col_idx_t.data_ptr(), M, N, col_idx_t.numel(), float(alpha),
+                                    int(block_size), C.byref(opts) if opts is not None else None, out.data_ptr(),
+                                    C.byref(n), C.byref(ncl), C.byref(ms), C.c_void_p(stream)))
     return out[: n.value], ncl.value, ms.value
 
 
-def layout_build_dev(row_off_t, col_idx_t, M, N, reordered_rows_t, delta, panel_begin=0, panel_end=0xFFFFFFFF):
+def layout_build_dev(row_off_t, col_idx_t, M, N, reordered_rows_t, delta, panel_begin=0, panel_end=0xFFFFFFFF,
+                     tiles="auto"):
     import torch
 
     L = _lib.lib()
     h = C.c_void_p()
     msC, msR = C.c_float(0), C.c_float(0)
     stream = torch.cuda.current_stream().cuda_stream
-    check(L.bsmr_layout_build_dev(row_off_t.data_ptr(), col_idx_t.data_ptr(), M, N, col_idx_t.numel(),
-                                  reordered_rows_t.data_ptr(), reordered_rows_t.numel(), float(delta), panel_begin,
-                                  panel_end, C.byref(h), C.byref(msC), C.byref(msR), C.c_void_p(stream)))
+    check(L.bsmr_layout_build_dev_ex(row_off_t.data_ptr(), col_idx_t.data_ptr(), M, N, col_idx_t.numel(),
+                                     reordered_rows_t.data_ptr(), reordered_rows_t.numel(), float(delta), panel_begin,
+                                     panel_end, _lib.BUILD_TILES[tiles], C.byref(h), C.byref(msC), C.byref(msR),
+                                     C.c_void_p(stream)))
     return Layout(h.value), msC.value, msR.value
 
 

@@ -163,7 +163,7 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
     syms = pkg.declared_symbols()
     assert len(syms) >= 18 and "sddmm_run_dev" in syms and "bsmr_row_reorder_dev" in syms
     L = pkg.lib()  # raises ImportError if the .so or any symbol is missing
-    assert L.sddmm_b200_abi_version() == 1
+    assert L.sddmm_b200_abi_version() == 2
 
 
 def test_product_fails_loudly_without_gpu():
