@@ -292,6 +292,36 @@ int sddmm_host(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, u
  * cuts[s+1] is shard s (numShards+1 entries).  Host arrays in, host array out. */
 int bsmr_shard_plan(const uint32_t* h_rowOff, const uint32_t* h_reorderedRows, uint32_t numRows,
                     uint32_t numShards, uint32_t* h_cuts);
+/* the same cuts from device-resident arrays (a 33 M-row order never has to visit the host); h_cuts on the host */
+int bsmr_shard_plan_dev(const uint32_t* d_rowOff, const uint32_t* d_reorderedRows, uint32_t numRows,
+                        uint32_t numShards, uint32_t* h_cuts, void* stream);
+
+/* One PROCESS per GPU.  NCCL (bound at run time with dlopen; SDDMM_B200_NCCL_LIB overrides the library name) is
+ * used for the two one-time replications only -- rank 0's row order and B -- and for the optional final merge of P.
+ * The steady state (sddmm_mgpu_run) has no collective: every rank computes the P entries of its own panel range.
+ *   rank 0:      sddmm_mgpu_unique_id(id)          -> ship the 128 bytes to every rank (file, MPI, torch.distributed)
+ *   every rank:  cudaSetDevice(local); sddmm_mgpu_init(rank, world, id, &g);
+ *                rank 0 runs bsmr_row_reorder_dev; then every rank calls
+ *                sddmm_mgpu_shard(g, ...)          -> broadcasts (numRows, reorderedRows) from rank 0, cuts the panels
+ *                                                     into `world` nnz-balanced ranges (the bsmr_shard_plan rule) and
+ *                                                     builds THIS rank's layout (panelBegin/panelEnd = its range)
+ *                sddmm_mgpu_bcast(g, d_B, bytes, 0, stream)   once per B
+ *                sddmm_mgpu_run(g, layout, K, d_A, d_B, d_P, stream)   per pass, no communication
+ *                sddmm_mgpu_gather(g, d_P, nnz, stream)       optional: every rank ends with the full P
+ * d_reorderedRows must have capacity M on every rank; *numRows is an input on rank 0 and an output elsewhere.
+ * h_cuts (optional, world + 1 entries) receives the panel cuts.  world == 1 needs no id and no NCCL. */
+#define SDDMM_MGPU_ID_BYTES 128
+typedef struct sddmm_mgpu sddmm_mgpu;
+int sddmm_mgpu_unique_id(void* id128);
+int sddmm_mgpu_init(int rank, int world, const void* id128, sddmm_mgpu** out);
+void sddmm_mgpu_destroy(sddmm_mgpu*);
+int sddmm_mgpu_shard(sddmm_mgpu*, const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N,
+                     uint32_t nnz, uint32_t* d_reorderedRows, uint32_t* numRows, float delta, uint32_t flags,
+                     bsmr_layout** out, uint32_t* h_cuts, float* msColReorder, float* msRphm, void* stream);
+int sddmm_mgpu_bcast(sddmm_mgpu*, void* d_buf, size_t bytes, int root, void* stream);
+int sddmm_mgpu_run(sddmm_mgpu*, const bsmr_layout*, uint32_t K, const float* d_A, const float* d_B, float* d_P,
+                   void* stream);
+int sddmm_mgpu_gather(sddmm_mgpu*, float* d_P, size_t count, void* stream);
 
 #ifdef __cplusplus
 }

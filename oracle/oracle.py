@@ -94,6 +94,8 @@ def ref():
         L.ref_sddmm_prepare.argtypes = [_f32p, _f32p, _u32p, _u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         L.ref_sddmm_run.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_sddmm_release.argtypes = [C.c_void_p]
+        L.ref_omp_threads.restype = C.c_int
+        L.ref_omp_threads.argtypes = [C.c_int]
         L.ref_check_data.restype = C.c_size_t
         L.ref_check_data.argtypes = [_f32p, _f32p, C.c_size_t]
         L.ref_mtx_load.restype = C.c_int

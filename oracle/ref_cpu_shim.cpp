@@ -15,6 +15,8 @@
 
 struct RefCtx { Matrix<float> A, B; sparseMatrix::CSR<float> S, P; };
 
+#include <omp.h>
+
 extern "C" {
 
 // colReordering_cpu on caller-provided CSR + row order.  Two-call protocol:
@@ -66,6 +68,13 @@ void ref_sddmm_run(void* ctx, float* P /* may be null */) {
   sddmm_cpu(c->A, c->B, c->S, c->P);
   if (P) std::memcpy(P, c->P.values().data(), sizeof(float) * c->P.values().size());
 }
+// OpenMP thread count the reference's `#pragma omp parallel for` (src/host.cpp:52) will really use; n > 0 sets it
+// first (torchrun exports OMP_NUM_THREADS=1 to its ranks, which would silently serialise the CPU baseline)
+int ref_omp_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+}
+
 void ref_sddmm_release(void* ctx) {
   delete static_cast<RefCtx*>(ctx);
 }

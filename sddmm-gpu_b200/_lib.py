@@ -123,6 +123,15 @@ def lib():
     L.sddmm_host_sync.argtypes = [vp]
     L.sddmm_host.argtypes = [vp, vp, u32, u32, u32, u32, vp, vp, f32, f32, u32, vp, C.POINTER(Stats), C.POINTER(vp)]
     L.bsmr_shard_plan.argtypes = [vp, vp, u32, u32, vp]
+    L.bsmr_shard_plan_dev.argtypes = [vp, vp, u32, u32, vp, vp]
+    L.sddmm_mgpu_unique_id.argtypes = [vp]
+    L.sddmm_mgpu_init.argtypes = [C.c_int, C.c_int, vp, C.POINTER(vp)]
+    L.sddmm_mgpu_destroy.argtypes = [vp]
+    L.sddmm_mgpu_destroy.restype = None
+    L.sddmm_mgpu_shard.argtypes = [vp, vp, vp, u32, u32, u32, vp, pu32, f32, u32, C.POINTER(vp), vp, pf32, pf32, vp]
+    L.sddmm_mgpu_bcast.argtypes = [vp, vp, C.c_size_t, C.c_int, vp]
+    L.sddmm_mgpu_run.argtypes = [vp, vp, u32, vp, vp, vp, vp]
+    L.sddmm_mgpu_gather.argtypes = [vp, vp, C.c_size_t, vp]
     L.bsmr_layout_eval.argtypes = [vp, f32, C.POINTER(Eval)]
     L.bsmr_original_block_stats_dev.argtypes = [vp, vp, u32, u32, u32, f32, vp, vp, vp]
     L.bsmr_original_block_stats.argtypes = [vp, vp, u32, u32, u32, f32, vp, vp]

@@ -126,6 +126,9 @@ int device_sm_count() {
 }
 }  // namespace sb
 
+namespace sb {
+void shard_cuts_from_prefix(const std::vector<u64>& pre, u32 numShards, u32* cuts);  // mgpu.cu
+}
 using namespace sb;
 
 #define API_BEGIN try {
@@ -610,18 +613,7 @@ int bsmr_shard_plan(const uint32_t* h_rowOff, const uint32_t* h_reorderedRows, u
     }
     pre[p + 1] = pre[p] + c;
   }
-  const u64 total = pre[P];
-  h_cuts[0] = 0;
-  u32 p = 0;
-  for (u32 s = 1; s < numShards; ++s) {
-    const u64 target = (total * s + numShards / 2) / numShards;
-    while (p < P && pre[p] < target) ++p;
-    // pick the closer of p-1 / p
-    if (p > 0 && target - pre[p - 1] < pre[p] - target) --p;
-    if (p < h_cuts[s - 1]) p = h_cuts[s - 1];
-    h_cuts[s] = p;
-  }
-  h_cuts[numShards] = P;
+  shard_cuts_from_prefix(pre, numShards, h_cuts);
   API_END
 }
 

@@ -1,0 +1,231 @@
+// mgpu.cu -- multi-GPU layer (the reference is single-GPU, so there is no counterpart to cite):
+// one process per GPU, row panels of the reordered matrix cut into nnz-balanced contiguous ranges, B and the row
+// order replicated ONCE over NCCL (NVLink 5 / NVSwitch), no collective in the steady state.
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2 -- the copy torch ships is found when the caller is a torchrun
+// rank; SDDMM_B200_NCCL_LIB names another one), so that the library loads and the single-GPU path works on a box
+// without NCCL.  The 128-byte communicator id travels out of band: the caller moves it from rank 0 to the other
+// ranks with whatever it has (a file, MPI, torch.distributed) -- see INTEGRATION.md.
+#include <dlfcn.h>
+
+#include <vector>
+
+#include "layout.cuh"
+#include "primitives.cuh"
+#include "sddmm_kernels.cuh"
+
+namespace sb {
+namespace {
+
+struct NcclId { char internal[SDDMM_MGPU_ID_BYTES]; };
+using ncclComm_t = void*;
+constexpr int kNcclUint8 = 1, kNcclFloat32 = 7, kNcclSum = 0;
+
+struct Nccl {
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+
+const Nccl& nccl() {
+  static Nccl n = [] {
+    Nccl r;
+    const char* names[] = {getenv("SDDMM_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      if (!nm || !*nm) continue;
+      r.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (r.handle) break;
+    }
+    if (!r.handle) return r;
+    auto sym = [&](const char* s) { return dlsym(r.handle, s); };
+    r.GetUniqueId = reinterpret_cast<decltype(r.GetUniqueId)>(sym("ncclGetUniqueId"));
+    r.CommInitRank = reinterpret_cast<decltype(r.CommInitRank)>(sym("ncclCommInitRank"));
+    r.CommDestroy = reinterpret_cast<decltype(r.CommDestroy)>(sym("ncclCommDestroy"));
+    r.Broadcast = reinterpret_cast<decltype(r.Broadcast)>(sym("ncclBroadcast"));
+    r.AllReduce = reinterpret_cast<decltype(r.AllReduce)>(sym("ncclAllReduce"));
+    r.GetErrorString = reinterpret_cast<decltype(r.GetErrorString)>(sym("ncclGetErrorString"));
+    if (!r.GetUniqueId || !r.CommInitRank || !r.CommDestroy || !r.Broadcast || !r.AllReduce) r.handle = nullptr;
+    return r;
+  }();
+  if (!n.handle)
+    fail(SDDMM_E_UNSUPPORTED, "NCCL is not available (dlopen libnccl.so.2 failed; set SDDMM_B200_NCCL_LIB): %s",
+         dlerror() ? dlerror() : "missing symbols");
+  return n;
+}
+
+void nccl_check(int rc, const char* what) {
+  if (rc != 0) {
+    const Nccl& n = nccl();
+    fail(SDDMM_E_CUDA, "%s failed: %s", what, n.GetErrorString ? n.GetErrorString(rc) : "NCCL error");
+  }
+}
+
+// per-panel stored-entry counts of the reordered matrix
+__global__ void k_panel_nnz(const u32* __restrict__ rowOff, const u32* __restrict__ R, u32 numRows, u32 P,
+                            u32* __restrict__ out) {
+  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
+    u32 c = 0;
+    for (u32 i = (u32)p * kPanel; i < ((u32)p + 1) * kPanel && i < numRows; ++i) {
+      const u32 r = R[i];
+      c += rowOff[r + 1] - rowOff[r];
+    }
+    out[p] = c;
+  }
+}
+
+}  // namespace
+
+// nnz-balanced contiguous panel ranges from a prefix sum over per-panel counts (the rule of bsmr_shard_plan)
+void shard_cuts_from_prefix(const std::vector<u64>& pre, u32 numShards, u32* cuts) {
+  const u32 P = (u32)pre.size() - 1;
+  const u64 total = pre[P];
+  cuts[0] = 0;
+  u32 p = 0;
+  for (u32 s = 1; s < numShards; ++s) {
+    const u64 target = (total * s + numShards / 2) / numShards;
+    while (p < P && pre[p] < target) ++p;
+    if (p > 0 && target - pre[p - 1] < pre[p] - target) --p;  // the closer of p-1 / p
+    if (p < cuts[s - 1]) p = cuts[s - 1];
+    cuts[s] = p;
+  }
+  cuts[numShards] = P;
+}
+
+void shard_plan_dev(const u32* d_rowOff, const u32* d_R, u32 numRows, u32 numShards, u32* cuts, cudaStream_t s) {
+  const u32 P = (numRows + kPanel - 1) / kPanel;
+  std::vector<u64> pre((size_t)P + 1, 0);
+  if (P) {
+    DevBuf<u32> cnt(P);
+    k_panel_nnz<<<grid_for(P), 256, 0, s>>>(d_rowOff, d_R, numRows, P, cnt.get());
+    SB_LAUNCH_CHECK();
+    std::vector<u32> h(P);
+    SB_CUDA(cudaMemcpyAsync(h.data(), cnt.get(), (size_t)P * 4, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    for (u32 p = 0; p < P; ++p) pre[p + 1] = pre[p] + h[p];
+  }
+  shard_cuts_from_prefix(pre, numShards, cuts);
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+struct sddmm_mgpu {
+  int rank = 0, world = 1, device = 0;
+  void* comm = nullptr;
+  std::vector<u32> cuts;
+};
+
+#define API_BEGIN try {
+#define API_END                                   \
+  }                                               \
+  catch (const sb::Error& e) {                    \
+    sb::set_last_error(e.what());                 \
+    return e.code;                                \
+  }                                               \
+  catch (const std::exception& e) {               \
+    sb::set_last_error(e.what());                 \
+    return SDDMM_E_CUDA;                          \
+  }                                               \
+  return SDDMM_OK;
+
+static void need(bool ok, const char* what) {
+  if (!ok) fail(SDDMM_E_ARG, "invalid argument: %s", what);
+}
+
+extern "C" {
+
+int sddmm_mgpu_unique_id(void* id128) {
+  API_BEGIN
+  need(id128 != nullptr, "null id buffer");
+  NcclId id;
+  nccl_check(nccl().GetUniqueId(&id), "ncclGetUniqueId");
+  std::memcpy(id128, id.internal, SDDMM_MGPU_ID_BYTES);
+  API_END
+}
+
+int sddmm_mgpu_init(int rank, int world, const void* id128, sddmm_mgpu** out) {
+  API_BEGIN
+  need(out && world >= 1 && rank >= 0 && rank < world && (world == 1 || id128), "rank / world / id");
+  auto g = std::make_unique<sddmm_mgpu>();
+  g->rank = rank;
+  g->world = world;
+  SB_CUDA(cudaGetDevice(&g->device));
+  if (world > 1) {
+    NcclId id;
+    std::memcpy(id.internal, id128, SDDMM_MGPU_ID_BYTES);
+    nccl_check(nccl().CommInitRank(&g->comm, world, id, rank), "ncclCommInitRank");
+  }
+  *out = g.release();
+  API_END
+}
+
+void sddmm_mgpu_destroy(sddmm_mgpu* g) {
+  if (!g) return;
+  if (g->comm) nccl().CommDestroy(g->comm);
+  delete g;
+}
+
+int sddmm_mgpu_bcast(sddmm_mgpu* g, void* d_buf, size_t bytes, int root, void* stream) {
+  API_BEGIN
+  need(g && (d_buf || bytes == 0) && root >= 0 && root < g->world, "arguments");
+  if (g->world > 1 && bytes)
+    nccl_check(nccl().Broadcast(d_buf, d_buf, bytes, kNcclUint8, root, g->comm, (cudaStream_t)stream), "ncclBroadcast");
+  API_END
+}
+
+int sddmm_mgpu_shard(sddmm_mgpu* g, const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N,
+                     uint32_t nnz, uint32_t* d_reorderedRows, uint32_t* numRows, float delta, uint32_t flags,
+                     bsmr_layout** out, uint32_t* h_cuts, float* msColReorder, float* msRphm, void* stream) {
+  API_BEGIN
+  need(g && d_rowOff && d_colIdx && d_reorderedRows && numRows && out, "null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  // rank 0's row order reaches every rank: the clustering is one sequential chain, it is computed once
+  if (g->world > 1) {
+    DevBuf<u32> n(1);
+    SB_CUDA(cudaMemcpyAsync(n.get(), numRows, 4, cudaMemcpyHostToDevice, s));
+    nccl_check(nccl().Broadcast(n.get(), n.get(), 4, kNcclUint8, 0, g->comm, s), "ncclBroadcast(numRows)");
+    SB_CUDA(cudaMemcpyAsync(numRows, n.get(), 4, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    need(*numRows <= M, "numRows from rank 0 exceeds M");
+    if (*numRows)
+      nccl_check(nccl().Broadcast(d_reorderedRows, d_reorderedRows, (size_t)*numRows * 4, kNcclUint8, 0, g->comm, s),
+                 "ncclBroadcast(reorderedRows)");
+  }
+  g->cuts.assign((size_t)g->world + 1, 0);
+  shard_plan_dev(d_rowOff, d_reorderedRows, *numRows, (u32)g->world, g->cuts.data(), s);
+  if (h_cuts) std::memcpy(h_cuts, g->cuts.data(), g->cuts.size() * 4);
+  *out = layout_build_dev(d_rowOff, d_colIdx, M, N, nnz, d_reorderedRows, *numRows, delta, g->cuts[g->rank],
+                          g->cuts[g->rank + 1], flags, msColReorder, msRphm, s);
+  API_END
+}
+
+int sddmm_mgpu_run(sddmm_mgpu* g, const bsmr_layout* L, uint32_t K, const float* d_A, const float* d_B, float* d_P,
+                   void* stream) {
+  // the steady state has no collective: a shard's pass is an ordinary pass over its own panel range
+  if (!g) { sb::set_last_error("sddmm_mgpu_run: null handle"); return SDDMM_E_ARG; }
+  return sddmm_run_dev(L, K, d_A, d_B, d_P, stream);
+}
+
+int sddmm_mgpu_gather(sddmm_mgpu* g, float* d_P, size_t count, void* stream) {
+  API_BEGIN
+  need(g && (d_P || count == 0), "arguments");
+  // shards write disjoint CSR positions and leave the rest untouched: with P zero-initialised a sum IS the merge
+  if (g->world > 1 && count)
+    nccl_check(nccl().AllReduce(d_P, d_P, count, kNcclFloat32, kNcclSum, g->comm, (cudaStream_t)stream), "ncclAllReduce");
+  API_END
+}
+
+int bsmr_shard_plan_dev(const uint32_t* d_rowOff, const uint32_t* d_reorderedRows, uint32_t numRows, uint32_t numShards,
+                        uint32_t* h_cuts, void* stream) {
+  API_BEGIN
+  need(d_rowOff && (d_reorderedRows || numRows == 0) && h_cuts && numShards > 0, "arguments");
+  shard_plan_dev(d_rowOff, d_reorderedRows, numRows, numShards, h_cuts, (cudaStream_t)stream);
+  API_END
+}
+
+}  // extern "C"

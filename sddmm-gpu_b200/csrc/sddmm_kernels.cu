@@ -1415,6 +1415,20 @@ void plan_prepare(const bsmr_layout* L, u32 K, u32 numBatch, const sddmm_plan& p
   if (p.residual == SDDMM_RESIDUAL_SUPERPANEL) ensure_superpanels(L, superpanel_G(K), s);
 }
 
+// The rounded-operand workspaces are shared by every pass of one (K, numBatch): passes on different streams are
+// ordered through the workspace's event.  Inside a stream capture the event is left alone (a captured event
+// cannot be waited on by later non-captured work); a graph's replays are ordered by their launch stream.
+static bool is_capturing(cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  return cudaStreamIsCapturing(s, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone;
+}
+static void workspace_acquire(cudaEvent_t busy, cudaStream_t s) {
+  if (!is_capturing(s)) SB_CUDA(cudaStreamWaitEvent(s, busy, 0));
+}
+static void workspace_release(cudaEvent_t busy, cudaStream_t s) {
+  if (!is_capturing(s)) SB_CUDA(cudaEventRecord(busy, s));
+}
+
 template <typename Kern>
 static void set_smem(Kern kern, size_t smem) {
   // per device and cheap: set on every launch path instead of caching a per-process flag
@@ -1448,7 +1462,7 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
     }
     const bsmr_layout::TileTma* t = ensure_tile_tma(L, K, numBatch);
     const size_t smem = (size_t)p.tileStages * kTlStageBytes + 1024;
-    SB_CUDA(cudaStreamWaitEvent(denseStream, t->busy, 0));  // an earlier pass on another stream may still read rA / rB
+    workspace_acquire(t->busy, denseStream);  // an earlier pass on another stream may still read rA / rB
     const size_t work = ((size_t)I.numRows + I.N) * K4;
     k_round_operands<<<dim3((unsigned)std::min<size_t>((work + 255) / 256, 148 * 16), numBatch), 256, 0, denseStream>>>(
         I.M, I.N, K4, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB),
@@ -1482,14 +1496,14 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
           L->tl->tiles.get(), L->tl->rowMeta.get(), L->tl->idx.get(), dP, bst.p);
       SB_LAUNCH_CHECK();
     }
-    SB_CUDA(cudaEventRecord(t->busy, denseStream));
+    workspace_release(t->busy, denseStream);
     return;
   }
   if (L->numDenseWork && (which & kLaunchDense)) {
     if (p.dense == SDDMM_DENSE_TMA) {
       const bsmr_layout::DenseTma* t = ensure_dense_tma(L, K, numBatch, denseStream);
       const bsmr_layout::DenseIndex* d = L->dix.get();
-      SB_CUDA(cudaStreamWaitEvent(denseStream, t->busy, 0));
+      workspace_acquire(t->busy, denseStream);
       const size_t rows = (size_t)d->numPanels * 16u + d->numCols;
       k_round_dense_rows<<<dim3((unsigned)std::min<size_t>((rows + 7) / 8, 148 * 16), numBatch), 256, 0, denseStream>>>(
           I.M, K4, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB), arr(BSMR_REORDERED_ROWS),
@@ -1503,7 +1517,7 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
           d->numCols ? d->numCols : 1u, d->colCompact.get(), arr(RPHM_BLOCK_OFFSETS), arr(RPHM_BLOCK_VALUES),
           L->denseWork.get(), d->workRowA.get(), dP, bst.p);
       SB_LAUNCH_CHECK();
-      SB_CUDA(cudaEventRecord(t->busy, denseStream));
+      workspace_release(t->busy, denseStream);
     } else {
       const size_t smem = (size_t)kDnStages * kDnStageBytes + 1024;
       set_smem(k_sddmm_dense, smem);

@@ -121,6 +121,63 @@ def rmat(scale, edge_factor, seed, abcd=(0.57, 0.19, 0.19, 0.05), name=None) -> 
     return _from_coo(n, n, r, col, name or f"rmat_s{scale}_ef{edge_factor}_seed{seed}")
 
 
+def rmat_device(scale, edge_factor, seed, abcd=(0.57, 0.19, 0.19, 0.05)):
+    """The same R-MAT recipe drawn, de-duplicated and turned into CSR ON THE CURRENT GPU (BASELINE configs 4 / 5:
+    2^25 vertices never exist on the host).  Returns (row_off int32[M+1] (uint32 bit patterns), col_idx int32[nnz]
+    ascending inside each row, M).  Philox with a fixed seed gives every rank of a job the same edges.
+    Input generation only: torch is plumbing here, the product path never sees it."""
+    import torch
+
+    n = edge_factor << scale
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    a, b, c, _ = abcd
+    key = torch.zeros(n, dtype=torch.int64, device="cuda")  # row << scale | col
+    for lvl in range(scale):
+        r = torch.rand(n, device="cuda", generator=g)
+        rowbit = (r >= a + b)
+        colbit = ((r >= a) & (r < a + b)) | (r >= a + b + c)
+        key |= (rowbit.to(torch.int64) << (scale + scale - 1 - lvl)) | (colbit.to(torch.int64) << (scale - 1 - lvl))
+        del r, rowbit, colbit
+    key = torch.unique(key)  # sorted, duplicates removed
+    M = 1 << scale
+    rows = key >> scale
+    ci = (key & (M - 1)).to(torch.int32)
+    del key
+    counts = torch.bincount(rows, minlength=M)
+    del rows
+    ro = torch.zeros(M + 1, dtype=torch.int64, device="cuda")
+    ro[1:] = torch.cumsum(counts, 0)
+    del counts
+    assert int(ro[-1]) < 2 ** 32
+    ro32 = torch.where(ro >= 2 ** 31, ro - 2 ** 32, ro).to(torch.int32)  # uint32 bit pattern
+    del ro
+    torch.cuda.empty_cache()
+    return ro32, ci, M
+
+
+def block_structured_scattered(M, N, n_groups, cols_per_group, row_fill, seed, noise=0.0, name=None) -> CSRPattern:
+    """Block-structured like `block_structured`, but rows of a group are interleaved over the whole matrix and
+    the group's columns are scattered over [0, N): the structure only shows after BSMR's row + column reordering
+    (the matrices the reference's dense/sparse split is made for)."""
+    rng = np.random.default_rng(seed)
+    grp = rng.integers(0, n_groups, M)
+    cols = [np.sort(rng.choice(N, cols_per_group, replace=False)) for _ in range(n_groups)]
+    rr, cc = [], []
+    for g in range(n_groups):
+        rows = np.nonzero(grp == g)[0]
+        keep = rng.random((rows.size, cols_per_group)) < row_fill
+        ri, ci = np.nonzero(keep)
+        rr.append(rows[ri])
+        cc.append(cols[g][ci])
+    if noise > 0:
+        nn = int(M * N * noise)
+        rr.append(rng.integers(0, M, nn))
+        cc.append(rng.integers(0, N, nn))
+    return _from_coo(M, N, np.concatenate(rr), np.concatenate(cc),
+                     name or f"blockscat_{M}x{N}_g{n_groups}_c{cols_per_group}_seed{seed}")
+
+
 def zipf_docs(M, N, nnz, seed, name=None) -> CSRPattern:
     """'Documents x words' with Zipf(1.0) word frequencies: surrogate for the missing
     dataset/nips.mtx (1500 x 12419, nnz 746316)."""

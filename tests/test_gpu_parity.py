@@ -485,3 +485,54 @@ def test_row_reorder_matches_reference_gpu_goldens(name):
     b = pkg.BSMR().rowReordering(alpha, S, block_size=int(g["block_size"]))
     assert np.array_equal(b.reorderedRows(), g["reorderedRows"])
     assert b.numClusters() == int(g["num_clusters"])
+
+
+def test_cli_test_mode_sweep_feeds_the_reference_analyser(tmp_path):
+    """`BSMR-sddmm -f file -t 1 -l dir` (sddmm_testMode, src/sddmm.cu:62-118; the invocation of
+    scripts/test_script.sh:92): the alpha x delta x K sweep writes one log per (K, alpha, delta) = 140 files, each
+    holding one [key : value] record; the reference's own analyser (scripts/analyze_results.cpp, compiled unmodified
+    into oracle/_ref/analyze_results) reads ALL of them and emits its per-K CSVs with the best BSMR GFLOP/s."""
+    exe = os.path.join(ROOT, "sddmm-gpu_b200", "BSMR-sddmm")
+    ana = os.path.join(ROOT, "oracle", "_ref", "analyze_results")
+    assert os.access(exe, os.X_OK), "CLI not built"
+    if not os.access(ana, os.X_OK):
+        pytest.skip("oracle/_ref/analyze_results not shipped")
+    S = gen.block_structured(256, 384, 4, 64, 0.8, seed=5, noise=0.01)
+    mtx = str(tmp_path / "sweep.mtx")
+    gen.write_mtx(mtx, S, order="col")
+    logdir = tmp_path / "logs"
+    logdir.mkdir()
+    p = subprocess.run([exe, "-f", mtx, "-t", "1", "-l", str(logdir) + "/", "-b", "16"], capture_output=True, text=True,
+                       timeout=900)
+    assert p.returncode == 0, p.stderr[-400:]
+    logs = sorted(os.listdir(logdir))
+    assert len(logs) == 5 * 7 * 4, len(logs)  # alphas x deltas x Ks
+    assert "BSMR_k_128_a_0.3_d_0.3.log" in logs and "BSMR_k_32_a_0.1_d_0.log" in logs and "BSMR_k_256_a_0.9_d_1.1.log" in logs
+    # every record carries the sweep's own (alpha, delta, K), a positive kernel time, and delta's effect on the split
+    seen = {}
+    for name in logs:
+        txt = open(logdir / name).read()
+        assert txt.count("---New data---") == 1
+        kv = dict(l.strip("[]").split(" : ", 1) for l in txt.replace("], [", "]\n[").splitlines() if " : " in l and l.startswith("["))
+        k, a, d = int(kv["K"]), float(kv["bsmr_alpha"]), float(kv["bsmr_delta"])
+        assert name == f"BSMR_k_{k}_a_{a:g}_d_{d:g}.log"
+        assert float(kv["bsmr_sddmm"]) > 0 and float(kv["bsmr_gflops"]) > 0 and int(kv["NNZ"]) == S.nnz
+        seen[(k, a, d)] = (int(kv["bsmr_numDenseData"]), int(kv["bsmr_numSparseData"]))
+    for (k, a, d), (nd, ns) in seen.items():
+        assert nd + ns == S.nnz
+        if d > 1.0:
+            assert nd == 0
+        if d == 0.0:
+            assert ns == 0
+    # the layout of one sweep point against the oracle (same alpha/delta, block size 16)
+    rr = O.row_reorder(S, 0.5, 16)
+    cr = O.col_reorder(S, rr["reorderedRows"], 0.3)
+    assert seen[(64, 0.5, 0.3)][1] == int(cr["sparseValueOffsets"][-1])
+    # the reference's analyser reads the 140 files
+    r = subprocess.run([ana] + [str(logdir / n) for n in logs], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-400:]
+    for k in (32, 64, 128, 256):
+        csv = [l for l in open(logdir / f"results_{k}.csv").read().splitlines() if l]
+        assert csv[0].startswith("file,M,N,NNZ,Sparsity,K,BSMR")
+        row = csv[1].split(",")
+        assert row[0] == mtx and int(row[3]) == S.nnz and int(row[5]) == k and float(row[6]) > 0

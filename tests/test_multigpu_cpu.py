@@ -1,6 +1,8 @@
-"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: row-order broadcast, nnz-balanced panel
-shards, B replication, and the disjoint-merge of P.  Each rank's share of P is produced by the oracle
-here (test infrastructure) -- the product kernels are covered by the -m gpu tests."""
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: the out-of-band exchange of the library's NCCL
+communicator id (multigpu.exchange_unique_id), nnz-balanced panel shards (bsmr_shard_plan: the rule
+sddmm_mgpu_shard applies on the device), and the disjoint-merge property sddmm_mgpu_gather relies on.  Each rank's
+share of P is produced by the oracle here (test infrastructure); the product kernels and the NCCL calls themselves
+run in the -m gpu tests and under bench.py --gpus N."""
 import os
 import socket
 import sys
@@ -37,13 +39,30 @@ def _worker(rank, world, port, q):
         S = gen.rmat(11, 8, 6)
         K = 32
         A, B = gen.dense_operands(S.M, S.N, K)
+        # the 128-byte communicator id is made on rank 0 (ncclGetUniqueId needs no GPU) and reaches every rank
+        ident = mg.exchange_unique_id()
+        assert len(ident) == mg.ID_BYTES and any(ident)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, ident)
+        assert all(g == gathered[0] for g in gathered)
+        # there is no CPU fallback behind the communicator either
+        with pytest.raises(pkg.SddmmError):
+            mg.MultiGpu(rank, world, ident)
         # rank 0 owns the row order (here from the oracle) and B; both are replicated once
-        R = O.row_reorder(S, 0.3, 16)["reorderedRows"] if rank == 0 else None
-        R = mg.broadcast_row_order(R, S.M, src=0)
+        Rt = torch.zeros(S.M, dtype=torch.int32)
+        n = torch.zeros(1, dtype=torch.int64)
+        if rank == 0:
+            R0 = O.row_reorder(S, 0.3, 16)["reorderedRows"]
+            Rt[: len(R0)] = torch.from_numpy(R0.view(np.int32))
+            n[0] = len(R0)
+        dist.broadcast(n, src=0)
+        dist.broadcast(Rt, src=0)
+        R = Rt[: int(n)].numpy().view(np.uint32)
         Bt = torch.from_numpy(B.copy()) if rank == 0 else torch.zeros((S.N, K))
-        mg.replicate_B(Bt, src=0)
+        dist.broadcast(Bt, src=0)
         assert np.array_equal(Bt.numpy(), B)
-        p0, p1, cuts = mg.my_panel_range(S, R)
+        cuts = pkg.shard_plan(S, R, world)
+        p0, p1 = int(cuts[rank]), int(cuts[rank + 1])
         assert cuts[0] == 0 and cuts[-1] == (len(R) + 15) // 16
         rows = R[p0 * 16: min(p1 * 16, len(R))]
         # this rank's disjoint share of P
@@ -54,7 +73,7 @@ def _worker(rank, world, port, q):
             mine[b:e] = Pfull[b:e]
         nnz_mine = int(sum(int(S.row_off[r + 1]) - int(S.row_off[r]) for r in rows))
         Pt = torch.from_numpy(mine)
-        mg.merge_P(Pt)
+        dist.all_reduce(Pt)  # disjoint pieces, zeros elsewhere: the sum IS the merge (sddmm_mgpu_gather)
         ok = np.array_equal(Pt.numpy(), Pfull)
         q.put((rank, ok, nnz_mine, S.nnz, [int(c) for c in cuts]))
     finally:

@@ -28,6 +28,10 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--rebuild", action="store_true", help="build the layout twice and print both timings")
     ap.add_argument("--Ks", default="", help="comma list: sweep K on one layout, one JSON line per K")
+    ap.add_argument("--plan", default="auto"); ap.add_argument("--dense", default="auto")
+    ap.add_argument("--residual", default="auto"); ap.add_argument("--tile", default="auto")
+    ap.add_argument("--stages", type=int, default=0); ap.add_argument("--tiles", default="auto")
+    ap.add_argument("--host-gen", action="store_true", help="R-MAT from the host generator (tests' matrices)")
     a = ap.parse_args()
     import torch
     pkg = load_package()
@@ -40,19 +44,30 @@ def main():
         S = gen.bernoulli_mask(4096, 4096, a.sparsity, 30)
     elif a.workload == "dlmc4096":
         S = gen.dlmc_magnitude_mask(4096, 4096, a.sparsity, 33)
-    elif a.workload == "rmat":
+    elif a.workload == "rmat" and a.host_gen:
         S = gen.rmat(a.scale, 16, 4)
+    elif a.workload == "rmat":
+        import types
+        ro, ci, M = gen.rmat_device(a.scale, 16, 4)
+        S = types.SimpleNamespace(M=M, N=M, nnz=int(ci.numel()), row_off=ro.cpu().numpy().view(np.uint32),
+                                  col_idx=None)
+    elif a.workload == "blockscat":
+        S = gen.block_structured_scattered(16384, 16384, 64, 512, 0.6, 41, noise=0.0005)
     else:
         raise SystemExit("unknown workload")
-    ro = torch.from_numpy(S.row_off.view(np.int32)).cuda()
-    ci = torch.from_numpy(S.col_idx.view(np.int32)).cuda()
+    if a.workload != "rmat" or a.host_gen:
+        ro = torch.from_numpy(S.row_off.view(np.int32)).cuda()
+        ci = torch.from_numpy(S.col_idx.view(np.int32)).cuda()
+    a.ci = ci
+    a.plan_obj = pkg.make_plan(a.plan, a.dense, a.residual, a.tile, a.stages)
     if a.reorder:
-        R, ncl, row_ms = pkg.row_reorder_dev(ro, ci, S.M, S.N, a.alpha, 0)
+        bs = pkg.calculateBlockSize(S, 180 * 10 ** 9)
+        R, ncl, row_ms = pkg.row_reorder_dev(ro, ci, S.M, S.N, a.alpha, bs)
     else:
         lens = np.diff(S.row_off.astype(np.int64))
         R = torch.from_numpy(np.nonzero(lens)[0].astype(np.int32)).cuda()
         ncl, row_ms = -1, 0.0
-    lay, col_ms, rphm_ms = pkg.layout_build_dev(ro, ci, S.M, S.N, R, a.delta)
+    lay, col_ms, rphm_ms = pkg.layout_build_dev(ro, ci, S.M, S.N, R, a.delta, tiles=a.tiles)
     if a.rebuild:  # second build in the same process: scratch pool already grown
         del lay
         lay, col2, rphm2 = pkg.layout_build_dev(ro, ci, S.M, S.N, R, a.delta)
@@ -67,11 +82,25 @@ def run_k(a, torch, pkg, gen, S, lay, K, ncl, row_ms, col_ms, rphm_ms):
     dA = torch.rand((S.M, K), device="cuda", generator=g) * 2  # U[0,2) like Matrix::makeData
     dB = torch.rand((S.N, K), device="cuda", generator=g) * 2
     dP = torch.zeros(max(1, S.nnz), dtype=torch.float32, device="cuda")
-    t = pkg.sddmm_gpu_timed(dA, dB, lay, dP, warmup=3, iters=a.iters)
+    names = pkg.plan_resolve(lay, K, 1, a.plan_obj)
+    if (a.plan, a.dense, a.residual, a.tile) == ("auto",) * 4:
+        t = pkg.sddmm_gpu_timed(dA, dB, lay, dP, warmup=3, iters=a.iters)
+    else:  # forced kernels: time whole passes with events on the current stream
+        pkg.sddmm_prepare(lay, K, 1, a.plan_obj)
+        for _ in range(3):
+            pkg.sddmm_gpu(dA, dB, lay, dP, plan=a.plan_obj)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.iters):
+            pkg.sddmm_gpu(dA, dB, lay, dP, plan=a.plan_obj)
+        e1.record()
+        torch.cuda.synchronize()
+        t = dict(dense_ms=0.0, sparse_ms=0.0, total_ms=e0.elapsed_time(e1) / a.iters)
     i = lay.info
     out = dict(workload=a.workload, M=S.M, N=S.N, nnz=S.nnz, K=K, delta=a.delta, dense_blocks=int(i.numDenseBlocks),
                dense_nnz=int(i.numDenseValues), residual_nnz=int(i.numSparseValues), row_ms=row_ms, clusters=ncl,
-               col_ms=col_ms, rphm_ms=rphm_ms, **t)
+               col_ms=col_ms, rphm_ms=rphm_ms, kernels=names, **t)
     out["gflops_total"] = 2.0 * S.nnz * K / (t["total_ms"] * 1e-3) / 1e9
     if t["sparse_ms"] > 0:
         out["residual_gflops"] = 2.0 * i.numSparseValues * K / (t["sparse_ms"] * 1e-3) / 1e9
@@ -81,7 +110,7 @@ def run_k(a, torch, pkg, gen, S, lay, K, ncl, row_ms, col_ms, rphm_ms):
     if a.check:  # sampled rows against fp64 on the device
         torch.cuda.synchronize()
         rows = np.random.default_rng(0).choice(S.M, 32, replace=False)
-        ci = torch.from_numpy(S.col_idx.view(np.int32)).cuda()
+        ci = a.ci
         worst = 0.0
         for r in rows:
             b, e = int(S.row_off[r]), int(S.row_off[r + 1])
