@@ -229,8 +229,9 @@ def run_reference(args, w):
     K = args.K or w["K"]
     ro, ci, M, N, A, B = host_pattern_for(args, w)
     nnz = int(ro[-1])
-    # bounded sample: ~2 s of CPU work per step
-    sample_rows = min(M, max(256, int(M * min(1.0, 2e10 / max(1.0, 2.0 * nnz * K)))))
+    # bounded sample: a few seconds of CPU work per step (gather-bound graphs run at ~1.5 GFLOP/s on 16 cores,
+    # L2-friendly uniform matrices at ~8)
+    sample_rows = min(M, max(256, int(M * min(1.0, (4e9 if w["kind"] == "rmat" else 2e10) / max(1.0, 2.0 * nnz * K)))))
     vals = []
     for i in range(args.warmup + args.steps):
         r = cpu_reference_gflops(ro, ci, M, N, A, B, K, sample_rows, repeats=1)
@@ -718,7 +719,7 @@ def main():
     ap.add_argument("--delta", type=float, default=0.3)
     ap.add_argument("--rows", type=int, default=0, help="debug: override the row count of a uniform workload")
     ap.add_argument("--scale", type=int, default=0, help="R-MAT scale override")
-    ap.add_argument("--cpu-gflop", type=float, default=60.0, help="GFLOP of work in the bounded cpu_baseline sample")
+    ap.add_argument("--cpu-gflop", type=float, default=8.0, help="GFLOP of work in the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="headline record only")
     ap.add_argument("--cfg5", type=int, default=1, help="also run config 5 (R-MAT scale 25, K=256) at this N")

@@ -224,14 +224,17 @@ int sddmm_run_dev(const bsmr_layout*, uint32_t K, const float* d_A, const float*
  *   dense    REG   = k_sddmm_dense      (operands staged through registers, cvt.rna.tf32 on the way)
  *            TMA   = k_sddmm_dense_tma  (TMA tile::gather4 of the denseCols rows from TF32-rounded copies)
  *   residual PANEL = k_sddmm_residual   (one 16-row panel per CTA; any K % 4 == 0)
- *            SUPERPANEL = k_sddmm_residual_sp (K in {32, 64, 128, 256, 512})
+ *            SUPERPANEL = k_sddmm_residual_sp (K in {32, 64, 128, 256, 512}; A rows of 16*G panels in shared
+ *                         memory, B^T rows reused from registers along column runs: masks, uniform matrices)
+ *            STREAM = k_sddmm_residual_stream (same K; entries in row order, A fragment in registers, up to 8
+ *                         gathered B^T rows in flight per lane, L2 eviction hints: graphs, where B >> L2)
  *   tile     REG / TMA / TMA_CLUSTER = k_sddmm_tile / k_sddmm_tile_tma / k_sddmm_tile_tma4
  * AUTO everywhere = the library's cost model (the defaults of sddmm_run_dev).  A choice that cannot serve the
  * call (SUPERPANEL with K = 36, TILE on a layout built with BSMR_BUILD_TILES_NEVER ...) fails with
  * SDDMM_E_UNSUPPORTED instead of silently running something else. */
 enum { SDDMM_PLAN_AUTO = 0, SDDMM_PLAN_BSMR = 1, SDDMM_PLAN_TILE = 2 };
 enum { SDDMM_DENSE_AUTO = 0, SDDMM_DENSE_REG = 1, SDDMM_DENSE_TMA = 2 };
-enum { SDDMM_RESIDUAL_AUTO = 0, SDDMM_RESIDUAL_PANEL = 1, SDDMM_RESIDUAL_SUPERPANEL = 2 };
+enum { SDDMM_RESIDUAL_AUTO = 0, SDDMM_RESIDUAL_PANEL = 1, SDDMM_RESIDUAL_SUPERPANEL = 2, SDDMM_RESIDUAL_STREAM = 3 };
 enum { SDDMM_TILE_AUTO = 0, SDDMM_TILE_REG = 1, SDDMM_TILE_TMA = 2, SDDMM_TILE_TMA_CLUSTER = 3 };
 typedef struct {
   uint32_t plan, dense, residual, tile;

@@ -16,7 +16,11 @@ struct Logger {
   int numRowPanels_ = 0, numDenseBlock_ = 0, numDenseThreadBlocks_ = 0, numSparseThreadBlocks_ = 0;
   int originalNumDenseBlock_ = 0;
   float originalAverageDensity_ = 0.f, errorRate_ = 0.f;
-  unsigned blockDimDense_ = 128, blockDimSparse_ = 1024;
+  // scripts/analyze_results.cpp treats blockDim_dense / blockDim_sparse as SETTINGS that must be identical in every
+  // record it reads (in the reference they are compile-time constants).  They are logged as the constant base CTA
+  // sizes of the dense-block and residual kernels; the CTA size the residual kernel picked for this K goes under
+  // the B200-only key b200_residual_cta.
+  unsigned blockDimDense_ = 128, blockDimSparse_ = 256, residualCta_ = 256;
   unsigned numDenseData_ = 0, numSparseData_ = 0;
   int numITER_ = 10, numClusters_ = 1;
   float alpha_ = 0.3f, delta_ = 0.3f, averageDensity_ = 0.f;
@@ -71,5 +75,6 @@ struct Logger {
     out << "[b200_rphm_build : " << rphmTime_ << "]\n";
     out << "[b200_dense_kernel_ms : " << denseTime_ << "]\n";
     out << "[b200_residual_kernel_ms : " << sparseTime_ << "]\n";
+    out << "[b200_residual_cta : " << residualCta_ << "]\n";
   }
 };

@@ -113,7 +113,9 @@ void sddmm_gpu(UIN, UIN, UIN K, const float* dA, const float* dB, const RPHM& rp
                               &t), "sddmm_run_timed_dev"))
     return;
   logger.sddmmTime_ = t;
-  logger.blockDimSparse_ = (K % 32u == 0 && K >= 256u && K <= 512u) ? 512u : (K % 32u == 0 && K <= 512u) ? 1024u : 256u;
+  sddmm_plan resolved{};
+  if (sddmm_plan_resolve(rphm.layout().get(), K, 1, nullptr, &resolved) == SDDMM_OK)
+    logger.residualCta_ = resolved.residual == SDDMM_RESIDUAL_SUPERPANEL ? (K >= 256u ? 512u : 1024u) : 256u;
   logger.denseTime_ = d;
   logger.sparseTime_ = s;
 }

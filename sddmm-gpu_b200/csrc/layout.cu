@@ -745,6 +745,68 @@ const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStre
   return (L->sp[G] = std::move(sp)).get();
 }
 
+// ---- row-stream residual layout (K7c): residual entries sorted by (reordered row position, column)
+namespace {
+__global__ void __launch_bounds__(256) k_st_keys(const u32* __restrict__ vOff, const u32* __restrict__ sCols,
+                                                 const u32* __restrict__ sRows, u32 P, int colBits,
+                                                 u64* __restrict__ keys, u32* __restrict__ vals) {
+  const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const u32 nw = (gridDim.x * blockDim.x) >> 5;
+  for (u32 p = gw; p < P; p += nw) {
+    const u32 b = vOff[p], e = vOff[p + 1];
+    for (u32 i = b + lane; i < e; i += 32) {
+      keys[i] = ((u64)(p * 16u + sRows[i]) << colBits) | sCols[i];
+      vals[i] = i;
+    }
+  }
+}
+__global__ void k_st_unpack(const u64* __restrict__ keys, const u32* __restrict__ vals, const u32* __restrict__ sVals,
+                            const u32* __restrict__ R, size_t n, int colBits, u32* __restrict__ row,
+                            u32* __restrict__ col, u32* __restrict__ idx) {
+  const u64 colMask = (((u64)1) << colBits) - 1;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const u64 k = keys[i];
+    row[i] = R[(u32)(k >> colBits)];
+    col[i] = (u32)(k & colMask);
+    idx[i] = sVals[vals[i]];
+  }
+}
+}  // namespace
+
+const StreamLayout* ensure_stream(const bsmr_layout* L, cudaStream_t s) {
+  if (L->st) return L->st.get();
+  TempScope tempScope(s);
+  const bsmr_layout_info& I = L->info;
+  auto st = std::make_unique<StreamLayout>();
+  const u32 n = I.numSparseValues, P = I.numRowPanels;
+  st->numEntries = n;
+  // 32 slack entries: the kernel reads metadata in whole 32-entry batches
+  st->row.alloc((size_t)n + 32, true);
+  st->col.alloc((size_t)n + 32, true);
+  st->idx.alloc((size_t)n + 32, true);
+  SB_CUDA(cudaMemsetAsync(st->row.get() + n, 0, 32 * 4, s));
+  SB_CUDA(cudaMemsetAsync(st->col.get() + n, 0, 32 * 4, s));
+  SB_CUDA(cudaMemsetAsync(st->idx.get() + n, 0, 32 * 4, s));
+  if (n && P) {
+    const int colBits = bits_for(I.N), rowBits = bits_for((u64)P * 16u);
+    DevBuf<u64> kA(n), kB(n);
+    DevBuf<u32> vA(n), vB(n);
+    k_st_keys<<<grid_for((size_t)P * 32), 256, 0, s>>>(L->arr[BSMR_SPARSE_VALUE_OFFSETS].get(),
+                                                      L->arr[RPHM_SPARSE_COL_INDICES].get(),
+                                                      L->arr[RPHM_SPARSE_RELATIVE_ROWS].get(), P, colBits, kA.get(),
+                                                      vA.get());
+    SB_LAUNCH_CHECK();
+    const int w = radix_sort_pairs<u64>(kA.get(), kB.get(), vA.get(), vB.get(), n, 0, colBits + rowBits, s);
+    k_st_unpack<<<grid_for(n), 256, 0, s>>>(w ? kB.get() : kA.get(), w ? vB.get() : vA.get(),
+                                           L->arr[RPHM_SPARSE_VALUES].get(), L->arr[BSMR_REORDERED_ROWS].get(), n,
+                                           colBits, st->row.get(), st->col.get(), st->idx.get());
+    SB_LAUNCH_CHECK();
+  }
+  SB_CUDA(cudaStreamSynchronize(s));
+  L->st = std::move(st);
+  return L->st.get();
+}
+
 // ---- on-disk layout cache: reordering costs orders of magnitude more than one SDDMM pass,
 // so a deployment keeps the layout keyed by (matrix, alpha, delta, block_size).  Versioned little-endian file:
 //   "BSMRLAY1" | u32 version | bsmr_layout_info | u32 sparseChunk | u32 numDenseWork | u32 numSparseWork |

@@ -19,6 +19,17 @@ struct SuperPanelLayout {
 }  // namespace sb
 
 namespace sb {
+// Private residual layout of the row-stream kernel (K7c): the residual entries in reordered-ROW order (then
+// column), so that the entries of one row are consecutive and its A fragment stays in registers.
+struct StreamLayout {
+  u32 numEntries = 0;
+  DevBuf<u32> row;  // per entry: ORIGINAL row id (index into A)
+  DevBuf<u32> col;  // per entry: column (index into B^T)
+  DevBuf<u32> idx;  // per entry: CSR index (index into P)
+};
+}  // namespace sb
+
+namespace sb {
 // Private layout of the "full tile" plan (K8): the reordered matrix is cut into 128-row x 128-column tiles
 // (rows in BSMR order, columns in natural order); every non-empty tile is one tcgen05 GEMM tile whose
 // epilogue picks the stored entries with per-row bitmasks.  Used when S is dense enough that computing
@@ -83,6 +94,7 @@ struct bsmr_layout {
   };
   mutable std::map<sb::u64, std::unique_ptr<DenseTma>> dtma;            // key = K << 32 | numBatch
   mutable std::map<sb::u32, std::unique_ptr<sb::SuperPanelLayout>> sp;  // key = G (panels per super-panel)
+  mutable std::unique_ptr<sb::StreamLayout> st;                         // K-independent, built on first use
   std::unique_ptr<sb::TileLayout> tl;                // built with the layout when S is dense enough to consider it
   // two-slot pipeline of sddmm_run_host_async
   struct HostPipe {
@@ -117,5 +129,7 @@ bsmr_layout* layout_load(const char* path);
 
 // builds (once, then cached) the super-panel layout for G panels per super-panel; returns it
 const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStream_t s);
+// builds (once) the row-ordered residual layout of the row-stream kernel
+const StreamLayout* ensure_stream(const bsmr_layout* L, cudaStream_t s);
 
 }  // namespace sb

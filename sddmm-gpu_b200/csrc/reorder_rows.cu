@@ -188,6 +188,24 @@ static __global__ void __launch_bounds__(256) k_encode_fill(const u32* __restric
   }
 }
 
+// Bitmap signatures of the sparse encodings: bit (block & sigMask) of row `pos` is set for every kept block.
+// With 32*W >= nbpr the map is the identity (an exact bitmap), otherwise a folding hash.  Used by the batched
+// clustering kernel to bound the similarity from above without reading a candidate's entry list (see
+// cb_sig_bound).  One warp per position; the signature array is zeroed beforehand.
+static __global__ void __launch_bounds__(256) k_build_sig(const uint2* __restrict__ enc, const uint4* __restrict__ meta,
+                                                          u32 M, u32 W, u32 sigMask, u32* __restrict__ sig) {
+  const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const u32 nw = (gridDim.x * blockDim.x) >> 5;
+  for (u32 pos = gw; pos < M; pos += nw) {
+    const uint4 m = meta[pos];
+    u32* out = sig + (size_t)pos * W;
+    for (u32 j = lane; j < m.y; j += 32) {
+      const u32 bit = enc[m.x + j].x & sigMask;
+      atomicOr(out + (bit >> 5), 1u << (bit & 31u));
+    }
+  }
+}
+
 static __global__ void k_gather_u32(const u32* __restrict__ src, const u32* __restrict__ idx, u32* __restrict__ dst,
                                     size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -419,8 +437,26 @@ struct ClusterBatchArgs {
   unsigned long long* slots;  // [3] earliest (pos << 8 | cluster-in-batch) that joins, per rotating window
   u32* accepts;               // [3] number of accepting candidates seen in the window (same rotation)
   u32* seeds;                 // [0] count, [1..8] positions of the next batch's seeds (written by block 0)
-  u32* stats;                 // [0] exact evaluations, [1] clusters created, [2] windows, [3] batches
+  u32* stats;                 // [0] exact evaluations, [1] clusters created, [2] windows, [3] batches,
+                              // [4] lane-path redo rows, [5] candidates rejected by the signature bound
+  const u32* sig;             // [M][W] bitmap signatures by position (nullptr / W == 0: filter off)
+  u32 W, sigMask;
+  float sigThr;               // reject when the upper bound of sim stays below this (alpha - tol, > 0)
 };
+
+// ---- signature upper bound -------------------------------------------------------------------------------
+// With a_i = ca_i / |a| and b_i = cb_i / |b| over the kept blocks:   sum_i min(a_i, b_i) <= sum_{i shared} b_i
+// = (sum_{i shared} cb_i) / |b|, and sum_{i shared} cb_i <= sh + (s1_b - popc(sig_b)), where sh = popc(sig_a & sig_b)
+// counts the shared signature bits and the second term is the total count excess of b over one per set bit
+// (valid for a folding hash too: a shared block always lands on a shared bit).  Symmetrically for a.  Since
+// sim = smin / (S_a + S_b - smin) grows with smin, the bound on smin bounds sim.  The caller compares with
+// alpha - tol, the same margin the estimate path uses, so a rejection here is a rejection there.
+__device__ __forceinline__ bool cb_sig_may_join(float sh, float exRep, float nRepInv, float Sa, float exCmp,
+                                                float nCmpInv, float Sb, float thr) {
+  const float ub = fminf((sh + exRep) * nRepInv, (sh + exCmp) * nCmpInv);
+  const float den = Sa + Sb - ub;
+  return !(den > 0.f && (ub / den) * 1.0001f < thr);
+}
 
 // block 0 only: the next (up to G) unclustered positions at or after `from`, in order
 __device__ void cb_find_seeds(const ClusterBatchArgs& a, u32 from, u32* sCount) {
@@ -457,10 +493,20 @@ __device__ void cb_find_seeds(const ClusterBatchArgs& a, u32 from, u32* sCount) 
 
 // applies "row at position f joins cluster jk": rep_jk += hist(f), sum of squares updated exactly in uint32
 template <int TG>
-__device__ __forceinline__ void cb_apply_join(const ClusterBatchArgs& a, u32* rep, u32* sSs, u32* sS1, u32* sRed,
-                                              u32 f, u32 jk) {
+__device__ __forceinline__ void cb_apply_join(const ClusterBatchArgs& a, u32* rep, u32* repSig, u32* sPop, u32* sSs,
+                                              u32* sS1, u32* sRed, u32 f, u32 jk) {
   const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint4 m = a.meta[f];
+  if (a.W) {  // signature of the representative = OR of its members'
+    u32 added = 0;
+    for (u32 w = threadIdx.x; w < a.W; w += kCbThreads) {
+      const u32 x = a.sig[(size_t)f * a.W + w], old = repSig[w * TG + jk];
+      added += __popc(x & ~old);
+      repSig[w * TG + jk] = old | x;
+    }
+    added = __reduce_add_sync(0xffffffffu, added);
+    if (lane == 0 && added) atomicAdd(sPop + jk, added);
+  }
   u32 dss = 0;
   u32* rk = rep + jk;
   for (u32 j = threadIdx.x; j < m.y; j += kCbThreads) {
@@ -487,12 +533,51 @@ __device__ __forceinline__ void cb_apply_join(const ClusterBatchArgs& a, u32* re
 // lanes).  Returns the cluster it joins (warp-uniform) or kNull.  Clusters are tried in order; the estimate
 // decides unless it is within `tol` of alpha, then the literal reduction tree does.
 template <int TG>
-__device__ __forceinline__ u32 cb_eval_row_warp(const ClusterBatchArgs& a, const u32* rep, const u32* sSs,
-                                                const float (&nRepInv)[TG], const float (&Sa)[TG], const uint4 m,
-                                                const u32 kmax, const float tol, const u32 lane) {
+__device__ __forceinline__ u32 cb_eval_row_warp(const ClusterBatchArgs& a, const u32* rep, const u32* repSig,
+                                                const u32* sPop, const u32* sSs, const u32* sS1,
+                                                const float (&nRepInv)[TG], const float (&Sa)[TG], const u32 pos,
+                                                const uint4 m, const u32 kmax, const float tol, const u32 lane) {
   const uint2* ent = a.enc + m.x;
   const u32 ssCmp = m.z;
   const float nCmpInv = ssCmp ? 1.0f / sqrtf((float)ssCmp) : 0.f;
+  if (a.W && ssCmp && m.y * 2u > a.W) {  // reading the signature is cheaper than reading the entries
+    u32 sh[TG], popB = 0;
+#pragma unroll
+    for (int k = 0; k < TG; ++k) sh[k] = 0;
+    const u32* sg = a.sig + (size_t)pos * a.W;
+    for (u32 w = lane; w < a.W; w += 32) {
+      const u32 x = sg[w];
+      popB += __popc(x);
+      u32 rs[TG];
+      if constexpr (TG >= 4) {
+#pragma unroll
+        for (int q = 0; q < TG / 4; ++q) {
+          const uint4 v4 = *reinterpret_cast<const uint4*>(repSig + (size_t)w * TG + q * 4);
+          rs[q * 4 + 0] = v4.x; rs[q * 4 + 1] = v4.y; rs[q * 4 + 2] = v4.z; rs[q * 4 + 3] = v4.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < TG; ++k) rs[k] = repSig[(size_t)w * TG + k];
+      }
+#pragma unroll
+      for (int k = 0; k < TG; ++k) sh[k] += __popc(x & rs[k]);
+    }
+    popB = __reduce_add_sync(0xffffffffu, popB);
+    const float exCmp = (float)(m.w - popB), Sb = (float)m.w * nCmpInv;
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < TG; ++k) {
+      if ((u32)k < kmax) {
+        const u32 shk = __reduce_add_sync(0xffffffffu, sh[k]);
+        any = any || sSs[k] == 0 ||
+              cb_sig_may_join((float)shk, (float)(sS1[k] - sPop[k]), nRepInv[k], Sa[k], exCmp, nCmpInv, Sb, a.sigThr);
+      }
+    }
+    if (!any) {
+      if (lane == 0) atomicAdd(a.stats + 5, 1u);
+      return kNull;
+    }
+  }
   float mn[TG];
 #pragma unroll
   for (int k = 0; k < TG; ++k) mn[k] = 0.f;
@@ -560,12 +645,48 @@ __device__ __forceinline__ u32 cb_eval_row_warp(const ClusterBatchArgs& a, const
 // The same decision for a SHORT row by one lane on its own (no shuffles).  If any cluster that has to be
 // decided is ambiguous the lane gives up (*again = true) and the row is redone by cb_eval_row_warp.
 template <int TG>
-__device__ __forceinline__ u32 cb_eval_row_lane(const ClusterBatchArgs& a, const u32* rep, const u32* sSs,
-                                                const float (&nRepInv)[TG], const float (&Sa)[TG], const uint4 m,
-                                                const u32 kmax, const float tol, bool* again) {
+__device__ __forceinline__ u32 cb_eval_row_lane(const ClusterBatchArgs& a, const u32* rep, const u32* repSig,
+                                                const u32* sPop, const u32* sSs, const u32* sS1,
+                                                const float (&nRepInv)[TG], const float (&Sa)[TG], const u32 pos,
+                                                const uint4 m, const u32 kmax, const float tol, bool* again) {
   const uint2* ent = a.enc + m.x;
   const u32 ssCmp = m.z;
   const float nCmpInv = ssCmp ? 1.0f / sqrtf((float)ssCmp) : 0.f;
+  *again = false;
+  if (a.W && ssCmp && m.y * 2u > a.W) {
+    u32 sh[TG], popB = 0;
+#pragma unroll
+    for (int k = 0; k < TG; ++k) sh[k] = 0;
+    const u32* sg = a.sig + (size_t)pos * a.W;
+    for (u32 w = 0; w < a.W; ++w) {
+      const u32 x = sg[w];
+      popB += __popc(x);
+      u32 rs[TG];
+      if constexpr (TG >= 4) {
+#pragma unroll
+        for (int q = 0; q < TG / 4; ++q) {
+          const uint4 v4 = *reinterpret_cast<const uint4*>(repSig + (size_t)w * TG + q * 4);
+          rs[q * 4 + 0] = v4.x; rs[q * 4 + 1] = v4.y; rs[q * 4 + 2] = v4.z; rs[q * 4 + 3] = v4.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < TG; ++k) rs[k] = repSig[(size_t)w * TG + k];
+      }
+#pragma unroll
+      for (int k = 0; k < TG; ++k) sh[k] += __popc(x & rs[k]);
+    }
+    const float exCmp = (float)(m.w - popB), Sb = (float)m.w * nCmpInv;
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < TG; ++k)
+      if ((u32)k < kmax)
+        any = any || sSs[k] == 0 ||
+              cb_sig_may_join((float)sh[k], (float)(sS1[k] - sPop[k]), nRepInv[k], Sa[k], exCmp, nCmpInv, Sb, a.sigThr);
+    if (!any) {
+      atomicAdd(a.stats + 5, 1u);
+      return kNull;
+    }
+  }
   float mn[TG];
 #pragma unroll
   for (int k = 0; k < TG; ++k) mn[k] = 0.f;
@@ -595,7 +716,6 @@ __device__ __forceinline__ u32 cb_eval_row_lane(const ClusterBatchArgs& a, const
     }
   }
   u32 joinK = kNull;
-  *again = false;
 #pragma unroll
   for (int k = 0; k < TG; ++k) {
     if ((u32)k < kmax && joinK == kNull && !*again) {
@@ -615,8 +735,9 @@ __device__ __forceinline__ u32 cb_eval_row_lane(const ClusterBatchArgs& a, const
 
 template <int TG>  // representatives interleaved: rep[block * TG + k], so one lookup serves all TG clusters
 static __global__ void __launch_bounds__(kCbThreads, 1) k_cluster_batched(ClusterBatchArgs a) {
-  extern __shared__ __align__(16) u32 rep[];  // nbpr x TG accumulated histograms
-  __shared__ u32 sSeed[kCbMaxG], sSs[kCbMaxG], sS1[kCbMaxG];
+  extern __shared__ __align__(16) u32 rep[];  // nbpr x TG accumulated histograms, then W x TG signature words
+  u32* repSig = rep + (((size_t)TG * a.nbpr + 3u) & ~(size_t)3u);
+  __shared__ u32 sSeed[kCbMaxG], sSs[kCbMaxG], sS1[kCbMaxG], sPop[kCbMaxG];
   __shared__ u32 sRed[kCbWarps];
   __shared__ u32 sCount;
   __shared__ u32 sTodo[kCbThreads], sTodoCnt;
@@ -646,8 +767,16 @@ static __global__ void __launch_bounds__(kCbThreads, 1) k_cluster_batched(Cluste
       sSs[threadIdx.x] = m.z;
       sS1[threadIdx.x] = m.w;
     }
+    if (threadIdx.x < kCbMaxG) sPop[threadIdx.x] = 0;
     for (u32 i = threadIdx.x; i < (u32)TG * a.nbpr; i += kCbThreads) rep[i] = 0;
+    for (u32 i = threadIdx.x; i < (u32)TG * a.W; i += kCbThreads) repSig[i] = 0;
     __syncthreads();
+    for (u32 i = threadIdx.x; i < g * a.W; i += kCbThreads) {
+      const u32 k = i / a.W, w = i - k * a.W;
+      const u32 x = a.sig[(size_t)sSeed[k] * a.W + w];
+      repSig[w * TG + k] = x;
+      if (x) atomicAdd(sPop + k, (u32)__popc(x));
+    }
     for (u32 k = 0; k < g; ++k) {
       const uint4 m = a.meta[sSeed[k]];
       for (u32 j = threadIdx.x; j < m.y; j += kCbThreads) {
@@ -693,7 +822,8 @@ static __global__ void __launch_bounds__(kCbThreads, 1) k_cluster_batched(Cluste
           u32 joinK = kNull;
           bool again = false;
           if (kmax) {
-            if (m.y <= a.laneRows) joinK = cb_eval_row_lane<TG>(a, rep, sSs, nRepInv, Sa, m, kmax, tol, &again);
+            if (m.y <= a.laneRows)
+              joinK = cb_eval_row_lane<TG>(a, rep, repSig, sPop, sSs, sS1, nRepInv, Sa, pos, m, kmax, tol, &again);
             else again = true;
           }
           if (again) {
@@ -713,7 +843,7 @@ static __global__ void __launch_bounds__(kCbThreads, 1) k_cluster_batched(Cluste
             u32 ks = 0;
 #pragma unroll
             for (int k = 0; k < TG; ++k) ks += ((u32)k < g && sSeed[k] < tp) ? 1u : 0u;
-            const u32 jk = cb_eval_row_warp<TG>(a, rep, sSs, nRepInv, Sa, a.meta[tp], ks, tol, lane);
+            const u32 jk = cb_eval_row_warp<TG>(a, rep, repSig, sPop, sSs, sS1, nRepInv, Sa, tp, a.meta[tp], ks, tol, lane);
             if (jk != kNull && lane == 0) {
               atomicMin(a.slots + slot, ((unsigned long long)tp << 8) | (unsigned long long)jk);
               atomicAdd(a.accepts + slot, 1u);
@@ -731,7 +861,7 @@ static __global__ void __launch_bounds__(kCbThreads, 1) k_cluster_batched(Cluste
           for (int k = 0; k < TG; ++k) kmax += ((u32)k < g && sSeed[k] < pos) ? 1u : 0u;
           if (kmax == 0) continue;
           const uint4 m = a.meta[pos];
-          const u32 joinK = cb_eval_row_warp<TG>(a, rep, sSs, nRepInv, Sa, m, kmax, tol, lane);
+          const u32 joinK = cb_eval_row_warp<TG>(a, rep, repSig, sPop, sSs, sS1, nRepInv, Sa, pos, m, kmax, tol, lane);
           if (joinK != kNull && lane == 0) {
             atomicMin(a.slots + slot, ((unsigned long long)pos << 8) | (unsigned long long)joinK);
             atomicAdd(a.accepts + slot, 1u);
@@ -762,7 +892,7 @@ static __global__ void __launch_bounds__(kCbThreads, 1) k_cluster_batched(Cluste
         for (u32 j = 1; j < g; ++j)
           if (sSeed[j] == f) newG = j;
         if (blockIdx.x == 0 && threadIdx.x == 0) a.cid[f] = c0 + jk;
-        cb_apply_join<TG>(a, rep, sSs, sS1, sRed, f, jk);
+        cb_apply_join<TG>(a, rep, repSig, sPop, sSs, sS1, sRed, f, jk);
         g = newG;
         p = f + 1;
         // rows tend to join in streaks and only the first joiner of a window counts: look at a few
@@ -930,14 +1060,37 @@ void row_reorder_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32
       a.laneRows = laneCfg == 0 ? 0u : laneCfg > 0 ? (u32)laneCfg : (avgEnt <= 24.0 ? 64u : 0u);
     }
     SB_CUDA(cudaMemsetAsync(acceptsBuf.get(), 0, 16, s));
-    u32 G = (u32)((200u * 1024u) / ((size_t)nbpr * 4));
+    // bitmap signatures (see cb_sig_may_join): ~8 bits per average kept entry, a power of two; an exact bitmap when
+    // that covers nbpr.  Off when alpha - tol <= 0 (nothing can be rejected) or by option.
+    DevBuf<u32> sigBuf;
+    a.sig = nullptr; a.W = 0; a.sigMask = 0xFFFFFFFFu;
+    a.sigThr = alpha - (kTolRel * fabsf(alpha) + kTolAbs);
+    {
+      int sigCfg = -1;
+      if (o.signature == BSMR_TRISTATE_OFF) sigCfg = 0;
+      else if (o.signature == BSMR_TRISTATE_ON) sigCfg = 1;
+      else if (const char* e = getenv("SDDMM_B200_CLUSTER_SIG")) sigCfg = atoi(e) != 0;
+      if (sigCfg != 0 && a.sigThr > 0.f && totalEnt) {
+        const double avgEnt = (double)totalEnt / (double)(M - zeroRows);
+        u32 bits = 64;
+        while (bits < 8.0 * avgEnt && bits < (1u << 16)) bits <<= 1;
+        if (bits >= nbpr) { a.W = (nbpr + 31u) / 32u; a.sigMask = 0xFFFFFFFFu; }
+        else { a.W = bits / 32u; a.sigMask = bits - 1u; }
+        sigBuf.alloc((size_t)M * a.W);
+        SB_CUDA(cudaMemsetAsync(sigBuf.get(), 0, (size_t)M * a.W * 4, s));
+        k_build_sig<<<grid_for((size_t)M * 32), 256, 0, s>>>(enc.get(), meta.get(), M, a.W, a.sigMask, sigBuf.get());
+        SB_LAUNCH_CHECK();
+        a.sig = sigBuf.get();
+      }
+    }
+    u32 G = (u32)((200u * 1024u) / (((size_t)nbpr + a.W + 1) * 4));
     if (o.batch && o.batch < G) G = o.batch;
     G = G >= 8 ? 8u : G >= 4 ? 4u : G >= 2 ? 2u : 1u;  // template instances
     a.G = G;
     SB_CUDA(cudaMemsetAsync(slots.get(), 0xFF, 4 * 8, s));
     SB_CUDA(cudaMemsetAsync(seedsBuf.get(), 0, 16 * 4, s));
     SB_CUDA(cudaMemsetAsync(statsBuf.get(), 0, 8 * 4, s));
-    const size_t smem = (size_t)G * nbpr * 4;
+    const size_t smem = ((((size_t)G * nbpr + 3u) & ~(size_t)3u) + (size_t)G * a.W) * 4;
     const void* kern = G == 8 ? (const void*)k_cluster_batched<8> : G == 4 ? (const void*)k_cluster_batched<4>
                      : G == 2 ? (const void*)k_cluster_batched<2> : (const void*)k_cluster_batched<1>;
     SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -957,8 +1110,8 @@ void row_reorder_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32
       u32 hs[8];
       SB_CUDA(cudaMemcpyAsync(hs, statsBuf.get(), sizeof hs, cudaMemcpyDeviceToHost, s));
       SB_CUDA(cudaStreamSynchronize(s));
-      fprintf(stderr, "[cluster] rows %u entries %u G %u grid %u laneRows %u: exact %u clusters %u windows %u batches %u redo %u\n",
-              M - zeroRows, totalEnt, G, grid, a.laneRows, hs[0], hs[1], hs[2], hs[3], hs[4]);
+      fprintf(stderr, "[cluster] rows %u entries %u G %u grid %u laneRows %u sigWords %u: exact %u clusters %u windows %u batches %u redo %u sig-rejected %u\n",
+              M - zeroRows, totalEnt, G, grid, a.laneRows, a.W, hs[0], hs[1], hs[2], hs[3], hs[4], hs[5]);
     }
     SB_CUDA(cudaMemcpyAsync(ncl.get(), statsBuf.get() + 1, 4, cudaMemcpyDeviceToDevice, s));
   } else if (zeroRows < M) {

@@ -242,6 +242,166 @@ k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restri
   }
 }
 
+// =============================================================================================
+// residual kernel, row-stream form (K7c) -- for matrices whose residual has (almost) no column reuse inside a
+// super-panel (graphs: B is gigabytes, every entry gathers its own B^T row from L2 / HBM, and the super-panel
+// kernel keeps only ONE such row in flight per 8 lanes: ncu on R-MAT scale 22 shows long-scoreboard stalls at 24
+// of 30 cycles per issue, DRAM at 50 %).  Here:
+//   * entries are walked in reordered-ROW order (private StreamLayout), so a row's A fragment stays in registers
+//     across its entries -- the L1/shared data pipe carries B only;
+//   * LANES lanes (K/4 float4 split over 8, 16 or 32 lanes, NB float4 each) work on one entry; every lane issues the
+//     gathered B^T loads of U = 8/NB consecutive entries before the first FMA, i.e. ~4 KB in flight per warp;
+//   * B^T rows are loaded with an L2 evict_last policy and bypass L1; metadata and the P stores stream with
+//     evict_first, so the hub columns of a power-law graph stay L2-resident instead of being washed out;
+//   * a warp takes 32 consecutive entries (coalesced metadata), lane l ends up with the result of entry l through
+//     a transposing butterfly (31 shuffles per 32 entries) and stores it.  Control flow is warp-uniform.
+// Replaces src/sddmmKernel.cu:1994-2104 / :2109-2199 like the other residual kernels.
+// =============================================================================================
+__device__ __forceinline__ u64 l2_policy_evict_last() {
+  u64 p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ u64 l2_policy_evict_first() {
+  u64 p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ldg_f4_policy(const float4* p, u64 pol) {
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ u32 ldg_u32_policy(const u32* p, u64 pol) {
+  u32 v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg_f32_policy(float* p, float v, u64 pol) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+
+template <int LANES, int NB>
+static __global__ void __launch_bounds__(256)
+k_sddmm_residual_stream(const float4* __restrict__ A4, const float4* __restrict__ B4, const u32* __restrict__ stRow,
+                        const u32* __restrict__ stCol, const u32* __restrict__ stIdx, u32 n, float* __restrict__ P,
+                        BatchStrides bs) {
+  A4 += (bs.a >> 2) * blockIdx.y;
+  B4 += (bs.b >> 2) * blockIdx.y;
+  P += bs.p * blockIdx.y;
+  constexpr u32 K4 = LANES * NB;            // float4 per row
+  constexpr int U = NB == 1 ? 8 : NB == 2 ? 4 : 2;  // entries whose B^T fragments are in flight per lane
+  constexpr int BODIES = LANES / 8;         // 8-entry bodies a group walks per 32-entry batch
+  const u32 lane = threadIdx.x & 31u, gl = lane % LANES, g0 = lane - gl;
+  const u64 polB = l2_policy_evict_last(), polS = l2_policy_evict_first();
+  const u32 numBatches = (n + 31u) >> 5;
+  const u32 warpsTotal = gridDim.x * (blockDim.x >> 5), gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const u32 per = (numBatches + warpsTotal - 1) / warpsTotal;
+  const u32 bBeg = min(gw * per, numBatches), bEnd = min(bBeg + per, numBatches);
+
+  u32 prevRow = kNull;
+  float4 a[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  u32 myRow = 0, myCol = 0, myIdx = 0;
+  if (bBeg < bEnd) {  // metadata arrays are padded by 32 entries
+    const u32 e = bBeg * 32u + lane;
+    myRow = ldg_u32_policy(stRow + e, polS);
+    myCol = ldg_u32_policy(stCol + e, polS);
+    myIdx = ldg_u32_policy(stIdx + e, polS);
+  }
+  for (u32 b = bBeg; b < bEnd; ++b) {
+    u32 nRow = 0, nCol = 0, nIdx = 0;
+    if (b + 1 < bEnd) {  // next batch's metadata
+      const u32 e = (b + 1) * 32u + lane;
+      nRow = ldg_u32_policy(stRow + e, polS);
+      nCol = ldg_u32_policy(stCol + e, polS);
+      nIdx = ldg_u32_policy(stIdx + e, polS);
+    }
+    const u32 left = n - b * 32u;  // entries of this batch that exist (>= 1)
+    float v[BODIES];
+#pragma unroll
+    for (int body = 0; body < BODIES; ++body) {
+      float acc[8];
+#pragma unroll
+      for (int h = 0; h < 8 / U; ++h) {
+        float4 bq[U][NB];
+        u32 rows[U];
+        bool live[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const u32 src = g0 + (u32)(body * 8 + h * U + u);  // lane that owns this entry's metadata
+          const u32 col = __shfl_sync(0xffffffffu, myCol, src);
+          rows[u] = __shfl_sync(0xffffffffu, myRow, src);
+          live[u] = src < left;
+          const float4* __restrict__ bp = B4 + (size_t)col * K4 + gl;
+#pragma unroll
+          for (int j = 0; j < NB; ++j)
+            bq[u][j] = live[u] ? ldg_f4_policy(bp + j * LANES, polB) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (live[u] && rows[u] != prevRow) {  // uniform inside the group
+            const float4* __restrict__ ap = A4 + (size_t)rows[u] * K4 + gl;
+#pragma unroll
+            for (int j = 0; j < NB; ++j) a[j] = __ldg(ap + j * LANES);
+            prevRow = rows[u];
+          }
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            const float4 av = a[j], bv = bq[u][j];
+            if (j & 1) {
+              s1 = fmaf(av.x, bv.x, s1); s1 = fmaf(av.y, bv.y, s1); s1 = fmaf(av.z, bv.z, s1); s1 = fmaf(av.w, bv.w, s1);
+            } else {
+              s0 = fmaf(av.x, bv.x, s0); s0 = fmaf(av.y, bv.y, s0); s0 = fmaf(av.z, bv.z, s0); s0 = fmaf(av.w, bv.w, s0);
+            }
+          }
+          acc[h * U + u] = s0 + s1;
+        }
+      }
+      // transposing butterfly over lane bits 0..2: lane ends with entry (gl & 7) of this body, summed over the 8
+      // lanes that share its upper bits
+      float b4[4], b2[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float send = (gl & 4u) ? acc[i] : acc[i + 4];
+        const float keep = (gl & 4u) ? acc[i + 4] : acc[i];
+        b4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float send = (gl & 2u) ? b4[i] : b4[i + 2];
+        const float keep = (gl & 2u) ? b4[i + 2] : b4[i];
+        b2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      const float send = (gl & 1u) ? b2[0] : b2[1];
+      const float keep = (gl & 1u) ? b2[1] : b2[0];
+      v[body] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+    float mine = v[0];
+    if constexpr (BODIES >= 2) {  // bit 3 picks the body inside a pair, the partner holds the other 8-lane partial
+      float w[BODIES / 2];
+#pragma unroll
+      for (int i = 0; i < BODIES / 2; ++i) {
+        const float send = (gl & 8u) ? v[2 * i] : v[2 * i + 1];
+        const float keep = (gl & 8u) ? v[2 * i + 1] : v[2 * i];
+        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      mine = w[0];
+      if constexpr (BODIES == 4) {
+        const float send = (gl & 16u) ? w[0] : w[1];
+        const float keep = (gl & 16u) ? w[1] : w[0];
+        mine = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+    }
+    if (lane < left) stg_f32_policy(P + myIdx, mine, polS);
+    myRow = nRow; myCol = nCol; myIdx = nIdx;
+  }
+}
+
 // panels per super-panel for a given K (A tile <= ~192 KB), 0 if the super-panel kernel does not apply
 static u32 superpanel_G(u32 K) {
   if (K % 32u || K > 512u) return 0;
@@ -1349,7 +1509,8 @@ void plan_default(sddmm_plan* out) {
   out->plan = env_choice("SDDMM_B200_PLAN", {{"bsmr", SDDMM_PLAN_BSMR}, {"full", SDDMM_PLAN_TILE}, {"tile", SDDMM_PLAN_TILE}});
   out->dense = env_choice("SDDMM_B200_DENSE", {{"reg", SDDMM_DENSE_REG}, {"tma", SDDMM_DENSE_TMA}});
   out->residual = env_choice("SDDMM_B200_RESIDUAL", {{"0", SDDMM_RESIDUAL_PANEL}, {"panel", SDDMM_RESIDUAL_PANEL},
-                                                     {"1", SDDMM_RESIDUAL_SUPERPANEL}, {"sp", SDDMM_RESIDUAL_SUPERPANEL}});
+                                                     {"1", SDDMM_RESIDUAL_SUPERPANEL}, {"sp", SDDMM_RESIDUAL_SUPERPANEL},
+                                                     {"2", SDDMM_RESIDUAL_STREAM}, {"stream", SDDMM_RESIDUAL_STREAM}});
   out->tile = env_choice("SDDMM_B200_TILE", {{"reg", SDDMM_TILE_REG}, {"tma1", SDDMM_TILE_TMA}, {"tma", SDDMM_TILE_TMA},
                                              {"tma4", SDDMM_TILE_TMA_CLUSTER}});
   if (const char* e = getenv("SDDMM_B200_TILE_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 4) out->tileStages = (u32)v; }
@@ -1362,7 +1523,7 @@ void plan_resolve(const bsmr_layout* L, u32 K, u32 numBatch, const sddmm_plan* i
   if (K == 0 || (K & 3u)) fail(SDDMM_E_ARG, "K=%u must be a positive multiple of 4", K);
   sddmm_plan p;
   if (in) p = *in; else plan_default(&p);
-  if (p.plan > SDDMM_PLAN_TILE || p.dense > SDDMM_DENSE_TMA || p.residual > SDDMM_RESIDUAL_SUPERPANEL ||
+  if (p.plan > SDDMM_PLAN_TILE || p.dense > SDDMM_DENSE_TMA || p.residual > SDDMM_RESIDUAL_STREAM ||
       p.tile > SDDMM_TILE_TMA_CLUSTER || (p.tileStages && (p.tileStages < 2 || p.tileStages > 4)))
     fail(SDDMM_E_ARG, "sddmm_plan holds an unknown selector");
   const bsmr_layout_info& I = L->info;
@@ -1395,9 +1556,19 @@ void plan_resolve(const bsmr_layout* L, u32 K, u32 numBatch, const sddmm_plan* i
     if (!L->numSparseWork) p.residual = SDDMM_RESIDUAL_AUTO;
     else {
       const u32 G = superpanel_G(K);
-      if (p.residual == SDDMM_RESIDUAL_SUPERPANEL && !G)
-        fail(SDDMM_E_UNSUPPORTED, "SDDMM_RESIDUAL_SUPERPANEL needs K in {32, 64, 128, 256, 512} (K=%u)", K);
-      if (p.residual == SDDMM_RESIDUAL_AUTO) p.residual = G ? SDDMM_RESIDUAL_SUPERPANEL : SDDMM_RESIDUAL_PANEL;
+      if ((p.residual == SDDMM_RESIDUAL_SUPERPANEL || p.residual == SDDMM_RESIDUAL_STREAM) && !G)
+        fail(SDDMM_E_UNSUPPORTED, "SDDMM_RESIDUAL_%s needs K in {32, 64, 128, 256, 512} (K=%u)",
+             p.residual == SDDMM_RESIDUAL_STREAM ? "STREAM" : "SUPERPANEL", K);
+      if (p.residual == SDDMM_RESIDUAL_AUTO) {
+        if (!G) p.residual = SDDMM_RESIDUAL_PANEL;
+        else {
+          // expected entries per (super-panel, column) run: below ~1.5 a fetched B^T row is not reused from
+          // registers and the super-panel kernel only pays for its shared-memory staging -> row-stream kernel
+          const double rowsSp = 16.0 * G;
+          const double run = 1.0 + rowsSp * (double)I.numSparseValues / ((double)(I.numRows ? I.numRows : 1) * (double)I.N);
+          p.residual = run >= 1.5 ? SDDMM_RESIDUAL_SUPERPANEL : SDDMM_RESIDUAL_STREAM;
+        }
+      }
       if (p.residual == SDDMM_RESIDUAL_PANEL && (size_t)16 * K * sizeof(float) > 200 * 1024)
         fail(SDDMM_E_UNSUPPORTED, "K=%u too large for the residual kernel's A tile", K);
     }
@@ -1413,6 +1584,7 @@ void plan_prepare(const bsmr_layout* L, u32 K, u32 numBatch, const sddmm_plan& p
   }
   if (p.dense == SDDMM_DENSE_TMA) ensure_dense_tma(L, K, numBatch, s);
   if (p.residual == SDDMM_RESIDUAL_SUPERPANEL) ensure_superpanels(L, superpanel_G(K), s);
+  if (p.residual == SDDMM_RESIDUAL_STREAM) ensure_stream(L, s);
 }
 
 // The rounded-operand workspaces are shared by every pass of one (K, numBatch): passes on different streams are
@@ -1528,7 +1700,30 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
     }
   }
   if (L->numSparseWork && (which & kLaunchSparse)) {
-    if (p.residual == SDDMM_RESIDUAL_SUPERPANEL) {
+    if (p.residual == SDDMM_RESIDUAL_STREAM) {
+      const StreamLayout* st = ensure_stream(L, sparseStream);
+      if (st->numEntries) {
+        const u32 numBatches = (st->numEntries + 31u) / 32u;
+        auto launch = [&](auto kern) {
+          // one resident wave: every warp walks ONE contiguous range of 32-entry batches (its rows' A fragments and
+          // the metadata stream stay local), so the grid is what fits on the device at once
+          int perSm = 0;
+          SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, 256, 0));
+          const u32 grid = std::min<u32>((numBatches + 7u) / 8u, (u32)device_sm_count() * (u32)std::max(perSm, 1));
+          kern<<<dim3(grid, numBatch), 256, 0, sparseStream>>>(reinterpret_cast<const float4*>(dA),
+                                                              reinterpret_cast<const float4*>(dB), st->row.get(),
+                                                              st->col.get(), st->idx.get(), st->numEntries, dP, bst);
+        };
+        switch (K / 32u) {
+          case 1: launch(k_sddmm_residual_stream<8, 1>); break;
+          case 2: launch(k_sddmm_residual_stream<16, 1>); break;
+          case 4: launch(k_sddmm_residual_stream<32, 1>); break;
+          case 8: launch(k_sddmm_residual_stream<32, 2>); break;
+          default: launch(k_sddmm_residual_stream<32, 4>); break;
+        }
+        SB_LAUNCH_CHECK();
+      }
+    } else if (p.residual == SDDMM_RESIDUAL_SUPERPANEL) {
       const SuperPanelLayout* sp = ensure_superpanels(L, superpanel_G(K), sparseStream);
       if (sp->numWork) {
         const size_t smem = (size_t)sp->rows * K * sizeof(float);

@@ -35,7 +35,7 @@ def _ptr(a):
 
 
 def make_plan(plan="auto", dense="auto", residual="auto", tile="auto", tile_stages=0):
-    """sddmm_plan by name: plan auto|bsmr|tile, dense auto|reg|tma, residual auto|panel|superpanel,
+    """sddmm_plan by name: plan auto|bsmr|tile, dense auto|reg|tma, residual auto|panel|superpanel|stream,
     tile auto|reg|tma|tma_cluster.  None where the library's defaults (environment, cost model) should decide."""
     return Plan(_lib.PLAN[plan], _lib.DENSE[dense], _lib.RESIDUAL[residual], _lib.TILE[tile], int(tile_stages))
 

@@ -6,6 +6,7 @@ reference's checkData tolerance (include/checkData.hpp:14-30).  One test id per 
   dense_tma    k_sddmm_dense_tma    BSMR dense blocks, TMA tile::gather4 operands (same reference kernels)
   res_panel    k_sddmm_residual     residual, one panel per CTA, any K % 4 == 0   (src/sddmmKernel.cu:1994-2104, :2109-2199)
   res_sp       k_sddmm_residual_sp  residual, super-panels, K in {32,...,512}     (same reference kernels)
+  res_stream   k_sddmm_residual_stream  residual, row order, deep gather pipeline, K in {32,...,512}
   tile_reg     k_sddmm_tile         128x128 tcgen05 tiles, register-staged
   tile_tma     k_sddmm_tile_tma     128x128 tcgen05 tiles, TMA-fed
   tile_tma4    k_sddmm_tile_tma4    2x2 clusters, multicast TMA
@@ -31,6 +32,7 @@ KERNELS = {
     "dense_tma": (0.0, dict(plan="bsmr", dense="tma"), dict(plan="bsmr", dense="tma")),
     "res_panel": (1.1, dict(plan="bsmr", residual="panel"), dict(plan="bsmr", residual="panel")),
     "res_sp": (1.1, dict(plan="bsmr", residual="superpanel"), dict(plan="bsmr", residual="superpanel")),
+    "res_stream": (1.1, dict(plan="bsmr", residual="stream"), dict(plan="bsmr", residual="stream")),
     "tile_reg": (0.3, dict(plan="tile", tile="reg"), dict(plan="tile", tile="reg")),
     "tile_tma": (0.3, dict(plan="tile", tile="tma"), dict(plan="tile", tile="tma")),
     "tile_tma3": (0.3, dict(plan="tile", tile="tma", tile_stages=3), dict(plan="tile", tile="tma", tile_stages=3)),
@@ -93,7 +95,7 @@ def test_kernel_parity(kernel, K, nb, mname, torch_mod):
     S = MATS[mname]
     lay = _layout(mname, delta)
     plan = pkg.make_plan(**kw)
-    if kernel == "res_sp" and K not in SP_KS:
+    if kernel in ("res_sp", "res_stream") and K not in SP_KS:
         with pytest.raises(pkg.SddmmError) as e:  # an impossible choice fails loudly, it never silently runs another kernel
             pkg.plan_resolve(lay, K, nb, plan)
         assert e.value.code == 4
@@ -118,7 +120,7 @@ def test_residual_panel_kernel_odd_K(K, torch_mod):
 
 
 @pytest.mark.parametrize("dense", ["reg", "tma"])
-@pytest.mark.parametrize("residual", ["panel", "superpanel"])
+@pytest.mark.parametrize("residual", ["panel", "superpanel", "stream"])
 @pytest.mark.parametrize("K", [64, 256])
 def test_mixed_dense_and_residual(dense, residual, K, torch_mod):
     """delta = 0.3: dense blocks and residual entries in the same pass, on two streams."""
