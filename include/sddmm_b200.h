@@ -289,6 +289,17 @@ int sddmm_host(const uint32_t* h_rowOff, const uint32_t* h_colIdx, uint32_t M, u
                uint32_t K, const float* h_A, const float* h_B, float alpha, float delta,
                uint32_t block_size, float* h_P, sddmm_stats* stats, bsmr_layout** layoutOut);
 
+/* ---- f1: CSR assembly on the device for the file loaders ------------------------------------------
+ * replaces the sort / duplicate-check / offset stages of
+ *   sparseMatrix::CSR<float>::initializeFromMtxFile          src/Matrix.cpp:398-480
+ *     (std::set duplicate check :447-461, thrust::host stable sort by row :467, rowOffsets :470-479)
+ * for triplets a loader has already parsed and range-checked: n entries in FILE order, 0-based.
+ * Output: rows ascending, FILE order kept inside a row (the reference sorts by row only).  *hasDuplicate = 1 when
+ * some (row, col) appears twice (the reference rejects such a file); the outputs are then untouched.
+ * h_vals / h_values may be NULL (pattern only). */
+int sddmm_coo_to_csr(const uint32_t* h_rows, const uint32_t* h_cols, const float* h_vals, uint32_t nnz, uint32_t M,
+                     uint32_t N, uint32_t* h_rowOff, uint32_t* h_colIdx, float* h_values, int* hasDuplicate);
+
 /* ---- e: multi-GPU row-panel sharding ----------------------------------------------------------
  * (no reference counterpart: the reference is single-GPU.)  Cuts the P row panels of the
  * reordered matrix into `numShards` contiguous ranges with equal non-zero counts; cuts[s] ..

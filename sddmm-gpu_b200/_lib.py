@@ -123,6 +123,7 @@ def lib():
     L.sddmm_host_sync.argtypes = [vp]
     L.sddmm_host.argtypes = [vp, vp, u32, u32, u32, u32, vp, vp, f32, f32, u32, vp, C.POINTER(Stats), C.POINTER(vp)]
     L.bsmr_shard_plan.argtypes = [vp, vp, u32, u32, vp]
+    L.sddmm_coo_to_csr.argtypes = [vp, vp, vp, u32, u32, u32, vp, vp, vp, C.POINTER(C.c_int)]
     L.bsmr_shard_plan_dev.argtypes = [vp, vp, u32, u32, vp, vp]
     L.sddmm_mgpu_unique_id.argtypes = [vp]
     L.sddmm_mgpu_init.argtypes = [C.c_int, C.c_int, vp, C.POINTER(vp)]

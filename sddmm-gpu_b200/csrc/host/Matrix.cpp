@@ -5,6 +5,7 @@
 // (row-only stable order) are those of src/Matrix.cpp:398-480.
 #include "Matrix.hpp"
 
+#include <cuda_runtime_api.h>
 #include <omp.h>
 #include <parallel/algorithm>
 
@@ -16,6 +17,8 @@
 #include <iostream>
 #include <random>
 #include <unordered_map>
+
+#include "sddmm_b200.h"
 
 template <typename T>
 void Matrix<T>::makeData(uint64_t seed) {
@@ -50,6 +53,16 @@ inline const char* next_line(const char* p) {
   return *p ? p + 1 : p;
 }
 inline bool at_eol(const char* p) { return *p == '\n' || *p == 0; }
+
+// device CSR assembly (libsddmm_b200's sddmm_coo_to_csr) for files of >= 4 M entries when a CUDA device exists
+bool use_device_loader(size_t nnz) {
+  const char* e = std::getenv("SDDMM_B200_LOADER");
+  if (e && !std::strcmp(e, "host")) return false;
+  int n = 0;
+  const bool haveDev = cudaGetDeviceCount(&n) == cudaSuccess && n > 0;
+  if (e && !std::strcmp(e, "device")) return true;  // forced: fails loudly without a device
+  return haveDev && nnz >= (static_cast<size_t>(1) << 22);
+}
 
 std::string suffix_of(const std::string& f) {
   const size_t dot = f.find_last_of('.');
@@ -142,17 +155,40 @@ bool CSR<T>::initializeFromMtxFile(const std::string& file) {
       o += tri[t].size();
     }
   }
-  std::vector<uint64_t> keys(nnz_);
   bool tooBig = false;
 #pragma omp parallel for reduction(|| : tooBig)
-  for (long i = 0; i < static_cast<long>(nnz_); ++i) {
-    tooBig = tooBig || ri[i] >= row_ || ci[i] >= col_;
-    keys[i] = (static_cast<uint64_t>(ri[i]) << 32) | ci[i];
-  }
+  for (long i = 0; i < static_cast<long>(nnz_); ++i) tooBig = tooBig || ri[i] >= row_ || ci[i] >= col_;
   if (tooBig) {
     std::cerr << "Error, file " << file << " row or col is too big!" << std::endl;
     return false;
   }
+  // CSR assembly: on the device (sddmm_coo_to_csr: duplicate check = key sort, stable radix sort by row, histogram +
+  // scan) for big files when a GPU is there, else the host stages below.  SDDMM_B200_LOADER=device|host forces one.
+  if (use_device_loader(nnz_)) {
+    int dup = 0;
+    rowOffsets_.assign(static_cast<size_t>(row_) + 1, 0);
+    colIndices_.resize(nnz_);
+    std::vector<float> vin(va.begin(), va.end()), vout(nnz_);
+    const int rc = sddmm_coo_to_csr(ri.data(), ci.data(), vin.data(), nnz_, row_, col_, rowOffsets_.data(),
+                                    colIndices_.data(), vout.data(), &dup);
+    if (rc != SDDMM_OK) {
+      std::cerr << "Error, device CSR build failed: " << sddmm_last_error() << std::endl;
+      return false;
+    }
+    if (dup) {
+      std::cerr << "Error, matrix has duplicate data!" << std::endl;
+      return false;
+    }
+    if (nnz_ <= 1) {
+      std::cerr << "Warning, file " << file << " nnz is 1, this is not a valid matrix!" << std::endl;
+      return false;
+    }
+    values_.assign(vout.begin(), vout.end());
+    return true;
+  }
+  std::vector<uint64_t> keys(nnz_);
+#pragma omp parallel for
+  for (long i = 0; i < static_cast<long>(nnz_); ++i) keys[i] = (static_cast<uint64_t>(ri[i]) << 32) | ci[i];
   __gnu_parallel::sort(keys.begin(), keys.end());
   if (std::adjacent_find(keys.begin(), keys.end()) != keys.end()) {
     std::cerr << "Error, matrix has duplicate data!" << std::endl;
