@@ -27,6 +27,8 @@ struct Logger {
   float sddmmTime_ = 0.f, denseTime_ = 0.f, sparseTime_ = 0.f, rowReorderingTime_ = 0.f, colReorderingTime_ = 0.f,
         reorderingTime_ = 0.f, rphmTime_ = 0.f;
   unsigned blockSize_ = 0;
+  int rank_ = 0, world_ = 1;
+  unsigned shardNnz_ = 0, shardPanelBegin_ = 0, shardPanelEnd_ = 0;
 
   void getInformation(const Options& o) {
     inputFile_ = o.inputFile(); K_ = o.K(); numITER_ = o.numIterations();
@@ -76,5 +78,8 @@ struct Logger {
     out << "[b200_dense_kernel_ms : " << denseTime_ << "]\n";
     out << "[b200_residual_kernel_ms : " << sparseTime_ << "]\n";
     out << "[b200_residual_cta : " << residualCta_ << "]\n";
+    if (world_ > 1)
+      out << "[b200_rank : " << rank_ << "], [b200_world : " << world_ << "], [b200_shard_panels : " << shardPanelBegin_
+          << " " << shardPanelEnd_ << "], [b200_shard_nnz : " << shardNnz_ << "]\n";
   }
 };

@@ -2,7 +2,8 @@
 //   -f/-F file, -k/-K K (32), -a/-A alpha (0.3), -d/-D delta (0.3), -t/-T test sweep, -l/-L log dir;
 //   with no option flags: argv[1] = file, argv[2] = K.
 // Additions (absent from the reference): -b block_size (0 = reference rule), -g free-memory bytes used
-// by that rule (reproducibility), -i iterations.
+// by that rule (reproducibility), -i iterations; multi-GPU (one process per GPU):
+// -r rank, -w world size, -u path of the file through which rank 0 hands the 128-byte NCCL id to the others.
 #pragma once
 #include <cstdlib>
 #include <iostream>
@@ -41,6 +42,9 @@ class Options {
   std::string outputLogDirectory() const { return logDir_; }
   uint32_t blockSize() const { return blockSize_; }
   uint64_t freeMemForBlockSize() const { return freeMem_; }
+  int rank() const { return rank_; }
+  int world() const { return world_; }
+  std::string idFile() const { return idFile_; }
 
  private:
   void parse(const std::string& o, const std::string& v) {
@@ -54,6 +58,9 @@ class Options {
       if (o == "-B" || o == "-b") blockSize_ = static_cast<uint32_t>(std::stoul(v));
       if (o == "-G" || o == "-g") freeMem_ = std::stoull(v);
       if (o == "-I" || o == "-i") numIterations_ = std::stoi(v);
+      if (o == "-R" || o == "-r") rank_ = std::stoi(v);
+      if (o == "-W" || o == "-w") world_ = std::stoi(v);
+      if (o == "-U" || o == "-u") idFile_ = v;
     } catch (const std::exception& e) {
       std::cerr << "Invalid argument: " << e.what() << std::endl;
     }
@@ -65,4 +72,6 @@ class Options {
   bool testMode_ = false;
   uint32_t blockSize_ = 0;
   uint64_t freeMem_ = 0;
+  int rank_ = 0, world_ = 1;
+  std::string idFile_;
 };

@@ -9,6 +9,8 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <fstream>
 
 #include "sddmm.hpp"
@@ -152,6 +154,102 @@ void sddmm(const Options& options, const Matrix<float>& A, const Matrix<float>& 
   RPHM rphm(P, bsmr);
   sddmm_gpu(A, B, rphm, P, logger);
   evaluationReordering(P, rphm, logger);  // src/sddmm.cu:32
+}
+
+// ---- multi-GPU: one process per GPU, driven through the C ABI's sddmm_mgpu_* entry points ----------------
+namespace {
+struct DevMem {
+  void* p = nullptr;
+  explicit DevMem(size_t bytes) { if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) p = nullptr; }
+  ~DevMem() { cudaFree(p); }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+// rank 0 publishes the NCCL id through a file (written under a temporary name, then renamed); the others poll
+bool exchange_id_through_file(const Options& o, unsigned char* id) {
+  const std::string path = o.idFile();
+  if (path.empty()) { std::fprintf(stderr, "multi-GPU run needs -u <id file>\n"); return false; }
+  if (o.rank() == 0) {
+    if (!ok(sddmm_mgpu_unique_id(id), "sddmm_mgpu_unique_id")) return false;
+    const std::string tmp = path + ".tmp";
+    std::ofstream f(tmp, std::ios::binary);
+    f.write(reinterpret_cast<const char*>(id), SDDMM_MGPU_ID_BYTES);
+    f.close();
+    return std::rename(tmp.c_str(), path.c_str()) == 0;
+  }
+  for (int tries = 0; tries < 6000; ++tries) {  // up to ~60 s
+    std::ifstream f(path, std::ios::binary);
+    if (f.good() && f.read(reinterpret_cast<char*>(id), SDDMM_MGPU_ID_BYTES)) return true;
+    struct timespec ts = {0, 10 * 1000 * 1000};
+    nanosleep(&ts, nullptr);
+  }
+  std::fprintf(stderr, "rank %d: no NCCL id appeared in %s\n", o.rank(), path.c_str());
+  return false;
+}
+}  // namespace
+
+bool sddmm_multiGpu(const Options& options, const Matrix<float>& A, const Matrix<float>& B, sparseMatrix::CSR<float>& P,
+                    Logger& logger) {
+  const int rank = options.rank(), world = options.world();
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { std::fprintf(stderr, "no CUDA device\n"); return false; }
+  const char* lr = std::getenv("LOCAL_RANK");
+  cudaSetDevice((lr ? std::atoi(lr) : rank) % ndev);
+  unsigned char id[SDDMM_MGPU_ID_BYTES] = {0};
+  if (world > 1 && !exchange_id_through_file(options, id)) return false;
+  sddmm_mgpu* g = nullptr;
+  if (!ok(sddmm_mgpu_init(rank, world, id, &g), "sddmm_mgpu_init")) return false;
+  const UIN M = P.row(), N = P.col(), nnz = P.nnz(), K = A.col();
+  DevMem ro((size_t)(M + 1) * 4), ci((size_t)nnz * 4), rr((size_t)M * 4), dA(A.size() * 4), dB(B.size() * 4), dP((size_t)nnz * 4);
+  bool good = ro.p && ci.p && rr.p && dA.p && dB.p && dP.p;
+  bsmr_layout* lay = nullptr;
+  if (good) {
+    cudaMemcpy(ro.p, P.rowOffsets().data(), (size_t)(M + 1) * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(ci.p, P.colIndices().data(), (size_t)nnz * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dA.p, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+    if (rank == 0) cudaMemcpy(dB.p, B.data(), B.size() * 4, cudaMemcpyHostToDevice);  // the others receive it
+    cudaMemset(dP.p, 0, (size_t)nnz * 4);
+    UIN numRows = 0;
+    int32_t ncl = 0;
+    float msRow = 0.f, msCol = 0.f, msRphm = 0.f;
+    UIN bs = options.blockSize() ? options.blockSize() : calculateBlockSize(P, options.freeMemForBlockSize());
+    if (rank == 0)
+      good = ok(bsmr_row_reorder_dev(ro.as<UIN>(), ci.as<UIN>(), M, N, nnz, options.similarityThresholdAlpha(), bs,
+                                     rr.as<UIN>(), &numRows, &ncl, &msRow, nullptr), "bsmr_row_reorder_dev");
+    std::vector<UIN> cuts(world + 1, 0);
+    good = good && ok(sddmm_mgpu_shard(g, ro.as<UIN>(), ci.as<UIN>(), M, N, nnz, rr.as<UIN>(), &numRows,
+                                       options.blockDensityThresholdDelta(), BSMR_BUILD_TILES_AUTO, &lay, cuts.data(),
+                                       &msCol, &msRphm, nullptr), "sddmm_mgpu_shard");
+    good = good && ok(sddmm_mgpu_bcast(g, dB.p, B.size() * 4, 0, nullptr), "sddmm_mgpu_bcast");
+    if (good) {
+      bsmr_layout_info info{};
+      bsmr_layout_get_info(lay, &info);
+      float d = 0.f, s = 0.f, t = 0.f;
+      good = ok(sddmm_run_timed_dev(lay, K, dA.as<float>(), dB.as<float>(), dP.as<float>(), 3,
+                                    logger.numITER_ > 0 ? logger.numITER_ : 10, &d, &s, &t), "sddmm_run_timed_dev");
+      good = good && ok(sddmm_mgpu_run(g, lay, K, dA.as<float>(), dB.as<float>(), dP.as<float>(), nullptr), "sddmm_mgpu_run");
+      good = good && ok(sddmm_mgpu_gather(g, dP.as<float>(), nnz, nullptr), "sddmm_mgpu_gather");
+      cudaDeviceSynchronize();
+      std::vector<float> out(nnz);
+      cudaMemcpy(out.data(), dP.p, (size_t)nnz * 4, cudaMemcpyDeviceToHost);
+      P.setValues() = out;
+      logger.sddmmTime_ = t; logger.denseTime_ = d; logger.sparseTime_ = s;
+      logger.rowReorderingTime_ = msRow; logger.colReorderingTime_ = msCol; logger.reorderingTime_ = msRow + msCol;
+      logger.rphmTime_ = msRphm; logger.numClusters_ = ncl; logger.blockSize_ = bs;
+      logger.numRowPanels_ = static_cast<int>(info.numRowPanels);
+      logger.rank_ = rank; logger.world_ = world;
+      logger.shardNnz_ = info.numDenseValues + info.numSparseValues;
+      logger.shardPanelBegin_ = cuts[rank]; logger.shardPanelEnd_ = cuts[rank + 1];
+      logger.numDenseData_ = info.numDenseValues; logger.numSparseData_ = info.numSparseValues;
+      logger.numDenseBlock_ = static_cast<int>(info.numDenseBlocks);
+      logger.numDenseThreadBlocks_ = static_cast<int>(info.numDenseThreadBlocks);
+      logger.numSparseThreadBlocks_ = static_cast<int>(info.numSparseThreadBlocks);
+    }
+  } else {
+    std::fprintf(stderr, "rank %d: device allocation failed\n", rank);
+  }
+  if (lay) bsmr_layout_destroy(lay);
+  sddmm_mgpu_destroy(g);
+  return good;
 }
 
 // ---- checker (verification only) ---------------------------------------------------------------------

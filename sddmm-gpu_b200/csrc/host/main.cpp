@@ -67,6 +67,13 @@ int main(int argc, char* argv[]) {
   logger.getInformation(matrixA, matrixB);
 
   sparseMatrix::CSR<float> matrixP(matrixS);
+  if (options.world() > 1) {
+    // one process per GPU: every rank loads the same file and draws the same A, B (fixed seeds)
+    if (!sddmm_multiGpu(options, matrixA, matrixB, matrixP, logger)) return -1;
+    if (validate) checkSddmm(matrixA, matrixB, matrixS, matrixP);  // after the gather every rank holds all of P
+    logger.printLogInformation();
+    return 0;
+  }
   sddmm(options, matrixA, matrixB, matrixP, logger);
   if (validate) checkSddmm(matrixA, matrixB, matrixS, matrixP);
   logger.printLogInformation();

@@ -9,6 +9,12 @@
 void sddmm(const Options& options, const Matrix<float>& matrixA, const Matrix<float>& matrixB,
            sparseMatrix::CSR<float>& matrixP, Logger& logger);
 void sddmm_testMode(const Options& options, sparseMatrix::CSR<float>& matrixP);
+// Multi-GPU form of sddmm() (no reference counterpart: the reference is single-GPU).  Called by EVERY rank's
+// process with the same S, A, B: rank 0 reorders, sddmm_mgpu_shard hands every rank its nnz-balanced row-panel
+// range, B is replicated once over NCCL, the timed passes run without any collective, sddmm_mgpu_gather leaves
+// the whole P on every rank.  Options: -r rank -w world -u id-file (rank 0 writes the NCCL id there).
+bool sddmm_multiGpu(const Options& options, const Matrix<float>& matrixA, const Matrix<float>& matrixB,
+                    sparseMatrix::CSR<float>& matrixP, Logger& logger);
 void sddmm_gpu(const Matrix<float>& matrixA, const Matrix<float>& matrixB, const RPHM& rphm,
                sparseMatrix::CSR<float>& matrixP, Logger& logger);
 // raw device-pointer overload (src/sddmmKernel.cu:2539)
