@@ -653,7 +653,7 @@ __device__ __forceinline__ u32 cb_eval_row_lane(const ClusterBatchArgs& a, const
   const u32 ssCmp = m.z;
   const float nCmpInv = ssCmp ? 1.0f / sqrtf((float)ssCmp) : 0.f;
   *again = false;
-  if (a.W && ssCmp && m.y * 2u > a.W) {
+  if (a.W && ssCmp && (m.y * 2u > a.W || m.y > a.laneRows)) {
     u32 sh[TG], popB = 0;
 #pragma unroll
     for (int k = 0; k < TG; ++k) sh[k] = 0;
@@ -682,10 +682,11 @@ __device__ __forceinline__ u32 cb_eval_row_lane(const ClusterBatchArgs& a, const
       if ((u32)k < kmax)
         any = any || sSs[k] == 0 ||
               cb_sig_may_join((float)sh[k], (float)(sS1[k] - sPop[k]), nRepInv[k], Sa[k], exCmp, nCmpInv, Sb, a.sigThr);
-    if (!any) {
-      atomicAdd(a.stats + 5, 1u);
-      return kNull;
-    }
+    if (!any) return kNull;
+  }
+  if (m.y > a.laneRows) {  // a long row that may join: redone by a whole warp
+    *again = true;
+    return kNull;
   }
   float mn[TG];
 #pragma unroll
@@ -822,9 +823,7 @@ static __global__ void __launch_bounds__(kCbThreads, 1) k_cluster_batched(Cluste
           u32 joinK = kNull;
           bool again = false;
           if (kmax) {
-            if (m.y <= a.laneRows)
-              joinK = cb_eval_row_lane<TG>(a, rep, repSig, sPop, sSs, sS1, nRepInv, Sa, pos, m, kmax, tol, &again);
-            else again = true;
+            joinK = cb_eval_row_lane<TG>(a, rep, repSig, sPop, sSs, sS1, nRepInv, Sa, pos, m, kmax, tol, &again);
           }
           if (again) {
             sTodo[atomicAdd(&sTodoCnt, 1u)] = pos;  // at most one per thread and step
@@ -1073,7 +1072,7 @@ void row_reorder_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32
       if (sigCfg != 0 && a.sigThr > 0.f && totalEnt) {
         const double avgEnt = (double)totalEnt / (double)(M - zeroRows);
         u32 bits = 64;
-        while (bits < 8.0 * avgEnt && bits < (1u << 16)) bits <<= 1;
+        while (bits < (a.laneRows ? 4.0 : 8.0) * avgEnt && bits < (1u << 16)) bits <<= 1;
         if (bits >= nbpr) { a.W = (nbpr + 31u) / 32u; a.sigMask = 0xFFFFFFFFu; }
         else { a.W = bits / 32u; a.sigMask = bits - 1u; }
         sigBuf.alloc((size_t)M * a.W);

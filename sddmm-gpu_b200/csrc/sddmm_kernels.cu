@@ -115,6 +115,33 @@ k_sddmm_residual(u32 M, u32 K4, const float4* __restrict__ A4, const float4* __r
 }
 
 
+// ---- L2 eviction-policy loads / stores (sm_80+: createpolicy + .L2::cache_hint) -------------------------
+__device__ __forceinline__ u64 l2_policy_evict_last() {
+  u64 p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ u64 l2_policy_evict_first() {
+  u64 p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ldg_f4_policy(const float4* p, u64 pol) {
+  float4 v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ u32 ldg_u32_policy(const u32* p, u64 pol) {
+  u32 v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg_f32_policy(float* p, float v, u64 pol) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+
 // =============================================================================================
 // residual kernel, super-panel form (K7b)
 //   CTA = one segment of one super-panel (G row panels) whose A rows (16*G x K) sit in shared memory.
@@ -125,7 +152,13 @@ k_sddmm_residual(u32 M, u32 K4, const float4* __restrict__ A4, const float4* __r
 //   predicated), so all shuffles use the full mask; lane t of a group keeps the result of entry t of the
 //   block and stores it itself.  L2->SM bytes per entry drop from 4K+16 to ~4K/(entries per column)+10.
 // =============================================================================================
-template <int NB, int kThreads>
+// kHints: gathered B^T rows are loaded with an L2 evict_last policy (and bypass L1), metadata and P stream with
+// evict_first -- for matrices whose B does not fit the L2 (graphs), so that the hub columns stay resident.
+// U > 0 ("gather mode", chosen when a (super-panel, column) run averages < 1.5 entries, i.e. graphs): there is no
+// column run to reuse, so every entry loads its own B^T fragment and the loads of U consecutive entries are issued
+// before the first FMA -- U x 4K bytes in flight per 8 lanes instead of one row (ncu, R-MAT scale 22: 24 of 30
+// cycles per issue were long-scoreboard stalls with one row in flight).  U = 0: column-run reuse from registers.
+template <int NB, int kThreads, bool kHints, int U>
 static __global__ void __launch_bounds__(kThreads, 1)
 k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restrict__ B4, const u32* __restrict__ R,
                     u32 nR, u32 spRows, u32 segLen, const u32* __restrict__ spOff, const u32* __restrict__ spCol,
@@ -156,6 +189,16 @@ k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restri
   __syncthreads();
 
   const u32 grp = threadIdx.x >> 3, gl = threadIdx.x & 7u;
+  u64 polB = 0, polS = 0;
+  if (kHints) { polB = l2_policy_evict_last(); polS = l2_policy_evict_first(); }
+  auto ld_meta4 = [&](const uint4* p) {
+    if (!kHints) return __ldg(p);
+    uint4 v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+        : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(polS));
+    return v;
+  };
+  auto ld_meta1 = [&](const u32* p) { return kHints ? ldg_u32_policy(p, polS) : __ldg(p); };
   // Groups own 8-aligned (absolute index) slices of the segment, so metadata comes in aligned 8-entry blocks:
   // two 16-byte loads of columns and one of rows, the same addresses for the 8 lanes of a group.  Only the
   // first / last group see entries of a neighbouring segment in their blocks; those are masked out.
@@ -174,25 +217,59 @@ k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restri
   uint4 c0 = make_uint4(~0u, ~0u, ~0u, ~0u), c1 = c0, r8 = make_uint4(0, 0, 0, 0);
   u32 mi = 0;
   if (aBeg < gEnd) {
-    c0 = __ldg(col4 + (aBeg >> 2));
-    c1 = __ldg(col4 + (aBeg >> 2) + 1);
-    r8 = __ldg(row4 + (aBeg >> 3));
-    mi = __ldg(spIdx + aBeg + gl);
+    c0 = ld_meta4(col4 + (aBeg >> 2));
+    c1 = ld_meta4(col4 + (aBeg >> 2) + 1);
+    r8 = ld_meta4(row4 + (aBeg >> 3));
+    mi = ld_meta1(spIdx + aBeg + gl);
   }
   for (u32 blk = 0; blk < nBlocks; ++blk) {
     const u32 base = aBeg + blk * 8u;
     uint4 nc0 = make_uint4(~0u, ~0u, ~0u, ~0u), nc1 = nc0, nr8 = make_uint4(0, 0, 0, 0);
     u32 ni = 0;
     if (base + 8u < gEnd) {  // next block's metadata
-      nc0 = __ldg(col4 + ((base + 8u) >> 2));
-      nc1 = __ldg(col4 + ((base + 8u) >> 2) + 1);
-      nr8 = __ldg(row4 + ((base + 8u) >> 3));
-      ni = __ldg(spIdx + base + 8u + gl);
+      nc0 = ld_meta4(col4 + ((base + 8u) >> 2));
+      nc1 = ld_meta4(col4 + ((base + 8u) >> 2) + 1);
+      nr8 = ld_meta4(row4 + ((base + 8u) >> 3));
+      ni = ld_meta1(spIdx + base + 8u + gl);
     }
     const u32 cols[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
     const u32 rows[8] = {r8.x & 0xFFFFu, r8.x >> 16, r8.y & 0xFFFFu, r8.y >> 16,
                          r8.z & 0xFFFFu, r8.z >> 16, r8.w & 0xFFFFu, r8.w >> 16};
     float acc[8];
+    if constexpr (U > 0) {
+#pragma unroll
+      for (int h = 0; h < 8 / U; ++h) {
+        float4 bq[U][NB];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int t = h * U + u;
+          const u32 e = base + t;
+          const bool live = e >= gBeg && e < gEnd;
+          const float4* __restrict__ b = B4 + (size_t)cols[t] * K4 + gl;
+#pragma unroll
+          for (int j = 0; j < NB; ++j)
+            bq[u][j] = live ? (kHints ? ldg_f4_policy(b + j * 8, polB) : __ldg(b + j * 8)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int t = h * U + u;
+          const float4* a = sA + rows[t] * K4 + gl;
+          float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            const float4 av = a[j * 8], bv = bq[u][j];
+            if (j & 1) {
+              acc1 = fmaf(av.x, bv.x, acc1); acc1 = fmaf(av.y, bv.y, acc1);
+              acc1 = fmaf(av.z, bv.z, acc1); acc1 = fmaf(av.w, bv.w, acc1);
+            } else {
+              acc0 = fmaf(av.x, bv.x, acc0); acc0 = fmaf(av.y, bv.y, acc0);
+              acc0 = fmaf(av.z, bv.z, acc0); acc0 = fmaf(av.w, bv.w, acc0);
+            }
+          }
+          acc[t] = acc0 + acc1;
+        }
+      }
+    } else {
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       const u32 e = base + t;
@@ -201,7 +278,7 @@ k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restri
       if (live && col != prevCol) {  // this group moves on to a new column
         const float4* __restrict__ b = B4 + (size_t)col * K4 + gl;
 #pragma unroll
-        for (int j = 0; j < NB; ++j) breg[j] = __ldg(b + j * 8);
+        for (int j = 0; j < NB; ++j) breg[j] = kHints ? ldg_f4_policy(b + j * 8, polB) : __ldg(b + j * 8);
         prevCol = col;
       }
       const float4* a = sA + rows[t] * K4 + gl;
@@ -218,6 +295,7 @@ k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restri
         }
       }
       acc[t] = acc0 + acc1;
+    }
     }
     // transposing butterfly: 7 shuffles reduce 8 entries over the 8 lanes; lane gl ends with entry gl
     float b4[4], b2[2];
@@ -237,7 +315,10 @@ k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restri
     const float keep = (gl & 1u) ? b2[1] : b2[0];
     const float mine = keep + __shfl_xor_sync(0xffffffffu, send, 1, 8);
     const u32 me = base + gl;
-    if (me >= gBeg && me < gEnd) P[mi] = mine;
+    if (me >= gBeg && me < gEnd) {
+      if (kHints) stg_f32_policy(P + mi, mine, polS);
+      else P[mi] = mine;
+    }
     c0 = nc0; c1 = nc1; r8 = nr8; mi = ni;
   }
 }
@@ -257,32 +338,6 @@ k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restri
 //     a transposing butterfly (31 shuffles per 32 entries) and stores it.  Control flow is warp-uniform.
 // Replaces src/sddmmKernel.cu:1994-2104 / :2109-2199 like the other residual kernels.
 // =============================================================================================
-__device__ __forceinline__ u64 l2_policy_evict_last() {
-  u64 p;
-  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ u64 l2_policy_evict_first() {
-  u64 p;
-  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ float4 ldg_f4_policy(const float4* p, u64 pol) {
-  float4 v;
-  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-      : "l"(p), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ u32 ldg_u32_policy(const u32* p, u64 pol) {
-  u32 v;
-  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ void stg_f32_policy(float* p, float v, u64 pol) {
-  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
-}
-
 template <int LANES, int NB>
 static __global__ void __launch_bounds__(256)
 k_sddmm_residual_stream(const float4* __restrict__ A4, const float4* __restrict__ B4, const u32* __restrict__ stRow,
@@ -1734,13 +1789,27 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
               I.numRows, sp->rows, sp->segLen, sp->off.get(), sp->col.get(), sp->row.get(), sp->idx.get(),
               sp->work.get(), dP, bst);
         };
+        // eviction hints when B (N x K floats) cannot live in the 126 MB L2 next to A and the layout; gather mode
+        // (several B^T rows in flight, no column-run reuse) when a run averages fewer than 1.5 entries
+        static const int hintCfg = [] { const char* e = getenv("SDDMM_B200_L2_HINTS"); return e ? atoi(e) : -1; }();
+        static const int gatherCfg = [] { const char* e = getenv("SDDMM_B200_SP_GATHER"); return e ? atoi(e) : -1; }();
+        const bool hints = hintCfg >= 0 ? hintCfg != 0 : (size_t)I.N * K * 4 > ((size_t)48 << 20);
+        const bool gather = gatherCfg >= 0 ? gatherCfg != 0 : (double)sp->numEntries < 1.5 * (double)sp->numRuns;
+#define SB_SP_CASE(NBv, THRv, Uv)                                                                 \
+  do {                                                                                            \
+    if (gather) { if (hints) launch(k_sddmm_residual_sp<NBv, THRv, true, Uv>, THRv);              \
+                  else launch(k_sddmm_residual_sp<NBv, THRv, false, Uv>, THRv); }                 \
+    else { if (hints) launch(k_sddmm_residual_sp<NBv, THRv, true, 0>, THRv);                      \
+           else launch(k_sddmm_residual_sp<NBv, THRv, false, 0>, THRv); }                         \
+  } while (0)
         switch (K / 32u) {
-          case 1: launch(k_sddmm_residual_sp<1, 1024>, 1024); break;
-          case 2: launch(k_sddmm_residual_sp<2, 1024>, 1024); break;
-          case 4: launch(k_sddmm_residual_sp<4, 1024>, 1024); break;
-          case 8: launch(k_sddmm_residual_sp<8, 512>, 512); break;
-          default: launch(k_sddmm_residual_sp<16, 512>, 512); break;
+          case 1: SB_SP_CASE(1, 1024, 8); break;
+          case 2: SB_SP_CASE(2, 1024, 4); break;
+          case 4: SB_SP_CASE(4, 1024, 2); break;
+          case 8: SB_SP_CASE(8, 512, 2); break;
+          default: SB_SP_CASE(16, 512, 1); break;
         }
+#undef SB_SP_CASE
         SB_LAUNCH_CHECK();
       }
     } else {

@@ -528,10 +528,13 @@ def test_cli_test_mode_sweep_feeds_the_reference_analyser(tmp_path):
     rr = O.row_reorder(S, 0.5, 16)
     cr = O.col_reorder(S, rr["reorderedRows"], 0.3)
     assert seen[(64, 0.5, 0.3)][1] == int(cr["sparseValueOffsets"][-1])
-    # the reference's analyser reads the 140 files
-    r = subprocess.run([ana] + [str(logdir / n) for n in logs], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
-    assert r.returncode == 0, r.stderr[-400:]
+    # the reference's analyser reads the 140 files: one invocation per K (it writes results_<K>.csv for the K of the
+    # records it was given, scripts/analyze_results.cpp:785-789), 35 (alpha, delta) logs each
     for k in (32, 64, 128, 256):
+        mine = [str(logdir / n) for n in logs if n.startswith(f"BSMR_k_{k}_")]
+        assert len(mine) == 35
+        r = subprocess.run([ana] + mine, capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+        assert r.returncode == 0, r.stderr[-400:]
         csv = [l for l in open(logdir / f"results_{k}.csv").read().splitlines() if l]
         assert csv[0].startswith("file,M,N,NNZ,Sparsity,K,BSMR")
         row = csv[1].split(",")
