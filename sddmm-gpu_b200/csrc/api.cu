@@ -195,6 +195,7 @@ int bsmr_row_reorder_dev_ex(const uint32_t* d_rowOff, const uint32_t* d_colIdx, 
                 (opts->batch == 0 || opts->batch == 1 || opts->batch == 2 || opts->batch == 4 || opts->batch == 8),
             "bsmr_reorder_opts holds an unknown selector");
   cudaStream_t s = (cudaStream_t)stream;
+  NvtxRange nvtx("sddmm_b200: row reorder (encode + sort + cluster)");
   Timer t(s);
   t.start();
   row_reorder_dev(d_rowOff, d_colIdx, M, N, nnz, alpha, block_size, opts, d_reorderedRows, numRows, numClusters, nullptr,
@@ -250,6 +251,7 @@ int bsmr_layout_build_dev_ex(const uint32_t* d_rowOff, const uint32_t* d_colIdx,
   require_device();
   require(d_rowOff && d_colIdx && out && (d_reorderedRows || numRows == 0), "null pointer");
   require(flags <= BSMR_BUILD_TILES_NEVER, "flags");
+  NvtxRange nvtx("sddmm_b200: column reorder + RPHM layout");
   *out = layout_build_dev(d_rowOff, d_colIdx, M, N, nnz, d_reorderedRows, numRows, delta, panelBegin, panelEnd, flags,
                           msColReorder, msRphm, (cudaStream_t)stream);
   API_END
@@ -380,6 +382,7 @@ Streams& streams() {
 void run_once(const bsmr_layout* L, u32 K, const float* dA, const float* dB, float* dP, cudaStream_t s,
               u32 numBatch = 1, const sddmm_plan* plan = nullptr) {
   require_layout_device(L);
+  NvtxRange nvtx("sddmm_b200: SDDMM pass");
   sddmm_plan p;
   plan_resolve(L, K, numBatch ? numBatch : 1, plan, &p);
   if (p.plan == SDDMM_PLAN_BSMR && L->numDenseWork && L->numSparseWork) {
@@ -416,6 +419,7 @@ int sddmm_prepare(const bsmr_layout* L, uint32_t K, uint32_t numBatch, const sdd
   sddmm_plan p;
   plan_resolve(L, K, numBatch, plan, &p);
   cudaStream_t s = streams().dense;
+  NvtxRange nvtx("sddmm_b200: prepare (K-dependent private layouts)");
   plan_prepare(L, K, numBatch, p, s);
   SB_CUDA(cudaStreamSynchronize(s));
   API_END

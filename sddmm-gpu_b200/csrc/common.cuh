@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges show up in nsys / ncu --nvtx, cost nothing otherwise
 
 #include <cstdarg>
 #include <cstdint>
@@ -135,6 +136,14 @@ struct Timer {
     SB_CUDA(cudaEventElapsedTime(&ms, a, b));
     return ms;
   }
+};
+
+// NVTX range over a stage of the path (reorder / layout / SDDMM pass), closed when the scope ends
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
 };
 
 inline u32 ceil_div(u32 a, u32 b) { return (a + b - 1) / b; }

@@ -886,25 +886,76 @@ bsmr_layout* layout_load(const char* path) {
     get(fl.f, &L->sparseChunk, 1);
     get(fl.f, &L->numDenseWork, 1);
     get(fl.f, &L->numSparseWork, 1);
-    std::vector<u32> host;
+    // Every array is read to the host first and cross-checked before anything reaches the device: a truncated,
+    // stale or foreign file must end in SDDMM_E_ARG, never in out-of-bounds reads inside the kernels.
+    std::vector<std::vector<u32>> H(BSMR_ARRAY_COUNT);
     for (int i = 0; i < BSMR_ARRAY_COUNT; ++i) {
       u64 n = 0;
       get(fl.f, &n, 1);
       if (n > ((u64)1 << 34)) fail(SDDMM_E_ARG, "layout cache: implausible array length");
-      host.resize(n);
-      get(fl.f, host.data(), n);
+      H[i].resize(n);
+      get(fl.f, H[i].data(), n);
+    }
+    std::vector<uint2> wd(L->numDenseWork <= ((u32)1 << 30) ? L->numDenseWork : 0), ws;
+    if (wd.size() != L->numDenseWork) fail(SDDMM_E_ARG, "layout cache: implausible work-list length");
+    get(fl.f, wd.data(), wd.size());
+    if (L->numSparseWork > ((u32)1 << 30)) fail(SDDMM_E_ARG, "layout cache: implausible work-list length");
+    ws.resize(L->numSparseWork);
+    get(fl.f, ws.data(), ws.size());
+    {
+      const bsmr_layout_info& I = L->info;
+      const u64 P = I.numRowPanels;
+      auto bad = [](const char* what) { fail(SDDMM_E_ARG, "layout cache: inconsistent file (%s)", what); };
+      auto len = [&](bsmr_array_id id) { return (u64)H[id].size(); };
+      auto monotone = [&](bsmr_array_id id, u64 last, const char* what) {
+        const auto& v = H[id];
+        if (v.size() != P + 1 || v[0] != 0 || v[P] != last) bad(what);
+        for (u64 i = 0; i < P; ++i) if (v[i] > v[i + 1]) bad(what);
+      };
+      auto below = [&](bsmr_array_id id, u64 limit, bool allowNull, const char* what) {
+        for (u32 x : H[id]) if (x >= limit && !(allowNull && x == kNull)) bad(what);
+      };
+      if (P != ((u64)I.numRows + kPanel - 1) / kPanel || len(BSMR_REORDERED_ROWS) != I.numRows) bad("row count");
+      below(BSMR_REORDERED_ROWS, I.M, false, "reorderedRows");
+      monotone(BSMR_DENSE_COL_OFFSETS, len(BSMR_DENSE_COLS), "denseColOffsets");
+      monotone(BSMR_SPARSE_COL_OFFSETS, len(BSMR_SPARSE_COLS), "sparseColOffsets");
+      monotone(BSMR_SPARSE_VALUE_OFFSETS, I.numSparseValues, "sparseValueOffsets");
+      monotone(RPHM_BLOCK_OFFSETS, I.numDenseBlocks, "blockOffsets");
+      if (len(RPHM_SPARSE_VALUES) != I.numSparseValues || len(RPHM_SPARSE_RELATIVE_ROWS) != I.numSparseValues ||
+          len(RPHM_SPARSE_COL_INDICES) != I.numSparseValues || len(RPHM_BLOCK_VALUES) != (u64)I.numDenseBlocks * 256u ||
+          len(BSMR_DENSE_COLS) != (u64)I.numDenseBlocks * 16u)
+        bad("array lengths");
+      for (u64 p = 0; p <= P; ++p)
+        if ((u64)H[RPHM_BLOCK_OFFSETS][p] * 16u != H[BSMR_DENSE_COL_OFFSETS][p]) bad("block / dense column offsets");
+      below(BSMR_DENSE_COLS, (u64)I.N + 1, false, "denseCols");
+      below(BSMR_SPARSE_COLS, (u64)I.N + 1, false, "sparseCols");
+      below(RPHM_SPARSE_COL_INDICES, I.N, false, "sparseColIndices");
+      below(RPHM_SPARSE_RELATIVE_ROWS, kPanel, false, "sparseRelativeRows");
+      below(RPHM_SPARSE_VALUES, I.nnz, false, "sparseValues");
+      below(RPHM_BLOCK_VALUES, I.nnz, true, "blockValues");
+      if (len(RPHM_DENSE_ROW_PANEL_IDS) != I.numDenseThreadBlocks || len(RPHM_DENSE_COL_BLOCK_ITERS) != I.numDenseThreadBlocks ||
+          len(RPHM_SPARSE_ROW_PANEL_IDS) != I.numSparseThreadBlocks || len(RPHM_SPARSE_COL_BLOCK_ITERS) != I.numSparseThreadBlocks)
+        bad("reference work lists");
+      below(RPHM_DENSE_ROW_PANEL_IDS, P, false, "denseRowPanelIds");
+      below(RPHM_SPARSE_ROW_PANEL_IDS, P, false, "sparseRowPanelIds");
+      if (L->sparseChunk < 32 || L->sparseChunk > 65536) bad("sparseChunk");
+      for (const uint2& w : wd)
+        if (w.x >= P || w.y >= H[RPHM_BLOCK_OFFSETS][w.x + 1] - H[RPHM_BLOCK_OFFSETS][w.x]) bad("dense work list");
+      for (const uint2& w : ws)
+        if (w.x >= P || w.y >= H[BSMR_SPARSE_VALUE_OFFSETS][w.x + 1] - H[BSMR_SPARSE_VALUE_OFFSETS][w.x]) bad("residual work list");
+      if ((u64)I.numDenseValues + I.numSparseValues > I.nnz) bad("entry counts");
+    }
+    for (int i = 0; i < BSMR_ARRAY_COUNT; ++i) {
+      const u64 n = H[i].size();
       L->arr[i].alloc(n ? n : 1, true);
       L->arr[i].n = n;
-      if (n) SB_CUDA(cudaMemcpy(L->arr[i].get(), host.data(), n * 4, cudaMemcpyHostToDevice));
+      if (n) SB_CUDA(cudaMemcpy(L->arr[i].get(), H[i].data(), n * 4, cudaMemcpyHostToDevice));
     }
-    std::vector<uint2> w(L->numDenseWork);
-    get(fl.f, w.data(), w.size());
     L->denseWork.alloc(L->numDenseWork ? L->numDenseWork : 1, true);
-    if (L->numDenseWork) SB_CUDA(cudaMemcpy(L->denseWork.get(), w.data(), w.size() * 8, cudaMemcpyHostToDevice));
-    w.resize(L->numSparseWork);
-    get(fl.f, w.data(), w.size());
+    if (L->numDenseWork) SB_CUDA(cudaMemcpy(L->denseWork.get(), wd.data(), wd.size() * 8, cudaMemcpyHostToDevice));
     L->sparseWork.alloc(L->numSparseWork ? L->numSparseWork : 1, true);
-    if (L->numSparseWork) SB_CUDA(cudaMemcpy(L->sparseWork.get(), w.data(), w.size() * 8, cudaMemcpyHostToDevice));
+    if (L->numSparseWork) SB_CUDA(cudaMemcpy(L->sparseWork.get(), ws.data(), ws.size() * 8, cudaMemcpyHostToDevice));
+    std::vector<u32> host;
     u32 hasTl = 0;
     get(fl.f, &hasTl, 1);
     if (hasTl) {
@@ -921,8 +972,14 @@ bsmr_layout* layout_load(const char* path) {
       get(fl.f, host.data(), host.size());
       T->rowMeta.alloc(host.size() ? host.size() : 1, true);
       if (!host.empty()) SB_CUDA(cudaMemcpy(T->rowMeta.get(), host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+      if ((u64)T->numEntries > L->info.nnz) fail(SDDMM_E_ARG, "layout cache: inconsistent file (tile entries)");
+      for (const uint4& t : tiles)
+        if (t.x >= T->tileRows || t.y >= T->tileCols || (u64)t.z + t.w > T->numEntries || t.w > 16384u)
+          fail(SDDMM_E_ARG, "layout cache: inconsistent file (tile records)");
       host.resize(T->numEntries);
       get(fl.f, host.data(), host.size());
+      for (u32 x : host)
+        if (x >= L->info.nnz) fail(SDDMM_E_ARG, "layout cache: inconsistent file (tile CSR indices)");
       T->idx.alloc(host.size() ? host.size() : 1, true);
       if (!host.empty()) SB_CUDA(cudaMemcpy(T->idx.get(), host.data(), host.size() * 4, cudaMemcpyHostToDevice));
       build_quads(*T);

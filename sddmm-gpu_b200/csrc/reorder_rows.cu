@@ -894,9 +894,10 @@ static __global__ void __launch_bounds__(kCbThreads, 1) k_cluster_batched(Cluste
         cb_apply_join<TG>(a, rep, repSig, sPop, sSs, sS1, sRed, f, jk);
         g = newG;
         p = f + 1;
-        // rows tend to join in streaks and only the first joiner of a window counts: look at a few
-        // candidates right behind it (one per CTA), then widen again while nothing joins
-        chunk = gridDim.x * unit;
+        // rows tend to join in streaks and only the first joiner of a window counts: look at the candidates right
+        // behind it, then widen again while nothing joins.  A window costs its latency (one evaluation + one grid
+        // barrier, ~10-20 us), not its width, so the first window after a join already uses a quarter of the warps.
+        chunk = gridDim.x * (kCbWarps / 4) * unit;
         calm = false;
       } else {
         p = e;

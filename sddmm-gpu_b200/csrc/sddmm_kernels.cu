@@ -1286,7 +1286,9 @@ static __global__ void __launch_bounds__(256) k_round_dense_rows(u32 M, u32 K4, 
   }
 }
 
-static __global__ void __launch_bounds__(kDnThreads)
+constexpr int kDtThreads = 160;  // warps 0-3: TMA producers + epilogue (the 4 TMEM lane quarters), warp 4: MMA issuer
+
+static __global__ void __launch_bounds__(kDtThreads)
 k_sddmm_dense_tma(const __grid_constant__ CUtensorMap mapA16, const __grid_constant__ CUtensorMap mapBg, u32 K,
                   u32 numCompactCols, const u32* __restrict__ colCompact, const u32* __restrict__ blockOffsets,
                   const u32* __restrict__ blockValues, const uint2* __restrict__ work,
@@ -1312,7 +1314,7 @@ k_sddmm_dense_tma(const __grid_constant__ CUtensorMap mapA16, const __grid_const
   }
   if (tid == 32) {
     for (u32 s = 0; s < kDtStages; ++s) {
-      mbar_init(&fullBar[s], 1);
+      mbar_init(&fullBar[s], 4);  // one arrive.expect_tx per producer warp
       mbar_init(&emptyBar[s], 1);
     }
     mbar_init(&accBar, 1);
@@ -1325,31 +1327,36 @@ k_sddmm_dense_tma(const __grid_constant__ CUtensorMap mapA16, const __grid_const
   const u32 numChunks = (K + kDnKChunk - 1) / kDnKChunk;
   constexpr u32 idesc = umma_idesc_tf32(128, 16);
 
-  if (warp == 0) {
-    // ---- producer: lane l owns gathered rows 4l .. 4l+3 of the stage.  Slots past the group's last block and
+  if (warp < 4) {
+    // ---- producers: warp q feeds gathered rows 32q .. 32q+31 of every stage, lanes 0..7 one tile::gather4 each
+    // (4 row indices per instruction); warp 0 adds the panel's A box.  Slots past the group's last block and
     // sentinel columns read compact row 0: their accumulator lanes are never stored (blockValues holds NULL
     // there) and every TMEM lane depends on its own row only.
-    u32 rows[4];
+    u32 rows[4] = {0u, 0u, 0u, 0u};
     const u32 rowBase = blockIdx.y * numCompactCols;  // batch b's copy starts at row b * numCompactCols
+    if (lane < 8u) {
 #pragma unroll
-    for (u32 i = 0; i < 4; ++i) {
-      const u32 slot = lane * 4u + i;
-      rows[i] = rowBase + (slot < nBlk * 16u ? __ldg(colCompact + colBase + slot) : 0u);
+      for (u32 i = 0; i < 4; ++i) {
+        const u32 slot = warp * 32u + lane * 4u + i;
+        rows[i] = rowBase + (slot < nBlk * 16u ? __ldg(colCompact + colBase + slot) : 0u);
+      }
     }
     const u32 aRow = workRowA[blockIdx.x];
+    const u32 myBytes = 32u * 128u + (warp == 0 ? 16u * 128u : 0u);
     for (u32 kc = 0; kc < numChunks; ++kc) {
       const u32 s = kc % kDtStages;
       const u32 bar = smem_u32(&fullBar[s]);
       const u32 dst = smem_u32(stages + s * kDnStageBytes);
       if (lane == 0) {
         if (kc >= kDtStages) mbar_wait_bounded(&emptyBar[s], ((kc / kDtStages) - 1) & 1u);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kDnStageBytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(myBytes) : "memory");
       }
       __syncwarp();
-      tma_gather4_2d(dst + lane * 512u, &mapBg, bar, kc * kDnKChunk, rows[0], rows[1], rows[2], rows[3]);
-      if (lane == 0) tma_load_3d(dst + kDnRowsB * 128u, &mapA16, bar, kc * kDnKChunk, aRow, blockIdx.y);
+      if (lane < 8u)
+        tma_gather4_2d(dst + (warp * 32u + lane * 4u) * 128u, &mapBg, bar, kc * kDnKChunk, rows[0], rows[1], rows[2], rows[3]);
+      if (warp == 0 && lane == 0) tma_load_3d(dst + kDnRowsB * 128u, &mapA16, bar, kc * kDnKChunk, aRow, blockIdx.y);
     }
-  } else if (warp == 1) {
+  } else {
     for (u32 kc = 0; kc < numChunks; ++kc) {
       const u32 s = kc % kDtStages;
       if (lane == 0) {
@@ -1378,26 +1385,27 @@ k_sddmm_dense_tma(const __grid_constant__ CUtensorMap mapA16, const __grid_const
       __syncwarp();
     }
   }
-  mbar_wait_bounded(&accBar, 0u);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-  // ---- epilogue: TMEM lane = gathered column slot j, register n = panel row
-  u32 acc[16];
-  const u32 taddr = tmem + ((warp * 32u) << 16);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]), "=r"(acc[7]),
-        "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]), "=r"(acc[14]),
-        "=r"(acc[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  if (tid < nBlk * 16u) {
-    const u32* bv = blockValues + ((size_t)(blkBeg + firstBlk) + (tid >> 4)) * 256u + (tid & 15u);
+  if (warp < 4) {
+    mbar_wait_bounded(&accBar, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- epilogue: TMEM lane = gathered column slot j, register n = panel row
+    u32 acc[16];
+    const u32 taddr = tmem + ((warp * 32u) << 16);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]), "=r"(acc[7]),
+          "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]), "=r"(acc[14]),
+          "=r"(acc[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (tid < nBlk * 16u) {
+      const u32* bv = blockValues + ((size_t)(blkBeg + firstBlk) + (tid >> 4)) * 256u + (tid & 15u);
 #pragma unroll
-    for (u32 r = 0; r < 16; ++r) {
-      const u32 idx = __ldg(bv + r * 16u);
-      if (idx != kNull) P[idx] = __uint_as_float(acc[r]);
+      for (u32 r = 0; r < 16; ++r) {
+        const u32 idx = __ldg(bv + r * 16u);
+        if (idx != kNull) P[idx] = __uint_as_float(acc[r]);
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1619,9 +1627,11 @@ void plan_resolve(const bsmr_layout* L, u32 K, u32 numBatch, const sddmm_plan* i
         else {
           // expected entries per (super-panel, column) run: below ~1.5 a fetched B^T row is not reused from
           // registers and the super-panel kernel only pays for its shared-memory staging -> row-stream kernel
-          const double rowsSp = 16.0 * G;
-          const double run = 1.0 + rowsSp * (double)I.numSparseValues / ((double)(I.numRows ? I.numRows : 1) * (double)I.N);
-          p.residual = run >= 1.5 ? SDDMM_RESIDUAL_SUPERPANEL : SDDMM_RESIDUAL_STREAM;
+          // the row-stream kernel stays opt-in: measured on R-MAT scale 22 it is slower than the super-panel kernel at
+          // every K (2.35 / 4.0 / 6.4 / 9.1 / 15.4 ms vs 2.07 / 2.46 / 3.58 / 7.5 / 15.5 ms at K = 32 ... 512; its
+          // per-row A fragment loads are exposed and it issues twice the instructions), and on uniform 100k^2
+          // (3.86 vs 3.24 ms at K=128)
+          p.residual = SDDMM_RESIDUAL_SUPERPANEL;
         }
       }
       if (p.residual == SDDMM_RESIDUAL_PANEL && (size_t)16 * K * sizeof(float) > 200 * 1024)
@@ -1739,7 +1749,7 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
       SB_LAUNCH_CHECK();
       const size_t smem = (size_t)kDtStages * kDnStageBytes + 1024;
       set_smem(k_sddmm_dense_tma, smem);
-      k_sddmm_dense_tma<<<dim3(L->numDenseWork, numBatch), kDnThreads, smem, denseStream>>>(
+      k_sddmm_dense_tma<<<dim3(L->numDenseWork, numBatch), kDtThreads, smem, denseStream>>>(
           *reinterpret_cast<const CUtensorMap*>(t->mapA16), *reinterpret_cast<const CUtensorMap*>(t->mapBg), K,
           d->numCols ? d->numCols : 1u, d->colCompact.get(), arr(RPHM_BLOCK_OFFSETS), arr(RPHM_BLOCK_VALUES),
           L->denseWork.get(), d->workRowA.get(), dP, bst.p);
@@ -1794,7 +1804,10 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
         static const int hintCfg = [] { const char* e = getenv("SDDMM_B200_L2_HINTS"); return e ? atoi(e) : -1; }();
         static const int gatherCfg = [] { const char* e = getenv("SDDMM_B200_SP_GATHER"); return e ? atoi(e) : -1; }();
         const bool hints = hintCfg >= 0 ? hintCfg != 0 : (size_t)I.N * K * 4 > ((size_t)48 << 20);
-        const bool gather = gatherCfg >= 0 ? gatherCfg != 0 : (double)sp->numEntries < 1.5 * (double)sp->numRuns;
+        // measured on R-MAT scale 22: gather mode 2.07 -> 1.17 ms at K=32 and 2.46 -> 2.03 ms at K=64, but 3.58 -> 4.00
+        // ms at K=128 and worse above (there one row per 8 lanes already keeps 64 KB per SM in flight and the L2
+        // fabric, ~8.5 TB/s of gathered rows, is the limit), hence K <= 64
+        const bool gather = gatherCfg >= 0 ? gatherCfg != 0 : (K <= 64 && (double)sp->numEntries < 1.5 * (double)sp->numRuns);
 #define SB_SP_CASE(NBv, THRv, Uv)                                                                 \
   do {                                                                                            \
     if (gather) { if (hints) launch(k_sddmm_residual_sp<NBv, THRv, true, Uv>, THRv);              \
