@@ -426,6 +426,16 @@ def record_rmat(ctx, w, headline=True, scale=None, K=None, reorder=True, steps=N
     torch.cuda.synchronize()
     bcast_ms = e0.elapsed_time(e1)
     dP = torch.zeros(max(1, nnz), dtype=torch.float32, device="cuda")
+    # cost-calibrated cuts (setup, like the reordering): equal nnz is not equal time on a power-law graph
+    cut_history = []
+    if ctx.world > 1 and args.rebalance > 0:
+        cut_history = sh.calibrate(dA, dB, dP, rounds=args.rebalance)
+        lay, info = sh.layout, sh.layout.info
+        my_nnz = sh.my_nnz
+        tot = ctx.sum_over_ranks([float(my_nnz)])
+        assert int(tot[0]) == nnz, f"rebalanced shards cover {int(tot[0])} of {nnz} stored entries"
+        mx_nnz = ctx.max_over_ranks([float(my_nnz)])[0]
+        dP.zero_()
     pkg.sddmm_prepare(lay, K)
 
     sampler = ClockSampler(ctx.local)
@@ -529,7 +539,8 @@ def record_rmat(ctx, w, headline=True, scale=None, K=None, reorder=True, steps=N
         desc = w["desc"] + f", scale {scale}"
         cfg = base_config(desc, M, N, nnz, K, alpha, delta)
         cfg.update(block_size=int(bs), reordered=bool(reorder), parallelism=f"one matrix, nnz-balanced row-panel ranges x{ctx.world}, B replicated once (NCCL), no steady-state collective",
-                   largest_shard_nnz_share=mx_nnz / max(1, nnz), l2="working set (A+B+layout+P) >> 126 MB L2, no flush between steps",
+                   largest_shard_nnz_share=mx_nnz / max(1, nnz), rebalance_rounds=len(cut_history),
+                   panel_cuts=[int(c) for c in sh.cuts], l2="working set (A+B+layout+P) >> 126 MB L2, no flush between steps",
                    num_row_panels_rank0=int(info.numRowPanels), num_clusters=int(sh.num_clusters),
                    dense_blocks_rank0=int(info.numDenseBlocks), dense_nnz_rank0=int(info.numDenseValues),
                    residual_nnz_rank0=int(info.numSparseValues), row_reorder_ms=sh.row_ms, col_reorder_ms=sh.col_ms,
@@ -722,6 +733,7 @@ def main():
     ap.add_argument("--cpu-gflop", type=float, default=8.0, help="GFLOP of work in the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="headline record only")
+    ap.add_argument("--rebalance", type=int, default=2, help="cost-calibration rounds of the panel cuts (N > 1)")
     ap.add_argument("--cfg5", type=int, default=1, help="also run config 5 (R-MAT scale 25, K=256) at this N")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

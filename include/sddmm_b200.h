@@ -332,6 +332,18 @@ void sddmm_mgpu_destroy(sddmm_mgpu*);
 int sddmm_mgpu_shard(sddmm_mgpu*, const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N,
                      uint32_t nnz, uint32_t* d_reorderedRows, uint32_t* numRows, float delta, uint32_t flags,
                      bsmr_layout** out, uint32_t* h_cuts, float* msColReorder, float* msRphm, void* stream);
+/* Cost calibration of the cuts (optional, collective): equal non-zero counts are not equal times when the shards'
+ * B^T rows hit the L2 at different rates (power-law graphs: the shard holding the hub rows is cheaper per non-zero).
+ * Every rank passes the device time of its last pass(es); a non-zero of shard r is charged ms_r / nnz_r, the cuts
+ * move so that every rank's estimated time is equal, and this rank's layout is rebuilt when its range changed
+ * (*layout is destroyed and replaced).  One or two rounds settle it; not part of the steady state. */
+int sddmm_mgpu_rebalance(sddmm_mgpu*, const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N,
+                         uint32_t nnz, const uint32_t* d_reorderedRows, uint32_t numRows, float delta, uint32_t flags,
+                         float myMs, bsmr_layout** layout, uint32_t* h_cuts, void* stream);
+/* the rule sddmm_mgpu_rebalance applies, on host arrays (no device, no communicator): prefix[numPanels + 1] of the
+ * per-panel non-zero counts, the old cuts, the measured time of every shard -> new cuts (numShards + 1 entries) */
+int bsmr_rebalance_cuts(const uint64_t* h_panelNnzPrefix, uint32_t numPanels, const uint32_t* h_oldCuts,
+                        const float* h_ms, uint32_t numShards, uint32_t* h_newCuts);
 int sddmm_mgpu_bcast(sddmm_mgpu*, void* d_buf, size_t bytes, int root, void* stream);
 int sddmm_mgpu_run(sddmm_mgpu*, const bsmr_layout*, uint32_t K, const float* d_A, const float* d_B, float* d_P,
                    void* stream);

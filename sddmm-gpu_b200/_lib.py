@@ -130,6 +130,8 @@ def lib():
     L.sddmm_mgpu_destroy.argtypes = [vp]
     L.sddmm_mgpu_destroy.restype = None
     L.sddmm_mgpu_shard.argtypes = [vp, vp, vp, u32, u32, u32, vp, pu32, f32, u32, C.POINTER(vp), vp, pf32, pf32, vp]
+    L.sddmm_mgpu_rebalance.argtypes = [vp, vp, vp, u32, u32, u32, vp, u32, f32, u32, f32, C.POINTER(vp), vp, vp]
+    L.bsmr_rebalance_cuts.argtypes = [vp, u32, vp, vp, u32, vp]
     L.sddmm_mgpu_bcast.argtypes = [vp, vp, C.c_size_t, C.c_int, vp]
     L.sddmm_mgpu_run.argtypes = [vp, vp, u32, vp, vp, vp, vp]
     L.sddmm_mgpu_gather.argtypes = [vp, vp, C.c_size_t, vp]

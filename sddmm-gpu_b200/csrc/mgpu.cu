@@ -95,7 +95,8 @@ void shard_cuts_from_prefix(const std::vector<u64>& pre, u32 numShards, u32* cut
   cuts[numShards] = P;
 }
 
-void shard_plan_dev(const u32* d_rowOff, const u32* d_R, u32 numRows, u32 numShards, u32* cuts, cudaStream_t s) {
+void shard_plan_dev(const u32* d_rowOff, const u32* d_R, u32 numRows, u32 numShards, u32* cuts, cudaStream_t s,
+                    std::vector<u64>* preOut = nullptr) {
   const u32 P = (numRows + kPanel - 1) / kPanel;
   std::vector<u64> pre((size_t)P + 1, 0);
   if (P) {
@@ -108,6 +109,39 @@ void shard_plan_dev(const u32* d_rowOff, const u32* d_R, u32 numRows, u32 numSha
     for (u32 p = 0; p < P; ++p) pre[p + 1] = pre[p] + h[p];
   }
   shard_cuts_from_prefix(pre, numShards, cuts);
+  if (preOut) *preOut = std::move(pre);
+}
+
+// Cost-calibrated cuts: shard r took ms[r] for its pre[cuts[r+1]] - pre[cuts[r]] non-zeros, so a non-zero of that
+// range is charged ms[r] / nnz_r; the new cuts give every rank the same estimated time.
+void rebalance_cuts(const std::vector<u64>& pre, const std::vector<u32>& oldCuts, const std::vector<float>& ms,
+                    std::vector<u32>& newCuts) {
+  const u32 world = (u32)ms.size(), P = (u32)pre.size() - 1;
+  std::vector<double> dens(world, 0.0);
+  double total = 0.0;
+  for (u32 r = 0; r < world; ++r) {
+    const double n = (double)(pre[oldCuts[r + 1]] - pre[oldCuts[r]]);
+    dens[r] = n > 0 ? (double)ms[r] / n : 0.0;
+    total += n > 0 ? (double)ms[r] : 0.0;
+  }
+  newCuts.assign((size_t)world + 1, 0);
+  newCuts[world] = P;
+  double acc = 0.0;
+  u32 s = 1, r = 0;
+  for (u32 p = 0; p < P && s < world; ++p) {
+    while (r + 1 < world && p >= oldCuts[r + 1]) ++r;
+    const double c = dens[r] * (double)(pre[p + 1] - pre[p]);
+    const double target = total * s / world;
+    if (acc + c >= target) {
+      // cut before or after panel p, whichever lands closer to the target
+      newCuts[s] = (target - acc < acc + c - target) ? p : p + 1;
+      if (newCuts[s] < newCuts[s - 1]) newCuts[s] = newCuts[s - 1];
+      ++s;
+      if (s < world && acc + c >= total * s / world) { --p; continue; }  // a heavy panel can close several shards
+    }
+    acc += c;
+  }
+  for (; s < world; ++s) newCuts[s] = P;
 }
 
 }  // namespace sb
@@ -118,6 +152,7 @@ struct sddmm_mgpu {
   int rank = 0, world = 1, device = 0;
   void* comm = nullptr;
   std::vector<u32> cuts;
+  std::vector<u64> pre;  // prefix sum of per-panel non-zero counts of the reordered matrix (kept for rebalancing)
 };
 
 #define API_BEGIN try {
@@ -197,10 +232,39 @@ int sddmm_mgpu_shard(sddmm_mgpu* g, const uint32_t* d_rowOff, const uint32_t* d_
                  "ncclBroadcast(reorderedRows)");
   }
   g->cuts.assign((size_t)g->world + 1, 0);
-  shard_plan_dev(d_rowOff, d_reorderedRows, *numRows, (u32)g->world, g->cuts.data(), s);
+  shard_plan_dev(d_rowOff, d_reorderedRows, *numRows, (u32)g->world, g->cuts.data(), s, &g->pre);
   if (h_cuts) std::memcpy(h_cuts, g->cuts.data(), g->cuts.size() * 4);
   *out = layout_build_dev(d_rowOff, d_colIdx, M, N, nnz, d_reorderedRows, *numRows, delta, g->cuts[g->rank],
                           g->cuts[g->rank + 1], flags, msColReorder, msRphm, s);
+  API_END
+}
+
+int sddmm_mgpu_rebalance(sddmm_mgpu* g, const uint32_t* d_rowOff, const uint32_t* d_colIdx, uint32_t M, uint32_t N,
+                         uint32_t nnz, const uint32_t* d_reorderedRows, uint32_t numRows, float delta, uint32_t flags,
+                         float myMs, bsmr_layout** layout, uint32_t* h_cuts, void* stream) {
+  API_BEGIN
+  need(g && d_rowOff && d_colIdx && d_reorderedRows && layout && *layout && myMs >= 0.f, "arguments");
+  need(g->cuts.size() == (size_t)g->world + 1 && !g->pre.empty(), "sddmm_mgpu_shard must come first");
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<float> ms((size_t)g->world, 0.f);
+  ms[g->rank] = myMs;
+  if (g->world > 1) {  // every rank learns every rank's time: a sum over one-hot vectors
+    DevBuf<float> d((size_t)g->world);
+    SB_CUDA(cudaMemcpyAsync(d.get(), ms.data(), ms.size() * 4, cudaMemcpyHostToDevice, s));
+    nccl_check(nccl().AllReduce(d.get(), d.get(), ms.size(), kNcclFloat32, kNcclSum, g->comm, s), "ncclAllReduce(times)");
+    SB_CUDA(cudaMemcpyAsync(ms.data(), d.get(), ms.size() * 4, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+  }
+  std::vector<u32> nc;
+  rebalance_cuts(g->pre, g->cuts, ms, nc);
+  if (h_cuts) std::memcpy(h_cuts, nc.data(), nc.size() * 4);
+  if (nc != g->cuts) {
+    bsmr_layout* fresh = layout_build_dev(d_rowOff, d_colIdx, M, N, nnz, d_reorderedRows, numRows, delta, nc[g->rank],
+                                          nc[g->rank + 1], flags, nullptr, nullptr, s);
+    bsmr_layout_destroy(*layout);
+    *layout = fresh;
+    g->cuts = nc;
+  }
   API_END
 }
 
@@ -217,6 +281,20 @@ int sddmm_mgpu_gather(sddmm_mgpu* g, float* d_P, size_t count, void* stream) {
   // shards write disjoint CSR positions and leave the rest untouched: with P zero-initialised a sum IS the merge
   if (g->world > 1 && count)
     nccl_check(nccl().AllReduce(d_P, d_P, count, kNcclFloat32, kNcclSum, g->comm, (cudaStream_t)stream), "ncclAllReduce");
+  API_END
+}
+
+int bsmr_rebalance_cuts(const uint64_t* h_panelNnzPrefix, uint32_t numPanels, const uint32_t* h_oldCuts,
+                        const float* h_ms, uint32_t numShards, uint32_t* h_newCuts) {
+  API_BEGIN
+  need(h_panelNnzPrefix && h_oldCuts && h_ms && h_newCuts && numShards > 0, "arguments");
+  need(h_oldCuts[0] == 0 && h_oldCuts[numShards] == numPanels, "old cuts must span [0, numPanels]");
+  for (uint32_t r = 0; r < numShards; ++r) need(h_oldCuts[r] <= h_oldCuts[r + 1] && h_ms[r] >= 0.f, "old cuts / times");
+  std::vector<u64> pre(h_panelNnzPrefix, h_panelNnzPrefix + (size_t)numPanels + 1);
+  std::vector<u32> oc(h_oldCuts, h_oldCuts + (size_t)numShards + 1), nc;
+  std::vector<float> ms(h_ms, h_ms + numShards);
+  rebalance_cuts(pre, oc, ms, nc);
+  std::memcpy(h_newCuts, nc.data(), nc.size() * 4);
   API_END
 }
 

@@ -94,6 +94,21 @@ class MultiGpu:
                                           C.byref(msR), C.c_void_p(stream)))
         return host.Layout(h.value), cuts, int(n.value), msC.value, msR.value
 
+    def rebalance(self, layout, row_off_t, col_idx_t, M, N, reordered_rows_t, num_rows, delta, my_ms, tiles="auto"):
+        """sddmm_mgpu_rebalance (collective): move the panel cuts so that every rank's estimated time is equal, given
+        the device time `my_ms` of this rank's last pass.  Returns (layout, cuts); the old layout object is consumed."""
+        import torch
+
+        cuts = np.zeros(self.world + 1, dtype=np.uint32)
+        h = C.c_void_p(layout.handle.value)
+        layout._h = None  # ownership moves into the call (it destroys / replaces the layout)
+        stream = torch.cuda.current_stream().cuda_stream
+        check(_lib.lib().sddmm_mgpu_rebalance(self._h, row_off_t.data_ptr(), col_idx_t.data_ptr(), M, N,
+                                              col_idx_t.numel(), reordered_rows_t.data_ptr(), int(num_rows), float(delta),
+                                              _lib.BUILD_TILES[tiles], float(my_ms), C.byref(h), cuts.ctypes.data,
+                                              C.c_void_p(stream)))
+        return host.Layout(h.value), cuts
+
     def bcast(self, tensor, root=0):
         """sddmm_mgpu_bcast: one replication of a device tensor (B) from `root`, on the current stream."""
         import torch
@@ -143,6 +158,7 @@ class ShardedSDDMM:
             R[:n] = Rr
         self.layout, self.cuts, self.num_rows, self.col_ms, self.rphm_ms = mg.shard(row_off_t, col_idx_t, M, N, R, n,
                                                                                    delta, tiles)
+        self._ro, self._ci, self._Rfull, self._delta, self._tiles = row_off_t, col_idx_t, R, delta, tiles
         self.R = R[: self.num_rows]
         self.reordered = bool(reorder)
         info = self.layout.info
@@ -150,6 +166,30 @@ class ShardedSDDMM:
 
     def replicate_B(self, B):
         return self.mg.bcast(B, 0)
+
+    def calibrate(self, dA, dB, dP, rounds=2, passes=3):
+        """Cost-calibrated cuts: time `passes` passes on every rank, let sddmm_mgpu_rebalance move the cuts, repeat.
+        Setup work like the reordering itself (not part of a timed step).  Returns the per-round cuts."""
+        import torch
+
+        history = []
+        for _ in range(rounds):
+            host.sddmm_prepare(self.layout, dA.shape[1])
+            self.run(dA, dB, dP)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(passes):
+                self.run(dA, dB, dP)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / passes
+            self.layout, self.cuts = self.mg.rebalance(self.layout, self._ro, self._ci, self.M, self.N, self._Rfull,
+                                                       self.num_rows, self._delta, ms, self._tiles)
+            info = self.layout.info
+            self.my_nnz = int(info.numDenseValues) + int(info.numSparseValues)
+            history.append([int(c) for c in self.cuts])
+        return history
 
     def run(self, dA, dB, dP):
         return self.mg.run(self.layout, dA, dB, dP)

@@ -99,3 +99,36 @@ def test_two_rank_shard_broadcast_merge():
     total = res[0][3]
     assert res[0][2] + res[1][2] == total              # shards cover every non-zero exactly once
     assert abs(res[0][2] - res[1][2]) < 0.2 * total    # balanced by nnz
+
+
+def test_rebalance_cuts_equalises_estimated_time():
+    """bsmr_rebalance_cuts (the rule behind sddmm_mgpu_rebalance), host only: with a cost per non-zero that differs
+    between the old shards, the new cuts equalise the estimated time; equal times leave balanced cuts alone."""
+    sys.path.insert(0, ROOT)
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    L = pkg.lib()
+    rng = np.random.default_rng(5)
+    P, world = 4000, 4
+    cnt = rng.integers(1, 400, P).astype(np.uint64)
+    pre = np.zeros(P + 1, np.uint64)
+    np.cumsum(cnt, out=pre[1:])
+    old = np.array([0, 1000, 2000, 3000, P], np.uint32)
+    true_cost = np.where(np.arange(P) < 1500, 3.0, 1.0) * cnt  # the first 1500 panels cost 3x per non-zero
+    for _ in range(4):  # a few rounds settle it (the cost density inside an old shard is not uniform)
+        ms = np.array([true_cost[old[r]:old[r + 1]].sum() for r in range(world)], np.float32)
+        new = np.zeros(world + 1, np.uint32)
+        assert L.bsmr_rebalance_cuts(pre.ctypes.data, P, old.ctypes.data, ms.ctypes.data, world, new.ctypes.data) == 0
+        assert new[0] == 0 and new[-1] == P and np.all(np.diff(new.astype(np.int64)) >= 0)
+        old = new
+    t = np.array([true_cost[old[r]:old[r + 1]].sum() for r in range(world)])
+    assert t.max() / t.mean() < 1.03, t
+    # already balanced: unchanged up to one panel
+    ms = np.array([float(pre[old[r + 1]] - pre[old[r]]) for r in range(world)], np.float32)
+    nnz_cuts = np.zeros(world + 1, np.uint32)
+    eq = np.array([0, 0, 0, 0, P], np.uint32)
+    for s in range(1, world):
+        eq[s] = int(np.searchsorted(pre, int(pre[-1]) * s // world))
+    ms = np.array([float(pre[eq[r + 1]] - pre[eq[r]]) for r in range(world)], np.float32)
+    assert L.bsmr_rebalance_cuts(pre.ctypes.data, P, eq.ctypes.data, ms.ctypes.data, world, nnz_cuts.ctypes.data) == 0
+    assert np.all(np.abs(nnz_cuts.astype(np.int64) - eq.astype(np.int64)) <= 1)
