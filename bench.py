@@ -476,48 +476,78 @@ def record_rmat(ctx, w, headline=True, scale=None, K=None, reorder=True, steps=N
     # ---- end to end through the host-buffer entry point, every rank on its own shard (pinned host memory;
     # each step copies its own A and B in and its whole P out inside the timed region)
     e2e_rec = None
-    host_ceiling = None
     if e2e:
-        e2e_steps = max(2, min(steps, 8 if ctx.world == 1 else 4))
+        e2e_steps = max(2, min(steps, 8))
         hA = dA.cpu().pin_memory()
         hB = dB.cpu().pin_memory()
         hP = [torch.zeros(max(1, nnz), dtype=torch.float32).pin_memory() for _ in range(2)]
         nA, nB, nPs = hA.numpy(), hB.numpy(), [t.numpy() for t in hP]
-        for i in range(2):
-            pkg.sddmm_gpu_async(nA, nB, lay, nPs[i], i)
-        pkg.sddmm_gpu_sync(lay)
+        W = ctx.world
+        if W == 1:
+            # one GPU: the streaming host-buffer entry point, two slots (H2D of step i+1, kernels of step i and D2H
+            # of step i-1 overlap); every step moves all of A and B in and all of P out
+            for i in range(2):
+                pkg.sddmm_gpu_async(nA, nB, lay, nPs[i], i)
+            pkg.sddmm_gpu_sync(lay)
+            ctx.barrier()
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                pkg.sddmm_gpu_async(nA, nB, lay, nPs[i & 1], i & 1)
+            pkg.sddmm_gpu_sync(lay)
+            torch.cuda.synchronize()
+            e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+            assert np.array_equal(nPs[0], nPs[1]), "pipelined slots disagree"
+            api = "sddmm_run_host_async, 2 slots (H2D / kernels / D2H of consecutive steps overlap)"
+        else:
+            # N GPUs: sddmm_mgpu_run_host -- every rank copies 1/N of A and of B over its own PCIe link, the slices are
+            # all-gathered over NVLink, P is summed onto rank 0, which copies it to the host: the job reads the host
+            # ONCE per step
+            for i in range(2):
+                ctx.mg.run_host(lay, nA, nB, nPs[0] if ctx.rank == 0 else None, 0)
+            ctx.barrier()
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                ctx.mg.run_host(lay, nA, nB, nPs[i & 1] if ctx.rank == 0 else None, 0)
+            torch.cuda.synchronize()
+            e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+            api = ("sddmm_mgpu_run_host: 1/N slices of A and B per rank over PCIe, all-gather over NVLink, P reduced "
+                   "to rank 0 and copied out")
+            if ctx.rank == 0:  # the merged result on the host against fp64, rows from every shard
+                pick_all = Rh[np.linspace(0, Rh.size - 1, 24).astype(np.int64)]
+                hPt = torch.from_numpy(nPs[(e2e_steps - 1) & 1]).cuda()
+                fp64_row_check(torch, ro_host, ci, dA, dB, hPt, pick_all)
+                del hPt
         ctx.barrier()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            pkg.sddmm_gpu_async(nA, nB, lay, nPs[i & 1], i & 1)
-        pkg.sddmm_gpu_sync(lay)
-        torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-        ctx.barrier()
-        assert np.array_equal(nPs[0], nPs[1]), "pipelined slots disagree"
         # host-copy ceiling: the same bytes per step moved by bare cudaMemcpyAsync (both directions concurrently),
-        # all ranks at once -- what the box's PCIe / host memory system gives N ranks, kernels excluded
+        # all ranks at once -- what the box's PCIe / host memory system gives N ranks, kernels and NVLink excluded
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        fa, fb = dA.view(-1), dB.view(-1)
+        ha, hb = hA.view(-1), hB.view(-1)
+        ca, cb = -(-fa.numel() // W), -(-fb.numel() // W)
+        sa = slice(min(fa.numel(), ctx.rank * ca), min(fa.numel(), (ctx.rank + 1) * ca))
+        sb_ = slice(min(fb.numel(), ctx.rank * cb), min(fb.numel(), (ctx.rank + 1) * cb))
         ctx.barrier()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
             with torch.cuda.stream(s_in):
-                dA.copy_(hA, non_blocking=True)
-                dB.copy_(hB, non_blocking=True)
-            with torch.cuda.stream(s_out):
-                hP[i & 1].copy_(dP, non_blocking=True)
+                fa[sa].copy_(ha[sa], non_blocking=True)
+                fb[sb_].copy_(hb[sb_], non_blocking=True)
+            if ctx.rank == 0:
+                with torch.cuda.stream(s_out):
+                    hP[i & 1].copy_(dP, non_blocking=True)
         torch.cuda.synchronize()
         ceil_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
         ctx.barrier()
         e2e_ms_max, ceil_ms_max = ctx.max_over_ranks([e2e_ms, ceil_ms])
         e2e_rec = dict(value=2.0 * nnz * K / (e2e_ms_max * 1e-3) / 1e9, unit=UNIT, ms_per_step=e2e_ms_max,
                        steps=e2e_steps, h2d_bytes_per_step=int(4 * K * (M + N)), d2h_bytes_per_step=int(4 * nnz),
-                       bytes_note="per rank: every rank copies all of A and B in and its P out every step",
-                       api="sddmm_run_host_async, 2 slots (H2D / kernels / D2H of consecutive steps overlap)",
+                       bytes_note=("whole job: A and B enter once per step (1/N per rank), P leaves once (rank 0)"
+                                   if W > 1 else "all of A and B in, all of P out, every step"),
+                       api=api,
                        host_copy_ceiling=dict(ms_per_step=ceil_ms_max, value=2.0 * nnz * K / (ceil_ms_max * 1e-3) / 1e9,
-                                              note="same bytes per step by bare pinned cudaMemcpyAsync on two streams, "
-                                                   "all ranks concurrently, no kernels"))
-        del hA, hB, hP
+                                              note="same host bytes per step by bare pinned cudaMemcpyAsync on two "
+                                                   "streams, all ranks concurrently, no kernels, no NVLink"))
+        del hA, hB, hP, ha, hb
 
     cpu_rec = None
     if cpu and ctx.world == 1 and ctx.rank == 0 and not args.no_cpu:

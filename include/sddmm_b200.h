@@ -348,6 +348,13 @@ int sddmm_mgpu_bcast(sddmm_mgpu*, void* d_buf, size_t bytes, int root, void* str
 int sddmm_mgpu_run(sddmm_mgpu*, const bsmr_layout*, uint32_t K, const float* d_A, const float* d_B, float* d_P,
                    void* stream);
 int sddmm_mgpu_gather(sddmm_mgpu*, float* d_P, size_t count, void* stream);
+/* Host-buffer pass of a multi-GPU job (the multi-GPU form of sddmm_run_host, collective, synchronous): every rank
+ * holds the same host A (M x K) and B (N x K) but copies only its 1/world slice of each over its own PCIe link;
+ * the slices are all-gathered over NVLink (so the host is read ONCE per job step, not once per rank), every rank
+ * computes its panel range, the disjoint pieces of P are summed onto `root`, and root copies the whole P to h_P
+ * (h_P may be NULL elsewhere).  msTotal (optional) = this rank's device time for the whole call. */
+int sddmm_mgpu_run_host(sddmm_mgpu*, const bsmr_layout*, uint32_t K, const float* h_A, const float* h_B, float* h_P,
+                        int root, float* msTotal);
 
 #ifdef __cplusplus
 }

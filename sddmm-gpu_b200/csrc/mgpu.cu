@@ -8,6 +8,8 @@
 // ranks with whatever it has (a file, MPI, torch.distributed) -- see INTEGRATION.md.
 #include <dlfcn.h>
 
+#include <algorithm>
+
 #include <vector>
 
 #include "layout.cuh"
@@ -28,6 +30,8 @@ struct Nccl {
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
 
@@ -47,8 +51,11 @@ const Nccl& nccl() {
     r.CommDestroy = reinterpret_cast<decltype(r.CommDestroy)>(sym("ncclCommDestroy"));
     r.Broadcast = reinterpret_cast<decltype(r.Broadcast)>(sym("ncclBroadcast"));
     r.AllReduce = reinterpret_cast<decltype(r.AllReduce)>(sym("ncclAllReduce"));
+    r.AllGather = reinterpret_cast<decltype(r.AllGather)>(sym("ncclAllGather"));
+    r.Reduce = reinterpret_cast<decltype(r.Reduce)>(sym("ncclReduce"));
     r.GetErrorString = reinterpret_cast<decltype(r.GetErrorString)>(sym("ncclGetErrorString"));
-    if (!r.GetUniqueId || !r.CommInitRank || !r.CommDestroy || !r.Broadcast || !r.AllReduce) r.handle = nullptr;
+    if (!r.GetUniqueId || !r.CommInitRank || !r.CommDestroy || !r.Broadcast || !r.AllReduce || !r.AllGather || !r.Reduce)
+      r.handle = nullptr;
     return r;
   }();
   if (!n.handle)
@@ -153,6 +160,15 @@ struct sddmm_mgpu {
   void* comm = nullptr;
   std::vector<u32> cuts;
   std::vector<u64> pre;  // prefix sum of per-panel non-zero counts of the reordered matrix (kept for rebalancing)
+  // sddmm_mgpu_run_host: device staging (grown on demand), two streams and their events
+  DevBuf<float> wsA, wsB, wsP, wsPfull;
+  cudaStream_t sCopy = nullptr, sWork = nullptr;
+  cudaEvent_t evA = nullptr, evB = nullptr, evDone = nullptr, evT0 = nullptr, evT1 = nullptr;
+  ~sddmm_mgpu() {
+    for (cudaEvent_t e : {evA, evB, evDone, evT0, evT1}) if (e) cudaEventDestroy(e);
+    if (sCopy) cudaStreamDestroy(sCopy);
+    if (sWork) cudaStreamDestroy(sWork);
+  }
 };
 
 #define API_BEGIN try {
@@ -273,6 +289,64 @@ int sddmm_mgpu_run(sddmm_mgpu* g, const bsmr_layout* L, uint32_t K, const float*
   // the steady state has no collective: a shard's pass is an ordinary pass over its own panel range
   if (!g) { sb::set_last_error("sddmm_mgpu_run: null handle"); return SDDMM_E_ARG; }
   return sddmm_run_dev(L, K, d_A, d_B, d_P, stream);
+}
+
+int sddmm_mgpu_run_host(sddmm_mgpu* g, const bsmr_layout* L, uint32_t K, const float* h_A, const float* h_B, float* h_P,
+                        int root, float* msTotal) {
+  API_BEGIN
+  need(g && L && h_A && h_B && root >= 0 && root < g->world && (h_P || g->rank != root), "arguments");
+  bsmr_layout_info I{};
+  bsmr_layout_get_info(L, &I);
+  const size_t W = (size_t)g->world;
+  // every rank brings 1/world of A and of B over its own PCIe link; the slices meet over NVLink (all-gather)
+  auto slice = [&](size_t n) { return (((n + W - 1) / W) + 3) & ~(size_t)3; };
+  const size_t nA = (size_t)I.M * K, nB = (size_t)I.N * K, nP = I.nnz ? I.nnz : 1;
+  const size_t cA = slice(nA), cB = slice(nB);
+  if (!g->sCopy) {
+    SB_CUDA(cudaStreamCreateWithFlags(&g->sCopy, cudaStreamNonBlocking));
+    SB_CUDA(cudaStreamCreateWithFlags(&g->sWork, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&g->evA, &g->evB, &g->evDone}) SB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    SB_CUDA(cudaEventCreate(&g->evT0));
+    SB_CUDA(cudaEventCreate(&g->evT1));
+  }
+  if (g->wsA.size() < cA * W) g->wsA.alloc(cA * W, true);
+  if (g->wsB.size() < cB * W) g->wsB.alloc(cB * W, true);
+  if (g->wsP.size() < nP) {  // zeroed once: a shard's pass never writes foreign entries, so the sum below IS the merge
+    g->wsP.alloc(nP, true);
+    SB_CUDA(cudaMemset(g->wsP.get(), 0, nP * 4));
+  }
+  if (g->rank == root && g->wsPfull.size() < nP) g->wsPfull.alloc(nP, true);
+  float *dA = g->wsA.get(), *dB = g->wsB.get(), *dP = g->wsP.get();
+  const size_t r = (size_t)g->rank;
+  auto h2d_slice = [&](float* d, const float* h, size_t n, size_t c) {
+    const size_t beg = std::min(n, r * c), end = std::min(n, (r + 1) * c);
+    if (end > beg) SB_CUDA(cudaMemcpyAsync(d + beg, h + beg, (end - beg) * 4, cudaMemcpyHostToDevice, g->sCopy));
+  };
+  SB_CUDA(cudaEventRecord(g->evT0, g->sCopy));
+  h2d_slice(dA, h_A, nA, cA);
+  SB_CUDA(cudaEventRecord(g->evA, g->sCopy));
+  h2d_slice(dB, h_B, nB, cB);
+  SB_CUDA(cudaEventRecord(g->evB, g->sCopy));
+  SB_CUDA(cudaStreamWaitEvent(g->sWork, g->evA, 0));
+  if (g->world > 1) nccl_check(nccl().AllGather(dA + r * cA, dA, cA, kNcclFloat32, g->comm, g->sWork), "ncclAllGather(A)");
+  SB_CUDA(cudaStreamWaitEvent(g->sWork, g->evB, 0));
+  if (g->world > 1) nccl_check(nccl().AllGather(dB + r * cB, dB, cB, kNcclFloat32, g->comm, g->sWork), "ncclAllGather(B)");
+  {
+    const int rc = sddmm_run_dev(L, K, dA, dB, dP, g->sWork);
+    if (rc) return rc;
+  }
+  float* out = dP;
+  if (g->world > 1) {
+    out = g->rank == root ? g->wsPfull.get() : nullptr;
+    nccl_check(nccl().Reduce(dP, out, (size_t)I.nnz, kNcclFloat32, kNcclSum, root, g->comm, g->sWork), "ncclReduce(P)");
+  }
+  if (g->rank == root && I.nnz) SB_CUDA(cudaMemcpyAsync(h_P, out, (size_t)I.nnz * 4, cudaMemcpyDeviceToHost, g->sWork));
+  SB_CUDA(cudaEventRecord(g->evDone, g->sWork));
+  SB_CUDA(cudaStreamWaitEvent(g->sCopy, g->evDone, 0));
+  SB_CUDA(cudaEventRecord(g->evT1, g->sCopy));
+  SB_CUDA(cudaEventSynchronize(g->evT1));
+  if (msTotal) SB_CUDA(cudaEventElapsedTime(msTotal, g->evT0, g->evT1));
+  API_END
 }
 
 int sddmm_mgpu_gather(sddmm_mgpu* g, float* d_P, size_t count, void* stream) {

@@ -127,6 +127,14 @@ class MultiGpu:
                                         C.c_void_p(stream)))
         return P
 
+    def run_host(self, layout, A, B, P=None, root=0):
+        """sddmm_mgpu_run_host: host numpy A, B in (every rank the same arrays; each copies only its slice), host P
+        out on `root`.  Returns this rank's device milliseconds for the call."""
+        ms = C.c_float(0)
+        check(_lib.lib().sddmm_mgpu_run_host(self._h, layout.handle, A.shape[1], A.ctypes.data, B.ctypes.data,
+                                             P.ctypes.data if P is not None else None, int(root), C.byref(ms)))
+        return ms.value
+
     def gather(self, P):
         """sddmm_mgpu_gather: disjoint pieces (zeros elsewhere) -> the full P on every rank."""
         import torch

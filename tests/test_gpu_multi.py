@@ -103,7 +103,21 @@ def _worker(rank, world, port, q):
         mine = int((P != 0).sum())
         g.gather(P)
         torch.cuda.synchronize()
-        ok = O.check_data(O.sddmm_cpu(S, A, B), P.cpu().numpy()) == 0
+        Pref = O.sddmm_cpu(S, A, B)
+        ok = O.check_data(Pref, P.cpu().numpy()) == 0
+        # host-buffer pass of the whole job: 1/world slices over PCIe, all-gather over NVLink, P reduced onto rank 0
+        hP = np.full(S.nnz, np.nan, np.float32) if rank == 0 else None
+        for _ in range(2):  # twice: the staging buffers are reused and must not accumulate
+            g.run_host(sh.layout, A, B, hP, 0)
+        if rank == 0:
+            ok = ok and O.check_data(Pref, hP) == 0
+        # cost calibration: the cuts may move, the union must still cover every non-zero exactly once
+        sh.calibrate(dA, dB, P, rounds=2, passes=2)
+        P.zero_()
+        sh.run(dA, dB, P)
+        g.gather(P)
+        torch.cuda.synchronize()
+        ok = ok and O.check_data(Pref, P.cpu().numpy()) == 0
         q.put((rank, ok and same_order, sh.my_nnz, mine, [int(c) for c in sh.cuts]))
         g.close()
     finally:

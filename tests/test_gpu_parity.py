@@ -539,3 +539,45 @@ def test_cli_test_mode_sweep_feeds_the_reference_analyser(tmp_path):
         assert csv[0].startswith("file,M,N,NNZ,Sparsity,K,BSMR")
         row = csv[1].split(",")
         assert row[0] == mtx and int(row[3]) == S.nnz and int(row[5]) == k and float(row[6]) > 0
+
+
+def test_layout_cache_rejects_tampered_files(tmp_path):
+    """bsmr_layout_load cross-checks the file before anything reaches the device: truncated, padded, or edited
+    files (an offset array that no longer matches, a CSR index past nnz, a work item past its panel) end in
+    SDDMM_E_ARG, never in out-of-bounds reads inside the kernels."""
+    S = gen.block_structured(300, 400, 4, 64, 0.8, seed=2, noise=0.01)
+    lay = pkg.BSMR(0.3, 0.3, S, block_size=16).layout()
+    good = tmp_path / "good.bsmr"
+    lay.save(good)
+    raw = bytearray(open(good, "rb").read())
+    pkg.Layout.load(good)  # sanity: the untouched file loads
+
+    def expect_reject(data, what):
+        p = tmp_path / (what + ".bsmr")
+        open(p, "wb").write(bytes(data))
+        with pytest.raises(pkg.SddmmError) as e:
+            pkg.Layout.load(p)
+        assert e.value.code == 1, what
+
+    expect_reject(raw[: len(raw) // 2], "truncated")
+    hdr = 8 + 4 + 13 * 4 + 3 * 4  # magic, version, bsmr_layout_info, sparseChunk, numDenseWork, numSparseWork
+    n0 = int.from_bytes(raw[hdr: hdr + 8], "little")  # length of reorderedRows
+    assert n0 == lay.info.numRows
+    bad = bytearray(raw)
+    bad[hdr + 8: hdr + 12] = (S.M + 5).to_bytes(4, "little")  # a row id past M
+    expect_reject(bad, "row_out_of_range")
+    bad = bytearray(raw)
+    bad[8 + 4 + 2 * 4: 8 + 4 + 3 * 4] = (7).to_bytes(4, "little")  # info.nnz = 7: every CSR index is now past nnz
+    expect_reject(bad, "nnz_too_small")
+    bad = bytearray(raw)
+    bad[8 + 4 + 3 * 4: 8 + 4 + 4 * 4] = (lay.info.numRows + 16).to_bytes(4, "little")  # info.numRows disagrees with the array
+    expect_reject(bad, "row_count")
+    # an offset array edited so that it no longer ends at the array it indexes
+    off = hdr + 8 + 4 * n0          # -> denseCols (length + data)
+    n1 = int.from_bytes(raw[off: off + 8], "little")
+    off2 = off + 8 + 4 * n1         # -> denseColOffsets
+    n2 = int.from_bytes(raw[off2: off2 + 8], "little")
+    bad = bytearray(raw)
+    last = off2 + 8 + 4 * (n2 - 1)
+    bad[last: last + 4] = (n1 + 16).to_bytes(4, "little")
+    expect_reject(bad, "offsets")
