@@ -236,10 +236,19 @@ enum { SDDMM_PLAN_AUTO = 0, SDDMM_PLAN_BSMR = 1, SDDMM_PLAN_TILE = 2 };
 enum { SDDMM_DENSE_AUTO = 0, SDDMM_DENSE_REG = 1, SDDMM_DENSE_TMA = 2 };
 enum { SDDMM_RESIDUAL_AUTO = 0, SDDMM_RESIDUAL_PANEL = 1, SDDMM_RESIDUAL_SUPERPANEL = 2, SDDMM_RESIDUAL_STREAM = 3 };
 enum { SDDMM_TILE_AUTO = 0, SDDMM_TILE_REG = 1, SDDMM_TILE_TMA = 2, SDDMM_TILE_TMA_CLUSTER = 3 };
+/* operands  EXACT = the reference's arithmetic: TF32 (round-to-nearest) operands into the tensor cores for dense
+ *                   blocks / tiles, fp32 operands for the residual; fp32 accumulation everywhere (the default)
+ *           FP16  = fp16 (round-to-nearest) copies of the operands where that halves the limiting traffic: the A
+ *                   tile of the super-panel residual kernel in shared memory, both operands of the TMA tile kernel
+ *                   (tcgen05 kind::f16).  fp32 accumulation.  Same 11 significant bits as TF32, so results stay
+ *                   within the reference's checkData tolerance, but |operand| must stay below 65504 and residual
+ *                   values are no longer the exact path's.  Opt-in only; AUTO never picks it. */
+enum { SDDMM_OPERANDS_EXACT = 0, SDDMM_OPERANDS_FP16 = 1 };
 typedef struct {
   uint32_t plan, dense, residual, tile;
   uint32_t tileStages;   /* 0 = default, else 2..4 operand stages of the TMA tile kernels                      */
-  uint32_t reserved[3];
+  uint32_t operands;     /* SDDMM_OPERANDS_*                                                                   */
+  uint32_t reserved[2];
 } sddmm_plan;
 /* fills *out with the defaults: AUTO unless an SDDMM_B200_* environment variable says otherwise */
 void sddmm_plan_default(sddmm_plan* out);

@@ -39,7 +39,7 @@ class Stats(C.Structure):
 class Plan(C.Structure):
     """sddmm_plan (include/sddmm_b200.h): which kernels serve a pass; 0 = AUTO everywhere."""
     _fields_ = [("plan", C.c_uint32), ("dense", C.c_uint32), ("residual", C.c_uint32), ("tile", C.c_uint32),
-                ("tileStages", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+                ("tileStages", C.c_uint32), ("operands", C.c_uint32), ("reserved", C.c_uint32 * 2)]
 
 
 class ReorderOpts(C.Structure):
@@ -52,6 +52,7 @@ PLAN = dict(auto=0, bsmr=1, tile=2)
 DENSE = dict(auto=0, reg=1, tma=2)
 RESIDUAL = dict(auto=0, panel=1, superpanel=2, stream=3)
 TILE = dict(auto=0, reg=1, tma=2, tma_cluster=3)
+OPERANDS = dict(exact=0, fp16=1)
 CLUSTER = dict(auto=0, legacy=1, batched=2)
 TRISTATE = dict(auto=0, off=1, on=2)
 BUILD_TILES = dict(auto=0, always=1, never=2)

@@ -13,7 +13,8 @@
 //                      shuffle reduction.  Replaces src/sddmmKernel.cu:1994-2104 and :2109-2199.
 #include <algorithm>
 
-#include <cuda.h>  // CUtensorMap and its enums only; the encoder is fetched through cudaGetDriverEntryPoint
+#include <cuda.h>
+#include <cuda_fp16.h>  // CUtensorMap and its enums only; the encoder is fetched through cudaGetDriverEntryPoint
 
 #include <cstring>
 #include <initializer_list>
@@ -158,13 +159,19 @@ __device__ __forceinline__ void stg_f32_policy(float* p, float v, u64 pol) {
 // column run to reuse, so every entry loads its own B^T fragment and the loads of U consecutive entries are issued
 // before the first FMA -- U x 4K bytes in flight per 8 lanes instead of one row (ncu, R-MAT scale 22: 24 of 30
 // cycles per issue were long-scoreboard stalls with one row in flight).  U = 0: column-run reuse from registers.
-template <int NB, int kThreads, bool kHints, int U>
+// kHalfA (opt-in, sddmm_plan.operands = SDDMM_OPERANDS_FP16): the A tile sits in shared memory as fp16 (round to
+// nearest; 11 significant bits, what the reference's TF32 dense path keeps), products and sums stay fp32.  Halves
+// the shared-memory bytes per non-zero -- the limiter of reuse mode -- and doubles the rows per super-panel, hence
+// the column-run reuse of B^T.  Values stay within the reference's checkData tolerance (tests), but they are no
+// longer the fp32 results of the exact path, and |A| must stay below 65504.
+template <int NB, int kThreads, bool kHints, int U, bool kHalfA>
 static __global__ void __launch_bounds__(kThreads, 1)
 k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restrict__ B4, const u32* __restrict__ R,
                     u32 nR, u32 spRows, u32 segLen, const u32* __restrict__ spOff, const u32* __restrict__ spCol,
                     const unsigned short* __restrict__ spRow, const u32* __restrict__ spIdx,
                     const uint2* __restrict__ work, float* __restrict__ P, BatchStrides bs) {
-  extern __shared__ float4 sA[];  // spRows x K4
+  extern __shared__ float4 sA[];  // spRows x K4 (fp32), or the same count of 4-half groups when kHalfA
+  uint2* sH = reinterpret_cast<uint2*>(sA);
   A4 += (bs.a >> 2) * blockIdx.y;
   B4 += (bs.b >> 2) * blockIdx.y;
   P += bs.p * blockIdx.y;
@@ -184,9 +191,22 @@ k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restri
       const u32 row = R[ri];
       if (row < M) v = __ldg(A4 + (size_t)row * K4 + c);
     }
-    sA[i] = v;
+    if (kHalfA) {
+      const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+      sH[i] = make_uint2(*reinterpret_cast<const u32*>(&lo), *reinterpret_cast<const u32*>(&hi));
+    } else {
+      sA[i] = v;
+    }
   }
   __syncthreads();
+  // 4 consecutive A values of the group's slice: one LDS.128 (fp32 tile) or one LDS.64 + 2 conversions (fp16 tile)
+  auto lda = [&](u32 idx) -> float4 {
+    if (!kHalfA) return sA[idx];
+    const uint2 h = sH[idx];
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+  };
 
   const u32 grp = threadIdx.x >> 3, gl = threadIdx.x & 7u;
   u64 polB = 0, polS = 0;
@@ -253,11 +273,11 @@ k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restri
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int t = h * U + u;
-          const float4* a = sA + rows[t] * K4 + gl;
+          const u32 a = rows[t] * K4 + gl;
           float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
           for (int j = 0; j < NB; ++j) {
-            const float4 av = a[j * 8], bv = bq[u][j];
+            const float4 av = lda(a + j * 8), bv = bq[u][j];
             if (j & 1) {
               acc1 = fmaf(av.x, bv.x, acc1); acc1 = fmaf(av.y, bv.y, acc1);
               acc1 = fmaf(av.z, bv.z, acc1); acc1 = fmaf(av.w, bv.w, acc1);
@@ -281,11 +301,11 @@ k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restri
         for (int j = 0; j < NB; ++j) breg[j] = kHints ? ldg_f4_policy(b + j * 8, polB) : __ldg(b + j * 8);
         prevCol = col;
       }
-      const float4* a = sA + rows[t] * K4 + gl;
+      const u32 a = rows[t] * K4 + gl;
       float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
-        const float4 av = a[j * 8];
+        const float4 av = lda(a + j * 8);
         if (j & 1) {
           acc1 = fmaf(av.x, breg[j].x, acc1); acc1 = fmaf(av.y, breg[j].y, acc1);
           acc1 = fmaf(av.z, breg[j].z, acc1); acc1 = fmaf(av.w, breg[j].w, acc1);
@@ -458,15 +478,15 @@ k_sddmm_residual_stream(const float4* __restrict__ A4, const float4* __restrict_
 }
 
 // panels per super-panel for a given K (A tile <= ~192 KB), 0 if the super-panel kernel does not apply
-static u32 superpanel_G(u32 K) {
+static u32 superpanel_G(u32 K, bool halfA = false) {
   if (K % 32u || K > 512u) return 0;
   const u32 NB = K / 32u;
   if (NB != 1 && NB != 2 && NB != 4 && NB != 8 && NB != 16) return 0;
   u32 tileKB = 192u;
   if (const char* e = getenv("SDDMM_B200_SP_SMEM_KB")) { const int v = atoi(e); if (v >= 16 && v <= 216) tileKB = (u32)v; }
-  u32 rows = (tileKB * 1024u) / (K * 4u);
+  u32 rows = (tileKB * 1024u) / (K * (halfA ? 2u : 4u));
   u32 G = rows / 16u;
-  if (G > 64u) G = 64u;
+  if (G > (halfA ? 128u : 64u)) G = halfA ? 128u : 64u;  // row ids inside a super-panel are 16-bit
   return G;
 }
 
@@ -878,6 +898,33 @@ static __global__ void __launch_bounds__(256) k_round_operands(u32 M, u32 N, u32
   }
 }
 
+// fp16 form of the copies (sddmm_plan.operands = SDDMM_OPERANDS_FP16): round to nearest, half the bytes
+static __global__ void __launch_bounds__(256) k_round_operands_half(u32 M, u32 N, u32 K4, const float4* __restrict__ A,
+                                                                    const float4* __restrict__ B,
+                                                                    const u32* __restrict__ R, u32 nR,
+                                                                    uint2* __restrict__ Ar, uint2* __restrict__ Br,
+                                                                    BatchStrides bs) {
+  A += (bs.a >> 2) * blockIdx.y;
+  B += (bs.b >> 2) * blockIdx.y;
+  Ar += (size_t)nR * K4 * blockIdx.y;
+  Br += (size_t)N * K4 * blockIdx.y;
+  const size_t nA = (size_t)nR * K4, nB = (size_t)N * K4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nA + nB; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < nA) {
+      const u32 r = (u32)(i / K4), c = (u32)(i - (size_t)r * K4);
+      const u32 row = R[r];
+      if (row < M) v = __ldg(A + (size_t)row * K4 + c);
+    } else {
+      v = __ldg(B + (i - nA));
+    }
+    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    const uint2 o = make_uint2(*reinterpret_cast<const u32*>(&lo), *reinterpret_cast<const u32*>(&hi));
+    if (i < nA) Ar[i] = o;
+    else Br[i - nA] = o;
+  }
+}
+
 // bounded wait: a protocol error must end in a launch failure, never in a hung GPU
 __device__ __forceinline__ void mbar_wait_bounded(u64* bar, u32 parity) {
   const long long t0 = clock64();
@@ -893,7 +940,12 @@ __device__ __forceinline__ void tma_load_3d(u32 dstSmem, const void* map, u32 ba
       : "memory");
 }
 
-template <u32 kStagesT>
+// kHalf: fp16 operand copies, 64 K-elements per 128-byte swizzle row, tcgen05.mma kind::f16 (K = 16 per instruction)
+__host__ __device__ constexpr u32 umma_idesc_f16(u32 Mdim, u32 Ndim) {
+  return (1u << 4) | ((Ndim >> 3) << 17) | ((Mdim >> 4) << 24);  // c = F32, a = b = F16 (format 0), K-major both
+}
+
+template <u32 kStagesT, bool kHalf>
 static __global__ void __launch_bounds__(kTlThreads)
 k_sddmm_tile_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, u32 K,
                  const uint4* __restrict__ tiles, const u32* __restrict__ rowMeta, const u32* __restrict__ entIdx,
@@ -924,8 +976,9 @@ k_sddmm_tile_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const u32 tmem = tmemBase;
-  const u32 numChunks = (K + kDnKChunk - 1) / kDnKChunk;
-  constexpr u32 idesc = umma_idesc_tf32(128, 128);
+  constexpr u32 kChunkElems = kHalf ? 64u : kDnKChunk;  // one 128-byte swizzle row of K
+  const u32 numChunks = (K + kChunkElems - 1) / kChunkElems;
+  constexpr u32 idesc = kHalf ? umma_idesc_f16(128, 128) : umma_idesc_tf32(128, 128);
 
   if (warp == 0) {
     // ---- producer: one thread feeds the stages through the TMA unit
@@ -936,8 +989,8 @@ k_sddmm_tile_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const u32 bar = smem_u32(&fullBar[s]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kTlStageBytes) : "memory");
         const u32 dst = smem_u32(stages + s * kTlStageBytes);
-        tma_load_3d(dst, &mapA, bar, kc * kDnKChunk, tile.x * 128u, blockIdx.y);
-        tma_load_3d(dst + 128u * 128u, &mapB, bar, kc * kDnKChunk, tile.y * 128u, blockIdx.y);
+        tma_load_3d(dst, &mapA, bar, kc * kChunkElems, tile.x * 128u, blockIdx.y);
+        tma_load_3d(dst + 128u * 128u, &mapB, bar, kc * kChunkElems, tile.y * 128u, blockIdx.y);
       }
       __syncwarp();
     }
@@ -954,6 +1007,13 @@ k_sddmm_tile_tma(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
         for (u32 k = 0; k < kDnKChunk / 8; ++k) {
           const u32 acc = (kc | k) ? 1u : 0u;
+          if (kHalf)
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem),
+                "l"(dA + 2ull * k), "l"(dB + 2ull * k), "r"(idesc), "r"(acc)
+                : "memory");
+          else
           asm volatile(
               "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem),
@@ -1492,7 +1552,8 @@ static const bsmr_layout::DenseIndex* ensure_dense_index(const bsmr_layout* L, c
 }
 
 // host side of the TMA kernels: workspaces + tensor maps (cached in the layout per K / batch count)
-static void encode_map(void* out, const float* base, int rank, u32 K, u64 rows, u32 numBatch, u32 boxRows) {
+static void encode_map(void* out, const float* base, int rank, u32 K, u64 rows, u32 numBatch, u32 boxRows,
+                       bool half = false) {
   using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1505,19 +1566,21 @@ static void encode_map(void* out, const float* base, int rank, u32 K, u64 rows, 
     return reinterpret_cast<EncodeFn>(p);
   }();
   if (!fn) fail(SDDMM_E_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t esz = half ? 2u : 4u;
   const cuuint64_t dims[3] = {K, rows, numBatch};
-  const cuuint64_t strides[2] = {(cuuint64_t)K * 4u, (cuuint64_t)rows * K * 4u};
-  const cuuint32_t box[3] = {kDnKChunk, boxRows, 1u};
+  const cuuint64_t strides[2] = {(cuuint64_t)K * esz, (cuuint64_t)rows * K * esz};
+  const cuuint32_t box[3] = {half ? 64u : kDnKChunk, boxRows, 1u};  // one 128-byte swizzle row of K
   const cuuint32_t estr[3] = {1u, 1u, 1u};
-  const CUresult rc = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+  const CUresult rc = fn(reinterpret_cast<CUtensorMap*>(out),
+                         half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
                          const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) fail(SDDMM_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
 }
 
-static const bsmr_layout::TileTma* ensure_tile_tma(const bsmr_layout* L, u32 K, u32 numBatch) {
-  const u64 key = ((u64)K << 32) | numBatch;
+static const bsmr_layout::TileTma* ensure_tile_tma(const bsmr_layout* L, u32 K, u32 numBatch, bool half = false) {
+  const u64 key = ((u64)K << 32) | numBatch | (half ? 0x80000000ull : 0ull);
   {
     auto it = L->tma.find(key);
     if (it != L->tma.end()) return it->second.get();
@@ -1527,12 +1590,13 @@ static const bsmr_layout::TileTma* ensure_tile_tma(const bsmr_layout* L, u32 K, 
   const u32 nR = I.numRows ? I.numRows : 1u;
   t->K = K;
   t->numBatch = numBatch;
-  t->rA.alloc((size_t)numBatch * nR * K, true);  // outlives any scratch scope
-  t->rB.alloc((size_t)numBatch * I.N * K, true);
-  encode_map(t->mapA, t->rA.get(), 3, K, nR, numBatch, 128u);
-  encode_map(t->mapB, t->rB.get(), 3, K, I.N, numBatch, 128u);
-  encode_map(t->mapA64, t->rA.get(), 3, K, nR, numBatch, 64u);
-  encode_map(t->mapB64, t->rB.get(), 3, K, I.N, numBatch, 64u);
+  // fp16 copies take half the floats' room (K is a multiple of 4, so K/2 floats per row hold K halves)
+  t->rA.alloc((size_t)numBatch * nR * K / (half ? 2 : 1), true);  // outlives any scratch scope
+  t->rB.alloc((size_t)numBatch * I.N * K / (half ? 2 : 1), true);
+  encode_map(t->mapA, t->rA.get(), 3, K, nR, numBatch, 128u, half);
+  encode_map(t->mapB, t->rB.get(), 3, K, I.N, numBatch, 128u, half);
+  encode_map(t->mapA64, t->rA.get(), 3, K, nR, numBatch, 64u, half);
+  encode_map(t->mapB64, t->rB.get(), 3, K, I.N, numBatch, 64u, half);
   SB_CUDA(cudaEventCreateWithFlags(&t->busy, cudaEventDisableTiming));
   return (L->tma[key] = std::move(t)).get();
 }
@@ -1576,6 +1640,7 @@ void plan_default(sddmm_plan* out) {
                                                      {"2", SDDMM_RESIDUAL_STREAM}, {"stream", SDDMM_RESIDUAL_STREAM}});
   out->tile = env_choice("SDDMM_B200_TILE", {{"reg", SDDMM_TILE_REG}, {"tma1", SDDMM_TILE_TMA}, {"tma", SDDMM_TILE_TMA},
                                              {"tma4", SDDMM_TILE_TMA_CLUSTER}});
+  out->operands = env_choice("SDDMM_B200_OPERANDS", {{"fp16", SDDMM_OPERANDS_FP16}});
   if (const char* e = getenv("SDDMM_B200_TILE_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 4) out->tileStages = (u32)v; }
 }
 
@@ -1587,7 +1652,8 @@ void plan_resolve(const bsmr_layout* L, u32 K, u32 numBatch, const sddmm_plan* i
   sddmm_plan p;
   if (in) p = *in; else plan_default(&p);
   if (p.plan > SDDMM_PLAN_TILE || p.dense > SDDMM_DENSE_TMA || p.residual > SDDMM_RESIDUAL_STREAM ||
-      p.tile > SDDMM_TILE_TMA_CLUSTER || (p.tileStages && (p.tileStages < 2 || p.tileStages > 4)))
+      p.tile > SDDMM_TILE_TMA_CLUSTER || (p.tileStages && (p.tileStages < 2 || p.tileStages > 4)) ||
+      p.operands > SDDMM_OPERANDS_FP16)
     fail(SDDMM_E_ARG, "sddmm_plan holds an unknown selector");
   const bsmr_layout_info& I = L->info;
   const bool haveTiles = L->tl && L->tl->numTiles;
@@ -1606,6 +1672,11 @@ void plan_resolve(const bsmr_layout* L, u32 K, u32 numBatch, const sddmm_plan* i
   if (p.plan == SDDMM_PLAN_TILE) {
     // REG: register-staged tiles; TMA: one CTA per tile fed by TMA (default for K >= 128; below that the rounding
     // pre-pass costs more than it saves); TMA_CLUSTER: 2x2 clusters with multicast (opt-in: measured slower)
+    if (p.operands == SDDMM_OPERANDS_FP16) {
+      if (p.tile == SDDMM_TILE_REG || p.tile == SDDMM_TILE_TMA_CLUSTER)
+        fail(SDDMM_E_UNSUPPORTED, "SDDMM_OPERANDS_FP16 is implemented by the TMA tile kernel only (tile = SDDMM_TILE_TMA)");
+      p.tile = SDDMM_TILE_TMA;
+    }
     if (p.tile == SDDMM_TILE_AUTO) p.tile = K >= 128 ? SDDMM_TILE_TMA : SDDMM_TILE_REG;
     if (p.tile == SDDMM_TILE_TMA_CLUSTER && !L->tl->numQuads) p.tile = SDDMM_TILE_TMA;
     if (!p.tileStages) p.tileStages = 2;
@@ -1618,7 +1689,7 @@ void plan_resolve(const bsmr_layout* L, u32 K, u32 numBatch, const sddmm_plan* i
     else if (p.dense == SDDMM_DENSE_AUTO) p.dense = SDDMM_DENSE_REG;
     if (!L->numSparseWork) p.residual = SDDMM_RESIDUAL_AUTO;
     else {
-      const u32 G = superpanel_G(K);
+      const u32 G = superpanel_G(K, p.operands == SDDMM_OPERANDS_FP16);
       if ((p.residual == SDDMM_RESIDUAL_SUPERPANEL || p.residual == SDDMM_RESIDUAL_STREAM) && !G)
         fail(SDDMM_E_UNSUPPORTED, "SDDMM_RESIDUAL_%s needs K in {32, 64, 128, 256, 512} (K=%u)",
              p.residual == SDDMM_RESIDUAL_STREAM ? "STREAM" : "SUPERPANEL", K);
@@ -1644,11 +1715,12 @@ void plan_resolve(const bsmr_layout* L, u32 K, u32 numBatch, const sddmm_plan* i
 // builds everything a run with this (resolved) plan needs; after it a run only enqueues
 void plan_prepare(const bsmr_layout* L, u32 K, u32 numBatch, const sddmm_plan& p, cudaStream_t s) {
   if (p.plan == SDDMM_PLAN_TILE) {
-    if (p.tile != SDDMM_TILE_REG) ensure_tile_tma(L, K, numBatch);
+    if (p.tile != SDDMM_TILE_REG) ensure_tile_tma(L, K, numBatch, p.operands == SDDMM_OPERANDS_FP16);
     return;
   }
   if (p.dense == SDDMM_DENSE_TMA) ensure_dense_tma(L, K, numBatch, s);
-  if (p.residual == SDDMM_RESIDUAL_SUPERPANEL) ensure_superpanels(L, superpanel_G(K), s);
+  if (p.residual == SDDMM_RESIDUAL_SUPERPANEL)
+    ensure_superpanels(L, superpanel_G(K, p.operands == SDDMM_OPERANDS_FP16), s);
   if (p.residual == SDDMM_RESIDUAL_STREAM) ensure_stream(L, s);
 }
 
@@ -1697,14 +1769,22 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
       SB_LAUNCH_CHECK();
       return;
     }
-    const bsmr_layout::TileTma* t = ensure_tile_tma(L, K, numBatch);
+    const bool half = p.operands == SDDMM_OPERANDS_FP16;
+    const bsmr_layout::TileTma* t = ensure_tile_tma(L, K, numBatch, half);
     const size_t smem = (size_t)p.tileStages * kTlStageBytes + 1024;
     workspace_acquire(t->busy, denseStream);  // an earlier pass on another stream may still read rA / rB
     const size_t work = ((size_t)I.numRows + I.N) * K4;
-    k_round_operands<<<dim3((unsigned)std::min<size_t>((work + 255) / 256, 148 * 16), numBatch), 256, 0, denseStream>>>(
-        I.M, I.N, K4, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB),
-        arr(BSMR_REORDERED_ROWS), I.numRows, reinterpret_cast<float4*>(t->rA.get()),
-        reinterpret_cast<float4*>(t->rB.get()), bst);
+    const dim3 rgrid((unsigned)std::min<size_t>((work + 255) / 256, (size_t)device_sm_count() * 16), numBatch);
+    if (half)
+      k_round_operands_half<<<rgrid, 256, 0, denseStream>>>(
+          I.M, I.N, K4, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB),
+          arr(BSMR_REORDERED_ROWS), I.numRows, reinterpret_cast<uint2*>(t->rA.get()),
+          reinterpret_cast<uint2*>(t->rB.get()), bst);
+    else
+      k_round_operands<<<rgrid, 256, 0, denseStream>>>(
+          I.M, I.N, K4, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB),
+          arr(BSMR_REORDERED_ROWS), I.numRows, reinterpret_cast<float4*>(t->rA.get()),
+          reinterpret_cast<float4*>(t->rB.get()), bst);
     SB_LAUNCH_CHECK();
     if (p.tile == SDDMM_TILE_TMA_CLUSTER) {
       auto kq = p.tileStages == 2 ? k_sddmm_tile_tma4<2> : p.tileStages == 3 ? k_sddmm_tile_tma4<3> : k_sddmm_tile_tma4<4>;
@@ -1726,7 +1806,10 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
                                  (const u32*)L->tl->idx.get(), dP, bst.p));
       SB_LAUNCH_CHECK();
     } else {
-      auto kt = p.tileStages == 2 ? k_sddmm_tile_tma<2> : p.tileStages == 3 ? k_sddmm_tile_tma<3> : k_sddmm_tile_tma<4>;
+      auto kt = half ? (p.tileStages == 2 ? k_sddmm_tile_tma<2, true> : p.tileStages == 3 ? k_sddmm_tile_tma<3, true>
+                                                                                      : k_sddmm_tile_tma<4, true>)
+                     : (p.tileStages == 2 ? k_sddmm_tile_tma<2, false> : p.tileStages == 3 ? k_sddmm_tile_tma<3, false>
+                                                                                       : k_sddmm_tile_tma<4, false>);
       set_smem(kt, smem);
       kt<<<dim3(L->tl->numTiles, numBatch), kTlThreads, smem, denseStream>>>(
           *reinterpret_cast<const CUtensorMap*>(t->mapA), *reinterpret_cast<const CUtensorMap*>(t->mapB), K,
@@ -1789,9 +1872,10 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
         SB_LAUNCH_CHECK();
       }
     } else if (p.residual == SDDMM_RESIDUAL_SUPERPANEL) {
-      const SuperPanelLayout* sp = ensure_superpanels(L, superpanel_G(K), sparseStream);
+      const bool halfA = p.operands == SDDMM_OPERANDS_FP16;
+      const SuperPanelLayout* sp = ensure_superpanels(L, superpanel_G(K, halfA), sparseStream);
       if (sp->numWork) {
-        const size_t smem = (size_t)sp->rows * K * sizeof(float);
+        const size_t smem = (size_t)sp->rows * K * (halfA ? 2 : 4);
         auto launch = [&](auto kern, int threads) {
           set_smem(kern, smem);
           kern<<<dim3(sp->numWork, numBatch), threads, smem, sparseStream>>>(
@@ -1808,12 +1892,17 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
         // ms at K=128 and worse above (there one row per 8 lanes already keeps 64 KB per SM in flight and the L2
         // fabric, ~8.5 TB/s of gathered rows, is the limit), hence K <= 64
         const bool gather = gatherCfg >= 0 ? gatherCfg != 0 : (K <= 64 && (double)sp->numEntries < 1.5 * (double)sp->numRuns);
-#define SB_SP_CASE(NBv, THRv, Uv)                                                                 \
+#define SB_SP_CASE2(NBv, THRv, Uv, HALFv)                                                         \
   do {                                                                                            \
-    if (gather) { if (hints) launch(k_sddmm_residual_sp<NBv, THRv, true, Uv>, THRv);              \
-                  else launch(k_sddmm_residual_sp<NBv, THRv, false, Uv>, THRv); }                 \
-    else { if (hints) launch(k_sddmm_residual_sp<NBv, THRv, true, 0>, THRv);                      \
-           else launch(k_sddmm_residual_sp<NBv, THRv, false, 0>, THRv); }                         \
+    if (gather) { if (hints) launch(k_sddmm_residual_sp<NBv, THRv, true, Uv, HALFv>, THRv);       \
+                  else launch(k_sddmm_residual_sp<NBv, THRv, false, Uv, HALFv>, THRv); }          \
+    else { if (hints) launch(k_sddmm_residual_sp<NBv, THRv, true, 0, HALFv>, THRv);               \
+           else launch(k_sddmm_residual_sp<NBv, THRv, false, 0, HALFv>, THRv); }                  \
+  } while (0)
+#define SB_SP_CASE(NBv, THRv, Uv)                    \
+  do {                                               \
+    if (halfA) SB_SP_CASE2(NBv, THRv, Uv, true);     \
+    else SB_SP_CASE2(NBv, THRv, Uv, false);          \
   } while (0)
         switch (K / 32u) {
           case 1: SB_SP_CASE(1, 1024, 8); break;
@@ -1823,6 +1912,7 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
           default: SB_SP_CASE(16, 512, 1); break;
         }
 #undef SB_SP_CASE
+#undef SB_SP_CASE2
         SB_LAUNCH_CHECK();
       }
     } else {

@@ -34,10 +34,11 @@ def _ptr(a):
     return a.data_ptr()
 
 
-def make_plan(plan="auto", dense="auto", residual="auto", tile="auto", tile_stages=0):
+def make_plan(plan="auto", dense="auto", residual="auto", tile="auto", tile_stages=0, operands="exact"):
     """sddmm_plan by name: plan auto|bsmr|tile, dense auto|reg|tma, residual auto|panel|superpanel|stream,
     tile auto|reg|tma|tma_cluster.  None where the library's defaults (environment, cost model) should decide."""
-    return Plan(_lib.PLAN[plan], _lib.DENSE[dense], _lib.RESIDUAL[residual], _lib.TILE[tile], int(tile_stages))
+    return Plan(_lib.PLAN[plan], _lib.DENSE[dense], _lib.RESIDUAL[residual], _lib.TILE[tile], int(tile_stages),
+                _lib.OPERANDS[operands])
 
 
 def make_reorder_opts(kernel="auto", batch=0, lane_rows="auto", signature="auto"):
@@ -55,7 +56,7 @@ def plan_resolve(layout, K, numBatch=1, plan=None):
     check(_lib.lib().sddmm_plan_resolve(lay.handle, int(K), int(numBatch), _plan_ptr(plan), C.byref(out)))
     inv = lambda d, v: next(k for k, x in d.items() if x == v)
     return dict(plan=inv(_lib.PLAN, out.plan), dense=inv(_lib.DENSE, out.dense), residual=inv(_lib.RESIDUAL, out.residual),
-                tile=inv(_lib.TILE, out.tile), tile_stages=int(out.tileStages))
+                tile=inv(_lib.TILE, out.tile), tile_stages=int(out.tileStages), operands=inv(_lib.OPERANDS, out.operands))
 
 
 def sddmm_prepare(layout, K, numBatch=1, plan=None):

@@ -10,6 +10,7 @@ reference's checkData tolerance (include/checkData.hpp:14-30).  One test id per 
   tile_reg     k_sddmm_tile         128x128 tcgen05 tiles, register-staged
   tile_tma     k_sddmm_tile_tma     128x128 tcgen05 tiles, TMA-fed
   tile_tma4    k_sddmm_tile_tma4    2x2 clusters, multicast TMA
+  res_sp_fp16 / tile_tma_fp16       the opt-in fp16-operand forms of K7b and K9 (fp32 accumulation, same tolerance)
 and the clustering kernels (k_cluster, k_cluster_batched<1|2|4|8>, lane sweep on/off, signature filter on/off)
 against the permutations of the unmodified reference GPU pipeline (tests/golden/ref_gpu).
 """
@@ -33,6 +34,10 @@ KERNELS = {
     "res_panel": (1.1, dict(plan="bsmr", residual="panel"), dict(plan="bsmr", residual="panel")),
     "res_sp": (1.1, dict(plan="bsmr", residual="superpanel"), dict(plan="bsmr", residual="superpanel")),
     "res_stream": (1.1, dict(plan="bsmr", residual="stream"), dict(plan="bsmr", residual="stream")),
+    # opt-in fp16 operand copies (sddmm_plan.operands): fp16 A tile in the super-panel kernel, kind::f16 tile kernel
+    "res_sp_fp16": (1.1, dict(plan="bsmr", residual="superpanel", operands="fp16"),
+                    dict(plan="bsmr", residual="superpanel", operands="fp16")),
+    "tile_tma_fp16": (0.3, dict(plan="tile", tile="tma", operands="fp16"), dict(plan="tile", tile="tma", operands="fp16")),
     "tile_reg": (0.3, dict(plan="tile", tile="reg"), dict(plan="tile", tile="reg")),
     "tile_tma": (0.3, dict(plan="tile", tile="tma"), dict(plan="tile", tile="tma")),
     "tile_tma3": (0.3, dict(plan="tile", tile="tma", tile_stages=3), dict(plan="tile", tile="tma", tile_stages=3)),
@@ -95,7 +100,7 @@ def test_kernel_parity(kernel, K, nb, mname, torch_mod):
     S = MATS[mname]
     lay = _layout(mname, delta)
     plan = pkg.make_plan(**kw)
-    if kernel in ("res_sp", "res_stream") and K not in SP_KS:
+    if kernel in ("res_sp", "res_stream", "res_sp_fp16") and K not in SP_KS:
         with pytest.raises(pkg.SddmmError) as e:  # an impossible choice fails loudly, it never silently runs another kernel
             pkg.plan_resolve(lay, K, nb, plan)
         assert e.value.code == 4

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--plan", default="auto"); ap.add_argument("--dense", default="auto")
     ap.add_argument("--residual", default="auto"); ap.add_argument("--tile", default="auto")
     ap.add_argument("--stages", type=int, default=0); ap.add_argument("--tiles", default="auto")
+    ap.add_argument("--operands", default="exact")
     ap.add_argument("--host-gen", action="store_true", help="R-MAT from the host generator (tests' matrices)")
     a = ap.parse_args()
     import torch
@@ -59,7 +60,7 @@ def main():
         ro = torch.from_numpy(S.row_off.view(np.int32)).cuda()
         ci = torch.from_numpy(S.col_idx.view(np.int32)).cuda()
     a.ci = ci
-    a.plan_obj = pkg.make_plan(a.plan, a.dense, a.residual, a.tile, a.stages)
+    a.plan_obj = pkg.make_plan(a.plan, a.dense, a.residual, a.tile, a.stages, a.operands)
     if a.reorder:
         bs = pkg.calculateBlockSize(S, 180 * 10 ** 9)
         R, ncl, row_ms = pkg.row_reorder_dev(ro, ci, S.M, S.N, a.alpha, bs)
@@ -83,7 +84,7 @@ def run_k(a, torch, pkg, gen, S, lay, K, ncl, row_ms, col_ms, rphm_ms):
     dB = torch.rand((S.N, K), device="cuda", generator=g) * 2
     dP = torch.zeros(max(1, S.nnz), dtype=torch.float32, device="cuda")
     names = pkg.plan_resolve(lay, K, 1, a.plan_obj)
-    if (a.plan, a.dense, a.residual, a.tile) == ("auto",) * 4:
+    if (a.plan, a.dense, a.residual, a.tile, a.operands) == ("auto",) * 4 + ("exact",):
         t = pkg.sddmm_gpu_timed(dA, dB, lay, dP, warmup=3, iters=a.iters)
     else:  # forced kernels: time whole passes with events on the current stream
         pkg.sddmm_prepare(lay, K, 1, a.plan_obj)
