@@ -671,9 +671,24 @@ void build_quads(TileLayout& T) {
   SB_CUDA(cudaMemcpy(T.quadTiles.get(), members.data(), members.size() * 4, cudaMemcpyHostToDevice));
 }
 
-const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStream_t s) {
+namespace {
+__global__ void k_col_degree(const u32* __restrict__ col, size_t n, u32* __restrict__ deg) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    atomicAdd(deg + col[i], 1u);
+}
+__global__ void k_flag_tail_cols(u32* __restrict__ col, size_t n, const u32* __restrict__ deg, u32 minDegree) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const u32 c = col[i];
+    if (deg[c] < minDegree) col[i] = c | 0x80000000u;
+  }
+}
+}  // namespace
+
+const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, u32 hubBudget, cudaStream_t s) {
+  if (L->info.N >= 0x80000000u) hubBudget = 0;  // bit 31 of a column index is not free
+  const u64 key = (u64)G | ((u64)hubBudget << 32);
   {
-    auto it = L->sp.find(G);
+    auto it = L->sp.find(key);
     if (it != L->sp.end()) return it->second.get();
   }
   TempScope tempScope(s);
@@ -687,7 +702,7 @@ const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStre
   const u32 n = I.numSparseValues;
   if (n == 0 || P == 0) {
     sp->numWork = 0;
-    return (L->sp[G] = std::move(sp)).get();
+    return (L->sp[key] = std::move(sp)).get();
   }
   const int rowBits = bits_for(sp->rows - 1), colBits = bits_for(I.N), spBits = bits_for(sp->numSp);
   const u32* vOff = L->arr[BSMR_SPARSE_VALUE_OFFSETS].get();
@@ -712,6 +727,39 @@ const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStre
                                          sp->row.get(), sp->idx.get(), nRuns.get());
   SB_LAUNCH_CHECK();
   sp->numRuns = read_u32(nRuns.get(), s);
+  if (hubBudget) {
+    // residency classes: column degrees over the residual entries, the degree threshold that keeps at most
+    // hubBudget columns, then the flag (bit 31) on every entry of a tail column
+    DevBuf<u32> deg(I.N);
+    SB_CUDA(cudaMemsetAsync(deg.get(), 0, (size_t)I.N * 4, s));
+    k_col_degree<<<grid_for(n), 256, 0, s>>>(sp->col.get(), n, deg.get());
+    SB_LAUNCH_CHECK();
+    std::vector<u32> h(I.N);
+    SB_CUDA(cudaMemcpyAsync(h.data(), deg.get(), (size_t)I.N * 4, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    constexpr u32 kCap = 1u << 20;
+    std::vector<u64> cnt(kCap + 1, 0), ent(kCap + 1, 0);
+    for (u32 d : h) {
+      const u32 b = d < kCap ? d : kCap;
+      cnt[b] += 1;
+      ent[b] += d;
+    }
+    u64 cols = 0, entries = 0;
+    u32 minDeg = kCap + 1;
+    for (u32 d = kCap; d >= 2; --d) {  // a column referenced once has nothing to gain from residency
+      if (cols + cnt[d] > hubBudget) break;
+      cols += cnt[d];
+      entries += ent[d];
+      minDeg = d;
+    }
+    sp->hubCols = (u32)cols;
+    sp->hubEntries = entries;
+    sp->hubMinDegree = minDeg;
+    sp->colMask = 0x7FFFFFFFu;
+    k_flag_tail_cols<<<grid_for(n), 256, 0, s>>>(sp->col.get(), n, deg.get(), minDeg);
+    SB_LAUNCH_CHECK();
+    SB_CUDA(cudaStreamSynchronize(s));
+  }
   // segment size: 32768 entries, shrunk for small problems so that there are several CTAs per SM
   {
     const u32 target = (u32)device_sm_count() * 4u;
@@ -742,7 +790,7 @@ const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStre
     sp->work = std::move(sorted);
   }
   SB_CUDA(cudaStreamSynchronize(s));
-  return (L->sp[G] = std::move(sp)).get();
+  return (L->sp[key] = std::move(sp)).get();
 }
 
 // ---- row-stream residual layout (K7c): residual entries sorted by (reordered row position, column)

@@ -11,6 +11,12 @@ namespace sb {
 // so that one B^T row fetched from L2 is reused from registers by every entry of that column.
 struct SuperPanelLayout {
   u32 G = 0, rows = 0, numSp = 0, segLen = 0, numWork = 0, numEntries = 0, numRuns = 0;
+  // L2 residency classes (graphs, B >> L2): the `hubCols` most referenced columns -- as many B^T rows as may stay
+  // in the L2 -- keep bit 31 of `col` clear and are loaded evict_last; every other ("tail") column has bit 31 set
+  // and streams through evict_first, so one-time rows cannot wash the hub rows out.  colMask strips the flag
+  // (0xFFFFFFFF = unflagged layout).
+  u32 hubCols = 0, hubMinDegree = 0, colMask = 0xFFFFFFFFu;
+  u64 hubEntries = 0;
   DevBuf<u32> off;              // [numSp+1] entry ranges per super-panel
   DevBuf<u32> col, idx;         // per entry: column, CSR index
   DevBuf<unsigned short> row;   // per entry: row inside the super-panel
@@ -93,7 +99,7 @@ struct bsmr_layout {
     ~DenseTma() { if (busy) cudaEventDestroy(busy); }
   };
   mutable std::map<sb::u64, std::unique_ptr<DenseTma>> dtma;            // key = K << 32 | numBatch
-  mutable std::map<sb::u32, std::unique_ptr<sb::SuperPanelLayout>> sp;  // key = G (panels per super-panel)
+  mutable std::map<sb::u64, std::unique_ptr<sb::SuperPanelLayout>> sp;  // key = G | hub budget << 32
   mutable std::unique_ptr<sb::StreamLayout> st;                         // K-independent, built on first use
   std::unique_ptr<sb::TileLayout> tl;                // built with the layout when S is dense enough to consider it
   // two-slot pipeline of sddmm_run_host_async
@@ -128,7 +134,8 @@ void layout_save(const bsmr_layout* L, const char* path);
 bsmr_layout* layout_load(const char* path);
 
 // builds (once, then cached) the super-panel layout for G panels per super-panel; returns it
-const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, cudaStream_t s);
+// hubBudget: number of B^T rows that may be kept L2-resident (0 = no residency classes)
+const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, u32 hubBudget, cudaStream_t s);
 // builds (once) the row-ordered residual layout of the row-stream kernel
 const StreamLayout* ensure_stream(const bsmr_layout* L, cudaStream_t s);
 

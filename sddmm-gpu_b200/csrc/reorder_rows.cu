@@ -453,9 +453,9 @@ struct ClusterBatchArgs {
 // alpha - tol, the same margin the estimate path uses, so a rejection here is a rejection there.
 __device__ __forceinline__ bool cb_sig_may_join(float sh, float exRep, float nRepInv, float Sa, float exCmp,
                                                 float nCmpInv, float Sb, float thr) {
+  // ub / (Sa + Sb - ub) * 1.0002 < thr   <=>   ub * (1.0002 + thr) < thr * (Sa + Sb)      (den > 0: ub <= min(Sa, Sb))
   const float ub = fminf((sh + exRep) * nRepInv, (sh + exCmp) * nCmpInv);
-  const float den = Sa + Sb - ub;
-  return !(den > 0.f && (ub / den) * 1.0001f < thr);
+  return !(ub * (1.0002f + thr) < thr * (Sa + Sb));
 }
 
 // block 0 only: the next (up to G) unclustered positions at or after `from`, in order

@@ -169,7 +169,7 @@ static __global__ void __launch_bounds__(kThreads, 1)
 k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restrict__ B4, const u32* __restrict__ R,
                     u32 nR, u32 spRows, u32 segLen, const u32* __restrict__ spOff, const u32* __restrict__ spCol,
                     const unsigned short* __restrict__ spRow, const u32* __restrict__ spIdx,
-                    const uint2* __restrict__ work, float* __restrict__ P, BatchStrides bs) {
+                    const uint2* __restrict__ work, float* __restrict__ P, BatchStrides bs, u32 colMask) {
   extern __shared__ float4 sA[];  // spRows x K4 (fp32), or the same count of 4-half groups when kHalfA
   uint2* sH = reinterpret_cast<uint2*>(sA);
   A4 += (bs.a >> 2) * blockIdx.y;
@@ -265,10 +265,13 @@ k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restri
           const int t = h * U + u;
           const u32 e = base + t;
           const bool live = e >= gBeg && e < gEnd;
-          const float4* __restrict__ b = B4 + (size_t)cols[t] * K4 + gl;
+          const float4* __restrict__ b = B4 + (size_t)(cols[t] & colMask) * K4 + gl;
+          const u64 pol = (cols[t] & ~colMask) ? polS : polB;  // tail column: stream through the L2
+          // (reusing the previous entry's fragment when the column repeats was tried: the register copy has to
+          //  wait for that entry's load, and in-order issue then serialises the loads behind it -- 2x slower)
 #pragma unroll
           for (int j = 0; j < NB; ++j)
-            bq[u][j] = live ? (kHints ? ldg_f4_policy(b + j * 8, polB) : __ldg(b + j * 8)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            bq[u][j] = live ? (kHints ? ldg_f4_policy(b + j * 8, pol) : __ldg(b + j * 8)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -296,9 +299,10 @@ k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restri
       const bool live = e >= gBeg && e < gEnd;
       const u32 col = cols[t];
       if (live && col != prevCol) {  // this group moves on to a new column
-        const float4* __restrict__ b = B4 + (size_t)col * K4 + gl;
+        const float4* __restrict__ b = B4 + (size_t)(col & colMask) * K4 + gl;
+        const u64 pol = (col & ~colMask) ? polS : polB;  // tail column: stream through the L2
 #pragma unroll
-        for (int j = 0; j < NB; ++j) breg[j] = kHints ? ldg_f4_policy(b + j * 8, polB) : __ldg(b + j * 8);
+        for (int j = 0; j < NB; ++j) breg[j] = kHints ? ldg_f4_policy(b + j * 8, pol) : __ldg(b + j * 8);
         prevCol = col;
       }
       const u32 a = rows[t] * K4 + gl;
@@ -1623,6 +1627,24 @@ static const bsmr_layout::DenseTma* ensure_dense_tma(const bsmr_layout* L, u32 K
 // =============================================================================================
 // plan resolution + launcher
 // =============================================================================================
+// L2 eviction policy of the super-panel kernel: wanted when B (N x K floats) cannot live in the 126 MB L2 next to A
+// and the layout.  hub_budget = how many B^T rows may then be pinned (evict_last): 60 % of the L2.
+static int l2_hint_cfg() {
+  const char* e = getenv("SDDMM_B200_L2_HINTS");
+  return e ? atoi(e) : -1;
+}
+static bool l2_hints_wanted(const bsmr_layout* L, u32 K) { return (size_t)L->info.N * K * 4 > ((size_t)48 << 20); }
+static u32 hub_budget(const bsmr_layout* L, u32 K) {
+  static const int cfg = l2_hint_cfg();
+  static const int hubCfg = [] { const char* e = getenv("SDDMM_B200_L2_HUB_MB"); return e ? atoi(e) : -1; }();
+  if (cfg == 0 || (cfg < 0 && !l2_hints_wanted(L, K))) return 0;
+  if (hubCfg == 0) return 0;
+  int dev = 0, l2 = 0;
+  SB_CUDA(cudaGetDevice(&dev));
+  SB_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
+  const size_t bytes = hubCfg > 0 ? (size_t)hubCfg << 20 : (size_t)l2 / 10 * 6;
+  return (u32)std::min<size_t>(bytes / ((size_t)K * 4), 0x7FFFFFFFu);
+}
 static u32 env_choice(const char* name, std::initializer_list<std::pair<const char*, u32>> table) {
   const char* e = getenv(name);
   if (!e) return 0u;
@@ -1720,7 +1742,7 @@ void plan_prepare(const bsmr_layout* L, u32 K, u32 numBatch, const sddmm_plan& p
   }
   if (p.dense == SDDMM_DENSE_TMA) ensure_dense_tma(L, K, numBatch, s);
   if (p.residual == SDDMM_RESIDUAL_SUPERPANEL)
-    ensure_superpanels(L, superpanel_G(K, p.operands == SDDMM_OPERANDS_FP16), s);
+    ensure_superpanels(L, superpanel_G(K, p.operands == SDDMM_OPERANDS_FP16), hub_budget(L, K), s);
   if (p.residual == SDDMM_RESIDUAL_STREAM) ensure_stream(L, s);
 }
 
@@ -1873,7 +1895,7 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
       }
     } else if (p.residual == SDDMM_RESIDUAL_SUPERPANEL) {
       const bool halfA = p.operands == SDDMM_OPERANDS_FP16;
-      const SuperPanelLayout* sp = ensure_superpanels(L, superpanel_G(K, halfA), sparseStream);
+      const SuperPanelLayout* sp = ensure_superpanels(L, superpanel_G(K, halfA), hub_budget(L, K), sparseStream);
       if (sp->numWork) {
         const size_t smem = (size_t)sp->rows * K * (halfA ? 2 : 4);
         auto launch = [&](auto kern, int threads) {
@@ -1881,13 +1903,13 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
           kern<<<dim3(sp->numWork, numBatch), threads, smem, sparseStream>>>(
               I.M, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB), arr(BSMR_REORDERED_ROWS),
               I.numRows, sp->rows, sp->segLen, sp->off.get(), sp->col.get(), sp->row.get(), sp->idx.get(),
-              sp->work.get(), dP, bst);
+              sp->work.get(), dP, bst, sp->colMask);
         };
         // eviction hints when B (N x K floats) cannot live in the 126 MB L2 next to A and the layout; gather mode
         // (several B^T rows in flight, no column-run reuse) when a run averages fewer than 1.5 entries
-        static const int hintCfg = [] { const char* e = getenv("SDDMM_B200_L2_HINTS"); return e ? atoi(e) : -1; }();
+        static const int hintCfg = l2_hint_cfg();
         static const int gatherCfg = [] { const char* e = getenv("SDDMM_B200_SP_GATHER"); return e ? atoi(e) : -1; }();
-        const bool hints = hintCfg >= 0 ? hintCfg != 0 : (size_t)I.N * K * 4 > ((size_t)48 << 20);
+        const bool hints = hintCfg >= 0 ? hintCfg != 0 : l2_hints_wanted(L, K);
         // measured on R-MAT scale 22: gather mode 2.07 -> 1.17 ms at K=32 and 2.46 -> 2.03 ms at K=64, but 3.58 -> 4.00
         // ms at K=128 and worse above (there one row per 8 lanes already keeps 64 KB per SM in flight and the L2
         // fabric, ~8.5 TB/s of gathered rows, is the limit), hence K <= 64

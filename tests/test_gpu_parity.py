@@ -581,3 +581,79 @@ def test_layout_cache_rejects_tampered_files(tmp_path):
     last = off2 + 8 + 4 * (n2 - 1)
     bad[last: last + 4] = (n1 + 16).to_bytes(4, "little")
     expect_reject(bad, "offsets")
+
+
+# ---- BASELINE configs at FULL size (the oracle cannot run these: size-independent properties instead) --------------
+def _full_size_properties(torch, ro, ci, ro_host, M, N, nnz, K, R, label, plan=None):
+    """(i) every P entry written exactly once (NaN canary), (ii) exact linearity under a power-of-two scale,
+    (iii) idempotence, (iv) sampled rows against fp64 on the device with the reference's checkData rule,
+    (v) the layout's entry counts add up to nnz."""
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    dA = torch.rand((M, K), device="cuda", generator=g) * 2
+    dB = torch.rand((N, K), device="cuda", generator=g) * 2
+    lay, _, _ = pkg.layout_build_dev(ro, ci, M, N, R, 0.3)
+    info = lay.info
+    assert int(info.numDenseValues) + int(info.numSparseValues) == nnz, label
+    P1 = torch.full((nnz,), float("nan"), device="cuda")
+    pkg.sddmm_gpu(dA, dB, lay, P1, plan=plan)
+    torch.cuda.synchronize()
+    assert not torch.isnan(P1).any(), label
+    P2 = torch.zeros(nnz, device="cuda")
+    pkg.sddmm_gpu(dA * 2, dB, lay, P2, plan=plan)
+    torch.cuda.synchronize()
+    assert torch.equal(P2, 2 * P1), label
+    P2.zero_()
+    pkg.sddmm_gpu(dA, dB, lay, P2, plan=plan)
+    torch.cuda.synchronize()
+    assert torch.equal(P2, P1), label
+    rows = np.random.default_rng(1).choice(M, 48, replace=False)
+    for r in rows:
+        b, e = int(ro_host[r]), int(ro_host[r + 1])
+        if e <= b:
+            continue
+        ref = (dA[int(r)].double()[None, :] * dB[ci[b:e].to(torch.int64)].double()).sum(1)
+        err = (P1[b:e].double() - ref).abs()
+        assert bool(((err < 1e-5) | (err / ref.abs().clamp_min(1e-3) < 1e-3)).all()), (label, int(r))  # checkData.hpp:14-30
+    return info
+
+
+def test_full_size_config4_rmat22_properties(torch_mod):
+    """BASELINE config 4 at full size: R-MAT scale 22 (4.19 M rows, ~65 M stored entries), K=128, generated on the
+    device; identity row order over the non-empty rows (the 37 s clustering is exercised by bench.py)."""
+    torch = torch_mod
+    ro, ci, M = gen.rmat_device(22, 16, 4)
+    ro_host = ro.cpu().numpy().view(np.uint32)
+    R = torch.nonzero((ro[1:] - ro[:-1]) != 0).flatten().to(torch.int32)
+    info = _full_size_properties(torch, ro, ci, ro_host, M, M, int(ci.numel()), 128, R, "config 4")
+    assert info.numRowPanels == (R.numel() + 15) // 16
+
+
+@pytest.mark.parametrize("sparsity,kind", [(0.70, "bern"), (0.80, "dlmc"), (0.90, "dlmc"), (0.95, "bern"), (0.98, "dlmc")])
+@pytest.mark.parametrize("K", [64, 256])
+def test_full_size_config3_masks_values_vs_oracle(sparsity, kind, K):
+    """BASELINE config 3 at full size: 4096 x 4096 masks at 70-98 % sparsity, K = 64 / 256, whole pipeline on host
+    buffers (reorder -> layout -> SDDMM with whatever plan the cost model picks) against the oracle's sddmm_cpu +
+    checkData; the permutation against the oracle's pruned clustering."""
+    S = gen.bernoulli_mask(4096, 4096, sparsity, 30) if kind == "bern" else gen.dlmc_magnitude_mask(4096, 4096, sparsity, 33)
+    A, B = operands(S, K)
+    res = pkg.sddmm(S, A, B, alpha=0.3, delta=0.3, block_size=16)
+    assert O.check_data(O.sddmm_cpu(S, A, B), res["P"]) == 0
+    assert res["numDenseValues"] + res["numSparseValues"] == S.nnz
+    lens = np.diff(S.row_off.astype(np.int64))
+    assert np.array_equal(np.sort(res["reorderedRows"]), np.nonzero(lens)[0])
+
+
+def test_full_size_config5_rmat25_properties(torch_mod):
+    """BASELINE config 5 at full size: R-MAT scale 25 (33.5 M rows, ~529 M stored entries) generated on the device;
+    K=64 keeps the operands at 8.6 GB each (the K=256 run is bench.py's); identity row order.  Exercises 64-bit
+    addressing (M*K > 2^31 elements) and the 2^29-entry layouts."""
+    torch = torch_mod
+    free, _ = torch.cuda.mem_get_info()
+    if free < 90e9:
+        pytest.skip("needs ~90 GB of free device memory")
+    ro, ci, M = gen.rmat_device(25, 16, 5)
+    ro_host = ro.cpu().numpy().view(np.uint32)
+    R = torch.nonzero((ro[1:] - ro[:-1]) != 0).flatten().to(torch.int32)
+    _full_size_properties(torch, ro, ci, ro_host, M, M, int(ci.numel()), 64, R, "config 5")
+    del ro, ci, R
+    torch.cuda.empty_cache()
