@@ -591,8 +591,9 @@ def record_rmat(ctx, w, headline=True, scale=None, K=None, reorder=True, steps=N
     return rec
 
 
-def record_single(ctx, name, w, K=None, steps=None, warmup=None, e2e=True, cpu=True, headline=False):
-    """single-GPU record (configs 2 / 3 and the block-structured case): whole pipeline on this GPU."""
+def record_single(ctx, name, w, K=None, steps=None, warmup=None, e2e=True, cpu=True, headline=False, plan_kw=None):
+    """single-GPU record (configs 2 / 3 and the block-structured case): whole pipeline on this GPU.
+    plan_kw: keywords of host.make_plan for a non-default plan (the opt-in fp16-operand records)."""
     torch, pkg, args, gen = ctx.torch, ctx.pkg, ctx.args, ctx.gen
     K = K or (args.K if headline and args.K else w["K"])
     steps = steps or args.steps
@@ -610,8 +611,9 @@ def record_single(ctx, name, w, K=None, steps=None, warmup=None, e2e=True, cpu=T
     R, ncl, row_ms = pkg.row_reorder_dev(ro, ci, S.M, S.N, alpha, bs)
     lay, col_ms, rphm_ms = pkg.layout_build_dev(ro, ci, S.M, S.N, R, delta)
     info = lay.info
-    pkg.sddmm_prepare(lay, K)
-    plan_names = pkg.plan_resolve(lay, K)
+    plan = pkg.make_plan(**plan_kw) if plan_kw else None
+    pkg.sddmm_prepare(lay, K, 1, plan)
+    plan_names = pkg.plan_resolve(lay, K, 1, plan)
 
     sampler = ClockSampler(ctx.local)
     sampler.start()
@@ -621,19 +623,23 @@ def record_single(ctx, name, w, K=None, steps=None, warmup=None, e2e=True, cpu=T
     if use_graph:
         side = torch.cuda.Stream()
         with torch.cuda.stream(side):
-            pkg.sddmm_gpu(dA, dB, lay, dP)
+            pkg.sddmm_gpu(dA, dB, lay, dP, plan=plan)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
-                pkg.sddmm_gpu(dA, dB, lay, dP)
+                pkg.sddmm_gpu(dA, dB, lay, dP, plan=plan)
         launches_per_step = pkg.launch_count() // 2
         step = graph.replay
     else:
-        pkg.sddmm_gpu(dA, dB, lay, dP)
+        pkg.sddmm_gpu(dA, dB, lay, dP, plan=plan)
         launches_per_step = pkg.launch_count()
-        step = lambda: pkg.sddmm_gpu(dA, dB, lay, dP)  # noqa: E731
+        step = lambda: pkg.sddmm_gpu(dA, dB, lay, dP, plan=plan)  # noqa: E731
     ms = ctx.timed_steps(step, warmup, steps)
-    kt = pkg.sddmm_gpu_timed(dA, dB, lay, dP, warmup=2, iters=max(3, min(steps, 10)))
+    if plan is None:
+        kt = pkg.sddmm_gpu_timed(dA, dB, lay, dP, warmup=2, iters=max(3, min(steps, 10)))
+    else:  # forced plan: one kernel class serves the pass; its time is the step time
+        kt = dict(dense_ms=ms if plan_names["plan"] == "tile" else 0.0, sparse_ms=0.0 if plan_names["plan"] == "tile" else ms,
+                  total_ms=ms)
     clocks = sampler.stop()
     value = 2.0 * S.nnz * K / (ms * 1e-3) / 1e9
     rows = np.random.default_rng(0).choice(S.M, min(8, S.M), replace=False)
@@ -675,6 +681,7 @@ def record_single(ctx, name, w, K=None, steps=None, warmup=None, e2e=True, cpu=T
     roof = kernel_roofline(ctx, lay, K, kt, int(info.numRows), cols_touched, S.M, S.nnz, f"{name}_k{K}", plan_names)
     cfg = base_config(w["desc"], S.M, S.N, S.nnz, K, alpha, delta)
     all_tf32 = plan_names["plan"] == "tile"
+    fp16 = plan_names.get("operands") == "fp16"
     cfg.update(block_size=int(bs), reordered=True, parallelism="single GPU", cuda_graph_per_step=bool(use_graph),
                l2=("working set >> 126 MB L2, no flush" if 4.0 * K * (S.M + S.N) + 20.0 * S.nnz > 200e6
                    else "working set fits the 126 MB L2: L2-resident by design (the reference's loop is the same)"),
@@ -684,7 +691,8 @@ def record_single(ctx, name, w, K=None, steps=None, warmup=None, e2e=True, cpu=T
                max_rel_err_sample=worst)
     rec = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=1, steps=steps, warmup=warmup, ms_per_step=ms,
                higher_is_better=True, scaling="weak", vs_baseline=None,
-               dtype=("tf32 for ALL entries (whole 128x128 tcgen05 tiles), fp32 accumulate" if all_tf32
+               dtype=("fp16 operand copies (opt-in sddmm_plan.operands), fp32 accumulate" if fp16
+                      else "tf32 for ALL entries (whole 128x128 tcgen05 tiles), fp32 accumulate" if all_tf32
                       else "tf32 (dense blocks, fp32 accumulate) / f32 (residual)"),
                data="synthetic", config=cfg, clocks=clocks, gpu_launches=int(launches_per_step * steps),
                gpu_launches_per_step=int(launches_per_step), roofline=roof)
@@ -731,14 +739,19 @@ def run_ours(args, w):
             except Exception as e:  # never lose the headline to an optional record
                 also["config5_rmat25_k256"] = dict(error=str(e)[:300])
         if ctx.world == 1:
-            for name, K in (("uniform100k", 128), ("dlmc4096_s70", 256), ("dlmc4096_s70", 64), ("dlmc4096_s90", 256),
-                            ("dlmc4096_s98", 64), ("blockscat16k", 128)):
+            fp16_sp = dict(plan="bsmr", residual="superpanel", operands="fp16")
+            fp16_tile = dict(plan="tile", tile="tma", operands="fp16")
+            for name, K, plan_kw in (("uniform100k", 128, None), ("dlmc4096_s70", 256, None), ("dlmc4096_s70", 64, None),
+                                     ("dlmc4096_s90", 256, None), ("dlmc4096_s98", 64, None), ("blockscat16k", 128, None),
+                                     # opt-in fp16 operand copies: NOT the default arithmetic, labelled in `dtype`
+                                     ("uniform100k", 128, fp16_sp), ("dlmc4096_s70", 256, fp16_tile)):
+                key = f"{name}_k{K}" + ("_fp16_operands" if plan_kw else "")
                 try:
-                    r = record_single(ctx, name, WORKLOADS[name], K=K, steps=10, warmup=3, e2e=(name == "uniform100k"),
-                                      cpu=False)
-                    also[f"{name}_k{K}"] = slim(r) if name != "uniform100k" else {**slim(r), "e2e": r["e2e"]}
+                    r = record_single(ctx, name, WORKLOADS[name], K=K, steps=10, warmup=3,
+                                      e2e=(name == "uniform100k" and plan_kw is None), cpu=False, plan_kw=plan_kw)
+                    also[key] = slim(r) if "e2e" not in r else {**slim(r), "e2e": r["e2e"]}
                 except Exception as e:
-                    also[f"{name}_k{K}"] = dict(error=str(e)[:300])
+                    also[key] = dict(error=str(e)[:300])
     if ctx.rank == 0:
         if also:
             rec["config"]["also"] = also
