@@ -229,13 +229,15 @@ int sddmm_run_dev(const bsmr_layout*, uint32_t K, const float* d_A, const float*
  *            STREAM = k_sddmm_residual_stream (same K; entries in row order, A fragment in registers, up to 8
  *                         gathered B^T rows in flight per lane, L2 eviction hints: graphs, where B >> L2)
  *   tile     REG / TMA / TMA_CLUSTER = k_sddmm_tile / k_sddmm_tile_tma / k_sddmm_tile_tma4
+ *            TMA_PAIR = k_sddmm_tile_pair: persistent CTA pairs, one 256x256 tcgen05.mma.cta_group::2 accumulator
+ *                       per 2x2 group of tiles, double-buffered in TMEM (epilogue under the next main loop)
  * AUTO everywhere = the library's cost model (the defaults of sddmm_run_dev).  A choice that cannot serve the
  * call (SUPERPANEL with K = 36, TILE on a layout built with BSMR_BUILD_TILES_NEVER ...) fails with
  * SDDMM_E_UNSUPPORTED instead of silently running something else. */
 enum { SDDMM_PLAN_AUTO = 0, SDDMM_PLAN_BSMR = 1, SDDMM_PLAN_TILE = 2 };
 enum { SDDMM_DENSE_AUTO = 0, SDDMM_DENSE_REG = 1, SDDMM_DENSE_TMA = 2 };
 enum { SDDMM_RESIDUAL_AUTO = 0, SDDMM_RESIDUAL_PANEL = 1, SDDMM_RESIDUAL_SUPERPANEL = 2, SDDMM_RESIDUAL_STREAM = 3 };
-enum { SDDMM_TILE_AUTO = 0, SDDMM_TILE_REG = 1, SDDMM_TILE_TMA = 2, SDDMM_TILE_TMA_CLUSTER = 3 };
+enum { SDDMM_TILE_AUTO = 0, SDDMM_TILE_REG = 1, SDDMM_TILE_TMA = 2, SDDMM_TILE_TMA_CLUSTER = 3, SDDMM_TILE_TMA_PAIR = 4 };
 /* operands  EXACT = the reference's arithmetic: TF32 (round-to-nearest) operands into the tensor cores for dense
  *                   blocks / tiles, fp32 operands for the residual; fp32 accumulation everywhere (the default)
  *           FP16  = fp16 (round-to-nearest) copies of the operands where that halves the limiting traffic: the A

@@ -51,7 +51,7 @@ class ReorderOpts(C.Structure):
 PLAN = dict(auto=0, bsmr=1, tile=2)
 DENSE = dict(auto=0, reg=1, tma=2)
 RESIDUAL = dict(auto=0, panel=1, superpanel=2, stream=3)
-TILE = dict(auto=0, reg=1, tma=2, tma_cluster=3)
+TILE = dict(auto=0, reg=1, tma=2, tma_cluster=3, tma_pair=4)
 OPERANDS = dict(exact=0, fp16=1)
 CLUSTER = dict(auto=0, legacy=1, batched=2)
 TRISTATE = dict(auto=0, off=1, on=2)

@@ -676,6 +676,14 @@ __global__ void k_col_degree(const u32* __restrict__ col, size_t n, u32* __restr
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     atomicAdd(deg + col[i], 1u);
 }
+__global__ void k_deg_to_flag(const u32* __restrict__ deg, u32 n, u32* __restrict__ flag) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    flag[i] = deg[i] ? 1u : 0u;
+}
+__global__ void k_compact_flagged(const u32* __restrict__ flag, const u32* __restrict__ ex, u32 n, u32* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    if (flag[i]) out[ex[i]] = (u32)i;
+}
 __global__ void k_flag_tail_cols(u32* __restrict__ col, size_t n, const u32* __restrict__ deg, u32 minDegree) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const u32 c = col[i];
@@ -727,13 +735,25 @@ const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, u32 hubB
                                          sp->row.get(), sp->idx.get(), nRuns.get());
   SB_LAUNCH_CHECK();
   sp->numRuns = read_u32(nRuns.get(), s);
-  if (hubBudget) {
-    // residency classes: column degrees over the residual entries, the degree threshold that keeps at most
-    // hubBudget columns, then the flag (bit 31) on every entry of a tail column
-    DevBuf<u32> deg(I.N);
-    SB_CUDA(cudaMemsetAsync(deg.get(), 0, (size_t)I.N * 4, s));
-    k_col_degree<<<grid_for(n), 256, 0, s>>>(sp->col.get(), n, deg.get());
+  // column degrees over the residual entries -> the list of referenced columns (and the residency classes below)
+  DevBuf<u32> deg(I.N);
+  SB_CUDA(cudaMemsetAsync(deg.get(), 0, (size_t)I.N * 4, s));
+  k_col_degree<<<grid_for(n), 256, 0, s>>>(sp->col.get(), n, deg.get());
+  SB_LAUNCH_CHECK();
+  {
+    DevBuf<u32> flag(I.N), ex((size_t)I.N + 1);
+    k_deg_to_flag<<<grid_for(I.N), 256, 0, s>>>(deg.get(), I.N, flag.get());
     SB_LAUNCH_CHECK();
+    scan_counts(flag.get(), ex.get(), I.N, s);
+    sp->numUsedCols = read_u32(ex.get() + I.N, s);
+    sp->usedCols.alloc(sp->numUsedCols ? sp->numUsedCols : 1u, true);
+    k_compact_flagged<<<grid_for(I.N), 256, 0, s>>>(flag.get(), ex.get(), I.N, sp->usedCols.get());
+    SB_LAUNCH_CHECK();
+    SB_CUDA(cudaStreamSynchronize(s));
+  }
+  if (hubBudget) {
+    // residency classes: the degree threshold that keeps at most hubBudget columns, then the flag (bit 31) on every
+    // entry of a tail column
     std::vector<u32> h(I.N);
     SB_CUDA(cudaMemcpyAsync(h.data(), deg.get(), (size_t)I.N * 4, cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaStreamSynchronize(s));

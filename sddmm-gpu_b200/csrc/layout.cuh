@@ -21,6 +21,10 @@ struct SuperPanelLayout {
   DevBuf<u32> col, idx;         // per entry: column, CSR index
   DevBuf<unsigned short> row;   // per entry: row inside the super-panel
   DevBuf<uint2> work;           // (super-panel, first entry of the segment inside it), segment-major
+  // distinct columns the residual references, ascending: the only B^T rows the fp16 copy of SDDMM_OPERANDS_FP16 has
+  // to rewrite per pass (half of the columns of an R-MAT graph are empty)
+  u32 numUsedCols = 0;
+  DevBuf<u32> usedCols;
 };
 }  // namespace sb
 
@@ -99,6 +103,14 @@ struct bsmr_layout {
     ~DenseTma() { if (busy) cudaEventDestroy(busy); }
   };
   mutable std::map<sb::u64, std::unique_ptr<DenseTma>> dtma;            // key = K << 32 | numBatch
+  // fp16 copy of B^T for the super-panel residual kernel under SDDMM_OPERANDS_FP16 (rewritten every pass)
+  struct HalfB {
+    sb::u32 K = 0, numBatch = 0;
+    sb::DevBuf<float> rB;  // [numBatch][N][K] halves
+    cudaEvent_t busy = nullptr;
+    ~HalfB() { if (busy) cudaEventDestroy(busy); }
+  };
+  mutable std::map<sb::u64, std::unique_ptr<HalfB>> halfB;              // key = K << 32 | numBatch
   mutable std::map<sb::u64, std::unique_ptr<sb::SuperPanelLayout>> sp;  // key = G | hub budget << 32
   mutable std::unique_ptr<sb::StreamLayout> st;                         // K-independent, built on first use
   std::unique_ptr<sb::TileLayout> tl;                // built with the layout when S is dense enough to consider it

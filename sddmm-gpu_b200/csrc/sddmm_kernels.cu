@@ -18,6 +18,8 @@
 
 #include <cstring>
 #include <initializer_list>
+#include <map>
+#include <mutex>
 #include <utility>
 
 #include "layout.cuh"
@@ -164,7 +166,28 @@ __device__ __forceinline__ void stg_f32_policy(float* p, float v, u64 pol) {
 // the shared-memory bytes per non-zero -- the limiter of reuse mode -- and doubles the rows per super-panel, hence
 // the column-run reuse of B^T.  Values stay within the reference's checkData tolerance (tests), but they are no
 // longer the fp32 results of the exact path, and |A| must stay below 65504.
-template <int NB, int kThreads, bool kHints, int U, bool kHalfA>
+// kHalfB (with kHalfA, K >= 64): the gathered B^T rows also come from an fp16 copy (k_round_b_half, once per pass), so
+// the L2 -> SM gather -- the limiter on graphs -- halves as well: a lane holds 8 consecutive K values of both
+// operands per 128-bit word and multiplies them with the mixed-precision fma.rn.f32.f16 (SASS FHFMA: fp16 x fp16
+// product, exact in fp32, added to an fp32 accumulator) -- no conversion instructions at all.
+__device__ __forceinline__ void fhfma2(float& acc, u32 a, u32 b) {
+  asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\t"
+      "fma.rn.f32.f16 %0, al, bl, %0;\n\tfma.rn.f32.f16 %0, ah, bh, %0;\n\t}"
+      : "+f"(acc)
+      : "r"(a), "r"(b));
+}
+__device__ __forceinline__ void fhfma8(float& acc0, float& acc1, const uint4& a, const uint4& b) {
+  fhfma2(acc0, a.x, b.x); fhfma2(acc1, a.y, b.y); fhfma2(acc0, a.z, b.z); fhfma2(acc1, a.w, b.w);
+}
+__device__ __forceinline__ uint4 ldg_u4_policy(const uint4* p, u64 pol) {
+  uint4 v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+      : "l"(p), "l"(pol));
+  return v;
+}
+
+template <int NB, int kThreads, bool kHints, int U, bool kHalfA, bool kHalfB = false>
 static __global__ void __launch_bounds__(kThreads, 1)
 k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restrict__ B4, const u32* __restrict__ R,
                     u32 nR, u32 spRows, u32 segLen, const u32* __restrict__ spOff, const u32* __restrict__ spCol,
@@ -208,6 +231,11 @@ k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restri
     return make_float4(lo.x, lo.y, hi.x, hi.y);
   };
 
+  static_assert(!kHalfB || (kHalfA && NB >= 2), "fp16 B^T rows need the fp16 A tile and K >= 64");
+  constexpr int NBH = kHalfB ? NB / 2 : 1;           // 128-bit words (8 halves) per lane and row
+  constexpr u32 KH = 4 * NB;                          // 128-bit words per fp16 row
+  const uint4* __restrict__ Bh = reinterpret_cast<const uint4*>(B4);  // kHalfB: B4 is the fp16 copy
+  const uint4* sA8 = reinterpret_cast<const uint4*>(sA);
   const u32 grp = threadIdx.x >> 3, gl = threadIdx.x & 7u;
   u64 polB = 0, polS = 0;
   if (kHints) { polB = l2_policy_evict_last(); polS = l2_policy_evict_first(); }
@@ -228,9 +256,12 @@ k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restri
   const u32 aBeg = min(aStart + grp * per, (segEnd + 7u) & ~7u);
   const u32 gBeg = max(aBeg, segBeg);
   const u32 gEnd = min(segEnd, aBeg + per);
-  float4 breg[NB];
+  float4 breg[kHalfB ? 1 : NB];
+  uint4 bregH[NBH];
 #pragma unroll
-  for (int j = 0; j < NB; ++j) breg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < (kHalfB ? 1 : NB); ++j) breg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < NBH; ++j) bregH[j] = make_uint4(0u, 0u, 0u, 0u);
   u32 prevCol = 0xFFFFFFFFu;
   const uint4* col4 = reinterpret_cast<const uint4*>(spCol);
   const uint4* row4 = reinterpret_cast<const uint4*>(spRow);
@@ -256,7 +287,52 @@ k_sddmm_residual_sp(u32 M, const float4* __restrict__ A4, const float4* __restri
     const u32 rows[8] = {r8.x & 0xFFFFu, r8.x >> 16, r8.y & 0xFFFFu, r8.y >> 16,
                          r8.z & 0xFFFFu, r8.z >> 16, r8.w & 0xFFFFu, r8.w >> 16};
     float acc[8];
-    if constexpr (U > 0) {
+    if constexpr (U > 0 && kHalfB) {
+      constexpr int UH = U * 2 > 8 ? 8 : U * 2;  // same bytes in flight per lane as the fp32 form
+#pragma unroll
+      for (int h = 0; h < 8 / UH; ++h) {
+        uint4 bq[UH][NBH];
+#pragma unroll
+        for (int u = 0; u < UH; ++u) {
+          const int t = h * UH + u;
+          const u32 e = base + t;
+          const bool live = e >= gBeg && e < gEnd;
+          const uint4* __restrict__ b = Bh + (size_t)(cols[t] & colMask) * KH + gl;
+          const u64 pol = (cols[t] & ~colMask) ? polS : polB;
+#pragma unroll
+          for (int j = 0; j < NBH; ++j)
+            bq[u][j] = live ? (kHints ? ldg_u4_policy(b + j * 8, pol) : __ldg(b + j * 8)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < UH; ++u) {
+          const int t = h * UH + u;
+          const u32 a = rows[t] * KH + gl;
+          float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < NBH; ++j) fhfma8(acc0, acc1, sA8[a + j * 8], bq[u][j]);
+          acc[t] = acc0 + acc1;
+        }
+      }
+    } else if constexpr (kHalfB) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const u32 e = base + t;
+        const bool live = e >= gBeg && e < gEnd;
+        const u32 col = cols[t];
+        if (live && col != prevCol) {  // this group moves on to a new column
+          const uint4* __restrict__ b = Bh + (size_t)(col & colMask) * KH + gl;
+          const u64 pol = (col & ~colMask) ? polS : polB;
+#pragma unroll
+          for (int j = 0; j < NBH; ++j) bregH[j] = kHints ? ldg_u4_policy(b + j * 8, pol) : __ldg(b + j * 8);
+          prevCol = col;
+        }
+        const u32 a = rows[t] * KH + gl;
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NBH; ++j) fhfma8(acc0, acc1, sA8[a + j * 8], bregH[j]);
+        acc[t] = acc0 + acc1;
+      }
+    } else if constexpr (U > 0) {
 #pragma unroll
       for (int h = 0; h < 8 / U; ++h) {
         float4 bq[U][NB];
@@ -929,6 +1005,22 @@ static __global__ void __launch_bounds__(256) k_round_operands_half(u32 M, u32 N
   }
 }
 
+// fp16 copy of the listed B^T rows only (the columns the residual references): the super-panel kernel's operand
+static __global__ void __launch_bounds__(256) k_round_rows_half(const u32* __restrict__ list, u32 numList, u32 K4,
+                                                                const float4* __restrict__ B, uint2* __restrict__ Bh,
+                                                                size_t srcStride4, size_t dstStride4) {
+  B += srcStride4 * blockIdx.y;
+  Bh += dstStride4 * blockIdx.y;
+  const size_t n = (size_t)numList * K4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const u32 li = (u32)(i / K4), c = (u32)(i - (size_t)li * K4);
+    const size_t at = (size_t)__ldg(list + li) * K4 + c;
+    const float4 v = __ldg(B + at);
+    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    Bh[at] = make_uint2(*reinterpret_cast<const u32*>(&lo), *reinterpret_cast<const u32*>(&hi));
+  }
+}
+
 // bounded wait: a protocol error must end in a launch failure, never in a hung GPU
 __device__ __forceinline__ void mbar_wait_bounded(u64* bar, u32 parity) {
   const long long t0 = clock64();
@@ -1292,6 +1384,250 @@ k_sddmm_tile_tma4(const __grid_constant__ CUtensorMap mapA64, const __grid_const
 }
 
 // =============================================================================================
+// tile kernel, CTA-pair form (K10): persistent, warp-specialised, tcgen05.mma.cta_group::2.
+//   Work unit = a 2x2 group of tiles (256 rows x 256 columns of the reordered S, `quads`), computed by the two CTAs
+//   of a cluster as ONE M=256 N=256 MMA: CTA r stages its own 128 A rows and HALF of the B^T rows (128 of the 256
+//   columns), the tensor cores of both SMs read both halves, and each CTA's TMEM receives 128 rows x 256 columns.
+//   Per 128x128 output tile a CTA therefore pulls 128 operand rows through the L2 -> SM fabric instead of 256 -- the
+//   limiter of the one-tile-per-CTA form (k_sddmm_tile_tma: 256 KB per tile at K=256).
+//   Roles (320 threads): warp 0 = TMA producer (both CTAs; the loads signal the LEADER's full barrier through the
+//   cta_group::2 form of cp.async.bulk.tensor), warp 1 = MMA issuer (leader only; tcgen05.commit multicasts the
+//   stage-free and accumulator-ready arrivals to both CTAs), warps 2..9 = epilogue (TMEM -> per-row mask compaction
+//   -> shared staging -> coalesced scatter through the tile's CSR-index list, as in the other tile kernels).
+//   Two 256-column accumulators (all 512 TMEM columns): the epilogue of quad i runs under the main loop of quad
+//   i+1, and the operand ring never drains between quads.  Every wait is bounded (a protocol error traps).
+//   Same operands as K9: TF32-rounded (or fp16) row-gathered copies, 128-row SWIZZLE_128B boxes.
+// =============================================================================================
+constexpr int kTpThreads = 320;
+constexpr u32 kTpStages = 4;
+constexpr u32 kTpStagingBytes = 128u * 128u * 4u;  // one 128x128 tile's stored entries at most
+constexpr u32 kTpPrefetch = 20;  // CSR indices per epilogue thread and tile requested ahead (covers 5120 entries)
+constexpr bool kPairDefault = false;  // AUTO's choice between K9 and K10 (set from measurements)
+
+__device__ __forceinline__ u32 mapa_u32(u32 smemAddr, u32 rank) {
+  u32 r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smemAddr), "r"(rank));
+  return r;
+}
+// both CTAs of a pair load into their OWN shared memory and complete the transaction on the LEADER's barrier
+__device__ __forceinline__ void tma_load_3d_pair(u32 dstSmem, const void* map, u32 leaderBar, u32 c0, u32 c1, u32 c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dstSmem), "l"(map), "r"(leaderBar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(u64* bar) {  // arrives on `bar` of BOTH CTAs when the MMAs retire
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)), "h"((unsigned short)3)
+      : "memory");
+}
+
+template <bool kHalf>
+static __global__ void __launch_bounds__(kTpThreads, 1)
+k_sddmm_tile_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, u32 K,
+                  u32 numQuads, const uint2* __restrict__ quads, const u32* __restrict__ quadTiles,
+                  const uint4* __restrict__ tiles, const u32* __restrict__ rowMeta, const u32* __restrict__ entIdx,
+                  float* __restrict__ P, size_t pStride) {
+  extern __shared__ __align__(1024) unsigned char smemRaw[];
+  P += pStride * blockIdx.y;
+  unsigned char* stages = smemRaw + ((1024u - (smem_u32(smemRaw) & 1023u)) & 1023u);
+  float* sOut = reinterpret_cast<float*>(stages + kTpStages * kTlStageBytes);
+  __shared__ u64 fullBar[kTpStages], emptyBar[kTpStages], accFull[2], accEmpty[2];
+  __shared__ u32 tmemBase;
+
+  const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const u32 rank = cluster_ctarank();
+  const u32 pairId = blockIdx.x >> 1, numPairs = gridDim.x >> 1;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmemBase)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (u32 s = 0; s < kTpStages; ++s) {
+      mbar_init(&fullBar[s], 1);   // the leader's arrive.expect_tx (bytes of both CTAs' boxes)
+      mbar_init(&emptyBar[s], 1);  // the MMA commit, multicast to both CTAs
+    }
+    for (u32 b = 0; b < 2; ++b) {
+      mbar_init(&accFull[b], 1);    // the MMA commit of a quad's last chunk, multicast
+      mbar_init(&accEmpty[b], 16);  // 8 epilogue warps of each CTA (used on the leader only)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers and TMEM exist before any remote arrive / multicast commit / MMA
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const u32 tmem = tmemBase;
+  constexpr u32 kChunkElems = kHalf ? 64u : kDnKChunk;
+  const u32 numChunks = (K + kChunkElems - 1) / kChunkElems;
+  constexpr u32 idesc = kHalf ? umma_idesc_f16(256, 256) : umma_idesc_tf32(256, 256);
+
+  if (warp == 0) {
+    // ---- producer (both CTAs): A rows of this CTA's tile row, B^T rows of this CTA's half of the 256 columns
+    u32 g = 0;
+    for (u32 q = pairId; q < numQuads; q += numPairs) {
+      const uint2 qrc = quads[q];
+      const u32 rowA = (qrc.x * 2u + rank) * 128u, rowB = (qrc.y * 2u + rank) * 128u;
+      for (u32 kc = 0; kc < numChunks; ++kc, ++g) {
+        const u32 s = g % kTpStages;
+        if (lane == 0) {
+          if (g >= kTpStages) mbar_wait_cluster_bounded(&emptyBar[s], ((g / kTpStages) - 1) & 1u);
+          if (rank == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&fullBar[s])),
+                         "r"(2u * kTlStageBytes)
+                         : "memory");
+          const u32 bar = mapa_u32(smem_u32(&fullBar[s]), 0u);
+          const u32 dst = smem_u32(stages + s * kTlStageBytes);
+          tma_load_3d_pair(dst, &mapA, bar, kc * kChunkElems, rowA, blockIdx.y);
+          tma_load_3d_pair(dst + 128u * 128u, &mapB, bar, kc * kChunkElems, rowB, blockIdx.y);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer (leader CTA only): one M=256 N=256 accumulator per quad, alternating TMEM halves
+    if (rank == 0) {
+      u32 g = 0, t = 0;
+      for (u32 q = pairId; q < numQuads; q += numPairs, ++t) {
+        const u32 buf = t & 1u;
+        if (lane == 0 && t >= 2u) mbar_wait_cluster_bounded(&accEmpty[buf], ((t >> 1) - 1u) & 1u);
+        __syncwarp();
+        for (u32 kc = 0; kc < numChunks; ++kc, ++g) {
+          const u32 s = g % kTpStages;
+          if (lane == 0) {
+            mbar_wait_cluster_bounded(&fullBar[s], (g / kTpStages) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const u32 base = smem_u32(stages + s * kTlStageBytes);
+            const u64 dA = umma_desc_sw128(base);
+            const u64 dB = umma_desc_sw128(base + 128u * 128u);
+#pragma unroll
+            for (u32 k = 0; k < kDnKChunk / 8; ++k) {
+              const u32 acc = (kc | k) ? 1u : 0u;
+              if (kHalf)
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + buf * 256u),
+                    "l"(dA + 2ull * k), "l"(dB + 2ull * k), "r"(idesc), "r"(acc)
+                    : "memory");
+              else
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + buf * 256u),
+                    "l"(dA + 2ull * k), "l"(dB + 2ull * k), "r"(idesc), "r"(acc)
+                    : "memory");
+            }
+            umma_commit_pair(&emptyBar[s]);
+            if (kc + 1 == numChunks) umma_commit_pair(&accFull[buf]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ---- epilogue (both CTAs, 8 warps): this CTA's 128 rows x 256 columns = the quad's tiles (rank, 0), (rank, 1).
+    // Only 8 warps per SM run it, so nothing hides a global-load round trip inside the loop: the row masks and the
+    // first kTpPrefetch CSR indices per thread of BOTH tiles are requested before the accumulator is waited for.
+    const u32 et = tid - 64u, q4 = warp & 3u, half = (warp - 2u) >> 2;  // TMEM lane quarter = warp id mod 4
+    const u32 r = q4 * 32u + lane;
+    u32 t = 0;
+    for (u32 q = pairId; q < numQuads; q += numPairs, ++t) {
+      const u32 buf = t & 1u;
+      u32 tIdx[2], tBeg[2] = {0u, 0u}, tCnt[2] = {0u, 0u}, mk[2][5], pf[2][kTpPrefetch];
+#pragma unroll
+      for (u32 sub = 0; sub < 2; ++sub) {
+        tIdx[sub] = quadTiles[q * 4u + rank * 2u + sub];
+        if (tIdx[sub] != kNull) {
+          const uint4 tile = tiles[tIdx[sub]];
+          tBeg[sub] = tile.z;
+          tCnt[sub] = tile.w;
+          const u32* meta = rowMeta + (size_t)tIdx[sub] * 640u + r * 5u;
+#pragma unroll
+          for (u32 i = 0; i < 5; ++i) mk[sub][i] = __ldg(meta + i);
+#pragma unroll
+          for (u32 j = 0; j < kTpPrefetch; ++j) {
+            const u32 e = et + j * 256u;
+            pf[sub][j] = e < tCnt[sub] ? __ldg(entIdx + tBeg[sub] + e) : 0u;
+          }
+        }
+      }
+      const u32 arriveAt = tIdx[1] != kNull ? 1u : 0u;  // ONE accEmpty arrive per warp and quad, after its last TMEM read
+      mbar_wait_cluster_bounded(&accFull[buf], (t >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (u32 sub = 0; sub < 2; ++sub) {
+        if (tIdx[sub] != kNull) {
+          u32 off = mk[sub][4] - tBeg[sub];
+          if (half) off += __popc(mk[sub][0]) + __popc(mk[sub][1]);
+#pragma unroll
+          for (u32 qq = 0; qq < 2; ++qq) {
+            const u32 qd = half * 2u + qq;
+            u32 acc[32];
+            const u32 taddr = tmem + ((q4 * 32u) << 16) + buf * 256u + sub * 128u + qd * 32u;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]),
+                  "=r"(acc[7]), "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]),
+                  "=r"(acc[14]), "=r"(acc[15]), "=r"(acc[16]), "=r"(acc[17]), "=r"(acc[18]), "=r"(acc[19]),
+                  "=r"(acc[20]), "=r"(acc[21]), "=r"(acc[22]), "=r"(acc[23]), "=r"(acc[24]), "=r"(acc[25]),
+                  "=r"(acc[26]), "=r"(acc[27]), "=r"(acc[28]), "=r"(acc[29]), "=r"(acc[30]), "=r"(acc[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const u32 mw = qd == 0 ? mk[sub][0] : qd == 1 ? mk[sub][1] : qd == 2 ? mk[sub][2] : mk[sub][3];
+#pragma unroll
+            for (u32 b = 0; b < 32; ++b) {
+              if ((mw >> b) & 1u) {
+                sOut[off] = __uint_as_float(acc[b]);
+                ++off;
+              }
+            }
+          }
+        }
+        if (sub == arriveAt) {  // the accumulator half is free for the quad after next
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(&accEmpty[buf], 0u);
+        }
+        if (tIdx[sub] != kNull) {
+          asm volatile("bar.sync 1, 256;" ::: "memory");  // the tile's values are staged
+          const u32 cnt = tCnt[sub];
+#pragma unroll
+          for (u32 j = 0; j < kTpPrefetch; ++j) {
+            const u32 e = et + j * 256u;
+            if (e < cnt) P[pf[sub][j]] = sOut[e];
+          }
+          if (cnt > kTpPrefetch * 256u) {  // denser than the prefetch depth covers: the rest with loads in the loop
+            const u32* __restrict__ idx = entIdx + tBeg[sub];
+            u32 e = et + kTpPrefetch * 256u;
+            for (; e + 768u < cnt; e += 1024u) {
+              const u32 i0 = __ldg(idx + e), i1 = __ldg(idx + e + 256u), i2 = __ldg(idx + e + 512u),
+                        i3 = __ldg(idx + e + 768u);
+              P[i0] = sOut[e];
+              P[i1] = sOut[e + 256u];
+              P[i2] = sOut[e + 512u];
+              P[i3] = sOut[e + 768u];
+            }
+            for (; e < cnt; e += 256u) P[__ldg(idx + e)] = sOut[e];
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");  // staging area free again
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves (or frees TMEM) while the partner can still signal or read
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// =============================================================================================
 // dense-block kernel, TMA form (K6t): the kernel that consumes the BSMR dense blocks (replaces
 // src/sddmmKernel.cu:213-351, whose gather is the scalar __ldg loop at :279-306) with both operands staged by
 // the TMA unit.  Operands come from TF32-rounded copies (k_round_dense_rows: tcgen05 kind::tf32 truncates, the
@@ -1605,6 +1941,25 @@ static const bsmr_layout::TileTma* ensure_tile_tma(const bsmr_layout* L, u32 K, 
   return (L->tma[key] = std::move(t)).get();
 }
 
+static const bsmr_layout::HalfB* ensure_half_b(const bsmr_layout* L, u32 K, u32 numBatch) {
+  const u64 key = ((u64)K << 32) | numBatch;
+  {
+    auto it = L->halfB.find(key);
+    if (it != L->halfB.end()) return it->second.get();
+  }
+  auto t = std::make_unique<bsmr_layout::HalfB>();
+  t->K = K;
+  t->numBatch = numBatch;
+  t->rB.alloc((size_t)numBatch * L->info.N * K / 2, true);  // K halves per row = K/2 floats' room
+  SB_CUDA(cudaEventCreateWithFlags(&t->busy, cudaEventDisableTiming));
+  return (L->halfB[key] = std::move(t)).get();
+}
+// whether SDDMM_OPERANDS_FP16 also reads B^T from an fp16 copy in the super-panel kernel (K >= 64)
+static bool sp_half_b(u32 K) {
+  const int cfg = [] { const char* e = getenv("SDDMM_B200_SP_HALF_B"); return e ? atoi(e) : 1; }();
+  return cfg != 0 && K >= 64u;
+}
+
 static const bsmr_layout::DenseTma* ensure_dense_tma(const bsmr_layout* L, u32 K, u32 numBatch, cudaStream_t s) {
   const u64 key = ((u64)K << 32) | numBatch;
   {
@@ -1634,16 +1989,17 @@ static int l2_hint_cfg() {
   return e ? atoi(e) : -1;
 }
 static bool l2_hints_wanted(const bsmr_layout* L, u32 K) { return (size_t)L->info.N * K * 4 > ((size_t)48 << 20); }
-static u32 hub_budget(const bsmr_layout* L, u32 K) {
-  static const int cfg = l2_hint_cfg();
-  static const int hubCfg = [] { const char* e = getenv("SDDMM_B200_L2_HUB_MB"); return e ? atoi(e) : -1; }();
+static u32 hub_budget(const bsmr_layout* L, u32 K, bool halfB = false) {
+  // read per call (getenv is cheap next to a launch), so that tests can switch the modes inside one process
+  const int cfg = l2_hint_cfg();
+  const int hubCfg = [] { const char* e = getenv("SDDMM_B200_L2_HUB_MB"); return e ? atoi(e) : -1; }();
   if (cfg == 0 || (cfg < 0 && !l2_hints_wanted(L, K))) return 0;
   if (hubCfg == 0) return 0;
   int dev = 0, l2 = 0;
   SB_CUDA(cudaGetDevice(&dev));
   SB_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
   const size_t bytes = hubCfg > 0 ? (size_t)hubCfg << 20 : (size_t)l2 / 10 * 6;
-  return (u32)std::min<size_t>(bytes / ((size_t)K * 4), 0x7FFFFFFFu);
+  return (u32)std::min<size_t>(bytes / ((size_t)K * (halfB ? 2 : 4)), 0x7FFFFFFFu);
 }
 static u32 env_choice(const char* name, std::initializer_list<std::pair<const char*, u32>> table) {
   const char* e = getenv(name);
@@ -1651,6 +2007,12 @@ static u32 env_choice(const char* name, std::initializer_list<std::pair<const ch
   for (const auto& kv : table)
     if (!strcmp(e, kv.first)) return kv.second;
   return 0u;
+}
+
+// whether AUTO picks the CTA-pair tile kernel (K10) over the one-tile-per-CTA TMA kernel (K9)
+static bool pair_default() {
+  static const bool v = [] { const char* e = getenv("SDDMM_B200_TILE_PAIR"); return e ? atoi(e) != 0 : kPairDefault; }();
+  return v;
 }
 
 void plan_default(sddmm_plan* out) {
@@ -1661,7 +2023,7 @@ void plan_default(sddmm_plan* out) {
                                                      {"1", SDDMM_RESIDUAL_SUPERPANEL}, {"sp", SDDMM_RESIDUAL_SUPERPANEL},
                                                      {"2", SDDMM_RESIDUAL_STREAM}, {"stream", SDDMM_RESIDUAL_STREAM}});
   out->tile = env_choice("SDDMM_B200_TILE", {{"reg", SDDMM_TILE_REG}, {"tma1", SDDMM_TILE_TMA}, {"tma", SDDMM_TILE_TMA},
-                                             {"tma4", SDDMM_TILE_TMA_CLUSTER}});
+                                             {"tma4", SDDMM_TILE_TMA_CLUSTER}, {"pair", SDDMM_TILE_TMA_PAIR}});
   out->operands = env_choice("SDDMM_B200_OPERANDS", {{"fp16", SDDMM_OPERANDS_FP16}});
   if (const char* e = getenv("SDDMM_B200_TILE_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 4) out->tileStages = (u32)v; }
 }
@@ -1674,7 +2036,7 @@ void plan_resolve(const bsmr_layout* L, u32 K, u32 numBatch, const sddmm_plan* i
   sddmm_plan p;
   if (in) p = *in; else plan_default(&p);
   if (p.plan > SDDMM_PLAN_TILE || p.dense > SDDMM_DENSE_TMA || p.residual > SDDMM_RESIDUAL_STREAM ||
-      p.tile > SDDMM_TILE_TMA_CLUSTER || (p.tileStages && (p.tileStages < 2 || p.tileStages > 4)) ||
+      p.tile > SDDMM_TILE_TMA_PAIR || (p.tileStages && (p.tileStages < 2 || p.tileStages > 4)) ||
       p.operands > SDDMM_OPERANDS_FP16)
     fail(SDDMM_E_ARG, "sddmm_plan holds an unknown selector");
   const bsmr_layout_info& I = L->info;
@@ -1696,11 +2058,12 @@ void plan_resolve(const bsmr_layout* L, u32 K, u32 numBatch, const sddmm_plan* i
     // pre-pass costs more than it saves); TMA_CLUSTER: 2x2 clusters with multicast (opt-in: measured slower)
     if (p.operands == SDDMM_OPERANDS_FP16) {
       if (p.tile == SDDMM_TILE_REG || p.tile == SDDMM_TILE_TMA_CLUSTER)
-        fail(SDDMM_E_UNSUPPORTED, "SDDMM_OPERANDS_FP16 is implemented by the TMA tile kernel only (tile = SDDMM_TILE_TMA)");
-      p.tile = SDDMM_TILE_TMA;
+        fail(SDDMM_E_UNSUPPORTED, "SDDMM_OPERANDS_FP16 is implemented by the TMA tile kernels only (tile = SDDMM_TILE_TMA / _TMA_PAIR)");
+      if (p.tile == SDDMM_TILE_AUTO) p.tile = pair_default() ? SDDMM_TILE_TMA_PAIR : SDDMM_TILE_TMA;
     }
-    if (p.tile == SDDMM_TILE_AUTO) p.tile = K >= 128 ? SDDMM_TILE_TMA : SDDMM_TILE_REG;
-    if (p.tile == SDDMM_TILE_TMA_CLUSTER && !L->tl->numQuads) p.tile = SDDMM_TILE_TMA;
+    if (p.tile == SDDMM_TILE_AUTO) p.tile = K >= 128 ? (pair_default() ? SDDMM_TILE_TMA_PAIR : SDDMM_TILE_TMA) : SDDMM_TILE_REG;
+    if ((p.tile == SDDMM_TILE_TMA_CLUSTER || p.tile == SDDMM_TILE_TMA_PAIR) && !L->tl->numQuads) p.tile = SDDMM_TILE_TMA;
+    if (p.tile == SDDMM_TILE_TMA_PAIR) p.tileStages = kTpStages;  // fixed ring depth
     if (!p.tileStages) p.tileStages = 2;
     p.dense = SDDMM_DENSE_AUTO;
     p.residual = SDDMM_RESIDUAL_AUTO;
@@ -1741,8 +2104,11 @@ void plan_prepare(const bsmr_layout* L, u32 K, u32 numBatch, const sddmm_plan& p
     return;
   }
   if (p.dense == SDDMM_DENSE_TMA) ensure_dense_tma(L, K, numBatch, s);
-  if (p.residual == SDDMM_RESIDUAL_SUPERPANEL)
-    ensure_superpanels(L, superpanel_G(K, p.operands == SDDMM_OPERANDS_FP16), hub_budget(L, K), s);
+  if (p.residual == SDDMM_RESIDUAL_SUPERPANEL) {
+    const bool halfA = p.operands == SDDMM_OPERANDS_FP16, halfB = halfA && sp_half_b(K);
+    ensure_superpanels(L, superpanel_G(K, halfA), hub_budget(L, K, halfB), s);
+    if (halfB) ensure_half_b(L, K, numBatch);
+  }
   if (p.residual == SDDMM_RESIDUAL_STREAM) ensure_stream(L, s);
 }
 
@@ -1808,7 +2174,47 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
           arr(BSMR_REORDERED_ROWS), I.numRows, reinterpret_cast<float4*>(t->rA.get()),
           reinterpret_cast<float4*>(t->rB.get()), bst);
     SB_LAUNCH_CHECK();
-    if (p.tile == SDDMM_TILE_TMA_CLUSTER) {
+    if (p.tile == SDDMM_TILE_TMA_PAIR) {
+      auto kp = half ? k_sddmm_tile_pair<true> : k_sddmm_tile_pair<false>;
+      const size_t psmem = (size_t)kTpStages * kTlStageBytes + kTpStagingBytes + 1024;
+      set_smem(kp, psmem);
+      cudaLaunchConfig_t cfg{};
+      cfg.blockDim = dim3(kTpThreads);
+      cfg.dynamicSmemBytes = psmem;
+      cfg.stream = denseStream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      // persistent: as many CTA pairs as can be resident at once (a static round-robin schedule must not queue pairs)
+      cfg.gridDim = dim3((unsigned)device_sm_count() & ~1u, 1);
+      static std::mutex occMu;
+      static std::map<std::pair<int, bool>, int> occ;  // (device, fp16 form) -> resident CTA pairs: the query costs
+      int maxPairs = 0;                                  // tens of microseconds on the host, a pass about as much
+      {
+        int dev = 0;
+        SB_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(occMu);
+        auto it = occ.find({dev, half});
+        if (it == occ.end()) {
+          SB_CUDA(cudaOccupancyMaxActiveClusters(&maxPairs, kp, &cfg));
+          occ[{dev, half}] = maxPairs;
+        } else {
+          maxPairs = it->second;
+        }
+      }
+      if (maxPairs < 1) fail(SDDMM_E_CUDA, "k_sddmm_tile_pair: no CTA pair fits on this device");
+      u32 perBatch = std::max<u32>(1u, (u32)maxPairs / numBatch);
+      if (const char* e = getenv("SDDMM_B200_PAIR_GRID")) { const int v = atoi(e); if (v >= 1) perBatch = std::min<u32>(perBatch, (u32)v); }
+      cfg.gridDim = dim3(2u * std::min<u32>(L->tl->numQuads, perBatch), numBatch);
+      SB_CUDA(cudaLaunchKernelEx(&cfg, kp, *reinterpret_cast<const CUtensorMap*>(t->mapA),
+                                 *reinterpret_cast<const CUtensorMap*>(t->mapB), K, (u32)L->tl->numQuads,
+                                 (const uint2*)L->tl->quads.get(), (const u32*)L->tl->quadTiles.get(),
+                                 (const uint4*)L->tl->tiles.get(), (const u32*)L->tl->rowMeta.get(),
+                                 (const u32*)L->tl->idx.get(), dP, bst.p));
+      SB_LAUNCH_CHECK();
+    } else if (p.tile == SDDMM_TILE_TMA_CLUSTER) {
       auto kq = p.tileStages == 2 ? k_sddmm_tile_tma4<2> : p.tileStages == 3 ? k_sddmm_tile_tma4<3> : k_sddmm_tile_tma4<4>;
       set_smem(kq, smem);
       cudaLaunchConfig_t cfg{};
@@ -1894,26 +2300,43 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
         SB_LAUNCH_CHECK();
       }
     } else if (p.residual == SDDMM_RESIDUAL_SUPERPANEL) {
-      const bool halfA = p.operands == SDDMM_OPERANDS_FP16;
-      const SuperPanelLayout* sp = ensure_superpanels(L, superpanel_G(K, halfA), hub_budget(L, K), sparseStream);
+      const bool halfA = p.operands == SDDMM_OPERANDS_FP16, halfB = halfA && sp_half_b(K);
+      const SuperPanelLayout* sp =
+          ensure_superpanels(L, superpanel_G(K, halfA), hub_budget(L, K, halfB), sparseStream);
       if (sp->numWork) {
         const size_t smem = (size_t)sp->rows * K * (halfA ? 2 : 4);
+        const float* bSrc = dB;
+        BatchStrides kst = bst;
+        const bsmr_layout::HalfB* hb = nullptr;
+        if (halfB) {  // fp16 copy of B^T, rewritten every pass (B may change between calls)
+          hb = ensure_half_b(L, K, numBatch);
+          workspace_acquire(hb->busy, sparseStream);
+          const size_t work = (size_t)sp->numUsedCols * K4;
+          const dim3 rgrid((unsigned)std::min<size_t>((work + 255) / 256, (size_t)device_sm_count() * 16), numBatch);
+          k_round_rows_half<<<rgrid, 256, 0, sparseStream>>>(
+              sp->usedCols.get(), sp->numUsedCols, K4, reinterpret_cast<const float4*>(dB),
+              reinterpret_cast<uint2*>(hb->rB.get()), numBatch > 1 ? (size_t)I.N * K4 : 0, (size_t)I.N * K4);
+          SB_LAUNCH_CHECK();
+          bSrc = hb->rB.get();
+          if (numBatch > 1) kst.b = (size_t)I.N * K / 2;  // batch stride of the copy, in floats
+        }
         auto launch = [&](auto kern, int threads) {
           set_smem(kern, smem);
           kern<<<dim3(sp->numWork, numBatch), threads, smem, sparseStream>>>(
-              I.M, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(dB), arr(BSMR_REORDERED_ROWS),
+              I.M, reinterpret_cast<const float4*>(dA), reinterpret_cast<const float4*>(bSrc), arr(BSMR_REORDERED_ROWS),
               I.numRows, sp->rows, sp->segLen, sp->off.get(), sp->col.get(), sp->row.get(), sp->idx.get(),
-              sp->work.get(), dP, bst, sp->colMask);
+              sp->work.get(), dP, kst, sp->colMask);
         };
         // eviction hints when B (N x K floats) cannot live in the 126 MB L2 next to A and the layout; gather mode
         // (several B^T rows in flight, no column-run reuse) when a run averages fewer than 1.5 entries
-        static const int hintCfg = l2_hint_cfg();
-        static const int gatherCfg = [] { const char* e = getenv("SDDMM_B200_SP_GATHER"); return e ? atoi(e) : -1; }();
+        const int hintCfg = l2_hint_cfg();
+        const int gatherCfg = [] { const char* e = getenv("SDDMM_B200_SP_GATHER"); return e ? atoi(e) : -1; }();
         const bool hints = hintCfg >= 0 ? hintCfg != 0 : l2_hints_wanted(L, K);
         // measured on R-MAT scale 22: gather mode 2.07 -> 1.17 ms at K=32 and 2.46 -> 2.03 ms at K=64, but 3.58 -> 4.00
         // ms at K=128 and worse above (there one row per 8 lanes already keeps 64 KB per SM in flight and the L2
-        // fabric, ~8.5 TB/s of gathered rows, is the limit), hence K <= 64
-        const bool gather = gatherCfg >= 0 ? gatherCfg != 0 : (K <= 64 && (double)sp->numEntries < 1.5 * (double)sp->numRuns);
+        // fabric, ~8.5 TB/s of gathered rows, is the limit), hence K <= 64.  With fp16 B^T rows a row is half as long
+        // and gather mode wins at every K (K = 64 / 256 / 512: 2.65 -> 1.78, 6.89 -> 5.41, 10.9 -> 10.6 ms)
+        const bool gather = gatherCfg >= 0 ? gatherCfg != 0 : ((halfB || K <= 64u) && (double)sp->numEntries < 1.5 * (double)sp->numRuns);
 #define SB_SP_CASE2(NBv, THRv, Uv, HALFv)                                                         \
   do {                                                                                            \
     if (gather) { if (hints) launch(k_sddmm_residual_sp<NBv, THRv, true, Uv, HALFv>, THRv);       \
@@ -1921,11 +2344,26 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
     else { if (hints) launch(k_sddmm_residual_sp<NBv, THRv, true, 0, HALFv>, THRv);               \
            else launch(k_sddmm_residual_sp<NBv, THRv, false, 0, HALFv>, THRv); }                  \
   } while (0)
+#define SB_SP_CASE3(NBv, THRv, Uv)                                                                         \
+  do {                                                                                                     \
+    if (gather) { if (hints) launch(k_sddmm_residual_sp<NBv, THRv, true, Uv, true, true>, THRv);           \
+                  else launch(k_sddmm_residual_sp<NBv, THRv, false, Uv, true, true>, THRv); }              \
+    else { if (hints) launch(k_sddmm_residual_sp<NBv, THRv, true, 0, true, true>, THRv);                   \
+           else launch(k_sddmm_residual_sp<NBv, THRv, false, 0, true, true>, THRv); }                      \
+  } while (0)
 #define SB_SP_CASE(NBv, THRv, Uv)                    \
   do {                                               \
     if (halfA) SB_SP_CASE2(NBv, THRv, Uv, true);     \
     else SB_SP_CASE2(NBv, THRv, Uv, false);          \
   } while (0)
+        if (halfB) {
+          switch (K / 32u) {
+            case 2: SB_SP_CASE3(2, 1024, 4); break;
+            case 4: SB_SP_CASE3(4, 1024, 2); break;
+            case 8: SB_SP_CASE3(8, 512, 2); break;
+            default: SB_SP_CASE3(16, 512, 1); break;
+          }
+        } else
         switch (K / 32u) {
           case 1: SB_SP_CASE(1, 1024, 8); break;
           case 2: SB_SP_CASE(2, 1024, 4); break;
@@ -1935,7 +2373,9 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
         }
 #undef SB_SP_CASE
 #undef SB_SP_CASE2
+#undef SB_SP_CASE3
         SB_LAUNCH_CHECK();
+        if (hb) workspace_release(hb->busy, sparseStream);
       }
     } else {
       const size_t smem = (size_t)16 * K * sizeof(float);

@@ -10,6 +10,7 @@ reference's checkData tolerance (include/checkData.hpp:14-30).  One test id per 
   tile_reg     k_sddmm_tile         128x128 tcgen05 tiles, register-staged
   tile_tma     k_sddmm_tile_tma     128x128 tcgen05 tiles, TMA-fed
   tile_tma4    k_sddmm_tile_tma4    2x2 clusters, multicast TMA
+  tile_pair    k_sddmm_tile_pair    persistent CTA pairs, 256x256 tcgen05.mma.cta_group::2, double-buffered TMEM
   res_sp_fp16 / tile_tma_fp16       the opt-in fp16-operand forms of K7b and K9 (fp32 accumulation, same tolerance)
 and the clustering kernels (k_cluster, k_cluster_batched<1|2|4|8>, lane sweep on/off, signature filter on/off)
 against the permutations of the unmodified reference GPU pipeline (tests/golden/ref_gpu).
@@ -42,6 +43,9 @@ KERNELS = {
     "tile_tma": (0.3, dict(plan="tile", tile="tma"), dict(plan="tile", tile="tma")),
     "tile_tma3": (0.3, dict(plan="tile", tile="tma", tile_stages=3), dict(plan="tile", tile="tma", tile_stages=3)),
     "tile_tma4": (0.3, dict(plan="tile", tile="tma_cluster"), dict(plan="tile", tile="tma_cluster")),
+    "tile_pair": (0.3, dict(plan="tile", tile="tma_pair"), dict(plan="tile", tile="tma_pair")),
+    "tile_pair_fp16": (0.3, dict(plan="tile", tile="tma_pair", operands="fp16"),
+                       dict(plan="tile", tile="tma_pair", operands="fp16")),
 }
 
 
@@ -115,6 +119,34 @@ def test_kernel_parity(kernel, K, nb, mname, torch_mod):
     _run(torch_mod, S, lay, K, nb, plan)
 
 
+@pytest.mark.parametrize("pairs", [1, 3, 7])
+@pytest.mark.parametrize("K", [32, 128, 200])
+@pytest.mark.parametrize("operands_", ["exact", "fp16"])
+def test_tile_pair_persistent_loop(pairs, K, operands_, torch_mod, monkeypatch):
+    """K10 with the grid capped at a few CTA pairs: every pair walks MANY 256x256 quads, so the operand ring wraps,
+    both TMEM accumulators are reused (full / empty phases flip) and quads with missing tiles are crossed."""
+    monkeypatch.setenv("SDDMM_B200_PAIR_GRID", str(pairs))
+    S = MATS["rmat11"]
+    lay = _layout("rmat11", 0.3)
+    assert lay.info.numRows > 256
+    _run(torch_mod, S, lay, K, 2, pkg.make_plan(plan="tile", tile="tma_pair", operands=operands_))
+
+
+@pytest.mark.parametrize("hints", ["0", "1"])
+@pytest.mark.parametrize("gather", ["0", "1"])
+@pytest.mark.parametrize("operands_", ["exact", "fp16"])
+@pytest.mark.parametrize("K", [32, 64, 128, 256, 512])
+def test_superpanel_kernel_modes(K, operands_, gather, hints, torch_mod, monkeypatch):
+    """K7b under every (gather mode, L2 eviction policy with hub / tail column classes) combination, with fp32
+    operands and with the fp16 copies (fp16 A tile; from K = 64 also fp16 B^T rows multiplied by FHFMA)."""
+    monkeypatch.setenv("SDDMM_B200_SP_GATHER", gather)
+    monkeypatch.setenv("SDDMM_B200_L2_HINTS", hints)
+    monkeypatch.setenv("SDDMM_B200_L2_HUB_MB", "1")  # 1 MB of hub rows: rmat11 then has hub AND tail columns
+    S = MATS["rmat11"]
+    lay = _layout("rmat11", 1.1)
+    _run(torch_mod, S, lay, K, 2, pkg.make_plan(plan="bsmr", residual="superpanel", operands=operands_))
+
+
 @pytest.mark.parametrize("K", [36, 100, 520])
 def test_residual_panel_kernel_odd_K(K, torch_mod):
     """K7 is the only residual kernel for K outside {32,...,512}: AUTO must pick it and it must be right."""
@@ -140,7 +172,8 @@ def test_prepare_then_graph_capture(torch_mod):
     torch = torch_mod
     S = MATS["blocks"]
     K = 128
-    for kw in (dict(plan="tile", tile="tma"), dict(plan="bsmr", dense="tma", residual="superpanel")):
+    for kw in (dict(plan="tile", tile="tma"), dict(plan="tile", tile="tma_pair"),
+               dict(plan="bsmr", dense="tma", residual="superpanel")):
         lay = _layout("blocks", 0.3)
         plan = pkg.make_plan(**kw)
         pkg.sddmm_prepare(lay, K, 1, plan)

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--stages", type=int, default=0); ap.add_argument("--tiles", default="auto")
     ap.add_argument("--operands", default="exact")
     ap.add_argument("--host-gen", action="store_true", help="R-MAT from the host generator (tests' matrices)")
+    ap.add_argument("--graph", action="store_true", help="forced plans: time replays of ONE CUDA graph per pass")
     a = ap.parse_args()
     import torch
     pkg = load_package()
@@ -91,10 +92,23 @@ def run_k(a, torch, pkg, gen, S, lay, K, ncl, row_ms, col_ms, rphm_ms):
         for _ in range(3):
             pkg.sddmm_gpu(dA, dB, lay, dP, plan=a.plan_obj)
         torch.cuda.synchronize()
+        step = lambda: pkg.sddmm_gpu(dA, dB, lay, dP, plan=a.plan_obj)  # noqa: E731
+        if a.graph:  # launch-bound regime: host launch cost out of the picture
+            side = torch.cuda.Stream()
+            with torch.cuda.stream(side):
+                step()
+                torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=side):
+                    step()
+            step = gr.replay
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(a.iters):
-            pkg.sddmm_gpu(dA, dB, lay, dP, plan=a.plan_obj)
+            step()
         e1.record()
         torch.cuda.synchronize()
         t = dict(dense_ms=0.0, sparse_ms=0.0, total_ms=e0.elapsed_time(e1) / a.iters)
