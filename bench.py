@@ -353,7 +353,8 @@ def kernel_roofline(ctx, lay, K, kt, rows_touched, cols_touched, M, nnz, workloa
         # tensor-core kernel (128x128 tcgen05 tiles or 16x16 BSMR blocks): useful flops vs the tf32 peak, taken as
         # half of the measured dense bf16 peak (tf32 runs at half the bf16 rate)
         kms = kt["dense_ms"]
-        kname = ("k_round_operands + k_sddmm_tile_tma" if plan_names["plan"] == "tile" and plan_names["tile"] != "reg"
+        kname = ("k_round_operands + k_sddmm_tile_pair (cta_group::2)" if plan_names["plan"] == "tile" and plan_names["tile"] == "tma_pair"
+                 else "k_round_operands + k_sddmm_tile_tma" if plan_names["plan"] == "tile" and plan_names["tile"] != "reg"
                  else "k_sddmm_tile" if plan_names["plan"] == "tile"
                  else "k_round_dense_rows + k_sddmm_dense_tma" if plan_names["dense"] == "tma" else "k_sddmm_dense")
         kname += " (tcgen05 kind::tf32)"
@@ -758,7 +759,7 @@ def run_ours(args, w):
                 also["config5_rmat25_k256"] = dict(error=str(e)[:300])
         if ctx.world == 1:
             fp16_sp = dict(plan="bsmr", residual="superpanel", operands="fp16")
-            fp16_tile = dict(plan="tile", tile="tma", operands="fp16")
+            fp16_tile = dict(plan="tile", operands="fp16")
             for name, K, plan_kw in (("uniform100k", 128, None), ("dlmc4096_s70", 256, None), ("dlmc4096_s70", 64, None),
                                      ("dlmc4096_s90", 256, None), ("dlmc4096_s98", 64, None), ("blockscat16k", 128, None),
                                      # opt-in fp16 operand copies: NOT the default arithmetic, labelled in `dtype`

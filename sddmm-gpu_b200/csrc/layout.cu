@@ -645,9 +645,27 @@ static void build_tiles(bsmr_layout* L, const u32* d_rowOff, const u32* d_colIdx
   L->tl = std::move(tl);
 }
 
+namespace {
+__global__ void __launch_bounds__(128) k_tile_meta_t(const u32* __restrict__ rowMeta, const uint4* __restrict__ tiles,
+                                                     uint2* __restrict__ out) {
+  const u32 t = blockIdx.x, r = threadIdx.x;
+  const u32* m = rowMeta + (size_t)t * 640u + r * 5u;
+  u32 off = m[4] - tiles[t].z;
+#pragma unroll
+  for (u32 cq = 0; cq < 4; ++cq) {
+    out[((size_t)t * 4u + cq) * 128u + r] = make_uint2(m[cq], off);
+    off += __popc(m[cq]);
+  }
+}
+}  // namespace
+
 void build_quads(TileLayout& T) {
   T.numQuads = 0;
   if (!T.numTiles) return;
+  T.rowMetaT.alloc((size_t)T.numTiles * 512u, true);
+  k_tile_meta_t<<<T.numTiles, 128>>>(T.rowMeta.get(), T.tiles.get(), T.rowMetaT.get());
+  SB_LAUNCH_CHECK();
+  SB_CUDA(cudaDeviceSynchronize());
   std::vector<uint4> tiles(T.numTiles);
   SB_CUDA(cudaMemcpy(tiles.data(), T.tiles.get(), (size_t)T.numTiles * sizeof(uint4), cudaMemcpyDeviceToHost));
   // tiles are sorted by (row, col); quads in order of first appearance keyed by (row/2, col/2)

@@ -54,6 +54,10 @@ struct TileLayout {
   u32 numQuads = 0;
   DevBuf<uint2> quads;
   DevBuf<u32> quadTiles;
+  // rowMeta transposed for the CTA-pair kernel, whose epilogue warp (row quarter, 32-column slice cq) wants ONE
+  // coalesced 8-byte load per thread: rowMetaT[(tile * 4 + cq) * 128 + row] = {mask word cq of the row, offset of the
+  // row's first stored entry inside slice cq relative to the tile's first entry}
+  DevBuf<uint2> rowMetaT;
 };
 void build_quads(TileLayout& T);  // from T.tiles (host pass over the tile list)
 }  // namespace sb

@@ -1390,19 +1390,23 @@ k_sddmm_tile_tma4(const __grid_constant__ CUtensorMap mapA64, const __grid_const
 //   columns), the tensor cores of both SMs read both halves, and each CTA's TMEM receives 128 rows x 256 columns.
 //   Per 128x128 output tile a CTA therefore pulls 128 operand rows through the L2 -> SM fabric instead of 256 -- the
 //   limiter of the one-tile-per-CTA form (k_sddmm_tile_tma: 256 KB per tile at K=256).
-//   Roles (320 threads): warp 0 = TMA producer (both CTAs; the loads signal the LEADER's full barrier through the
+//   Roles (576 threads): warp 0 = TMA producer (both CTAs; the loads signal the LEADER's full barrier through the
 //   cta_group::2 form of cp.async.bulk.tensor), warp 1 = MMA issuer (leader only; tcgen05.commit multicasts the
-//   stage-free and accumulator-ready arrivals to both CTAs), warps 2..9 = epilogue (TMEM -> per-row mask compaction
+//   stage-free and accumulator-ready arrivals to both CTAs), warps 2..17 = epilogue (TMEM -> per-row mask compaction
 //   -> shared staging -> coalesced scatter through the tile's CSR-index list, as in the other tile kernels).
 //   Two 256-column accumulators (all 512 TMEM columns): the epilogue of quad i runs under the main loop of quad
 //   i+1, and the operand ring never drains between quads.  Every wait is bounded (a protocol error traps).
 //   Same operands as K9: TF32-rounded (or fp16) row-gathered copies, 128-row SWIZZLE_128B boxes.
 // =============================================================================================
-constexpr int kTpThreads = 320;
+constexpr int kTpThreads = 576;           // producer warp + MMA warp + 16 epilogue warps
+constexpr u32 kTpEpiThreads = 512;
 constexpr u32 kTpStages = 4;
 constexpr u32 kTpStagingBytes = 128u * 128u * 4u;  // one 128x128 tile's stored entries at most
-constexpr u32 kTpPrefetch = 20;  // CSR indices per epilogue thread and tile requested ahead (covers 5120 entries)
-constexpr bool kPairDefault = false;  // AUTO's choice between K9 and K10 (set from measurements)
+constexpr u32 kTpPrefetch = 12;  // CSR indices per epilogue thread and tile requested ahead (covers 6144 entries)
+// AUTO's choice between K9 and K10 for K >= 128, from measurements (4096^2 masks, one CUDA graph per pass incl. the
+// rounding pre-pass, K=256, K9 / K10): 70 % sparse 35.1 / 30.7 us, 90 % 33.0 / 29.0, 50 % 40.7 / 40.5; fp16 operands
+// 27.0 / 24.9 us.  K = 64: 22.5 / 22.7 us (and 23.9 for the register-staged K8, which stays the choice below 128).
+constexpr bool kPairDefault = true;
 
 __device__ __forceinline__ u32 mapa_u32(u32 smemAddr, u32 rank) {
   u32 r;
@@ -1423,12 +1427,27 @@ __device__ __forceinline__ void umma_commit_pair(u64* bar) {  // arrives on `bar
       : "memory");
 }
 
+// Remote arrive without a release fence: what it orders here are TMEM reads, already fenced by tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync (a .release.cluster arrive costs a MEMBAR.ALL.GPU behind the scattered P stores).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(u64* bar, u32 rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(rank)
+      : "memory");
+}
+// debug timeline of the pair kernel (SDDMM_B200_PAIR_DEBUG=1): clock64 stamps of CTA 0 / 1, 8 quads x 8 events
+__device__ unsigned long long g_tpDbg[2][8][8];
+#define SB_TP_STAMP(t, ev)                                                                    \
+  do {                                                                                        \
+    if (dbg && blockIdx.x < 2 && blockIdx.y == 0 && (t) < 8u) g_tpDbg[blockIdx.x][(t)][(ev)] = clock64(); \
+  } while (0)
+
 template <bool kHalf>
 static __global__ void __launch_bounds__(kTpThreads, 1)
 k_sddmm_tile_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, u32 K,
                   u32 numQuads, const uint2* __restrict__ quads, const u32* __restrict__ quadTiles,
-                  const uint4* __restrict__ tiles, const u32* __restrict__ rowMeta, const u32* __restrict__ entIdx,
-                  float* __restrict__ P, size_t pStride) {
+                  const uint4* __restrict__ tiles, const uint2* __restrict__ rowMetaT, const u32* __restrict__ entIdx,
+                  float* __restrict__ P, size_t pStride, u32 dbg) {
   extern __shared__ __align__(1024) unsigned char smemRaw[];
   P += pStride * blockIdx.y;
   unsigned char* stages = smemRaw + ((1024u - (smem_u32(smemRaw) & 1023u)) & 1023u);
@@ -1452,7 +1471,7 @@ k_sddmm_tile_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
     for (u32 b = 0; b < 2; ++b) {
       mbar_init(&accFull[b], 1);    // the MMA commit of a quad's last chunk, multicast
-      mbar_init(&accEmpty[b], 16);  // 8 epilogue warps of each CTA (used on the leader only)
+      mbar_init(&accEmpty[b], 32);  // 16 epilogue warps of each CTA (used on the leader only)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1474,7 +1493,7 @@ k_sddmm_tile_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       for (u32 kc = 0; kc < numChunks; ++kc, ++g) {
         const u32 s = g % kTpStages;
         if (lane == 0) {
-          if (g >= kTpStages) mbar_wait_cluster_bounded(&emptyBar[s], ((g / kTpStages) - 1) & 1u);
+          if (g >= kTpStages) mbar_wait_bounded(&emptyBar[s], ((g / kTpStages) - 1) & 1u);
           if (rank == 0)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&fullBar[s])),
                          "r"(2u * kTlStageBytes)
@@ -1483,6 +1502,7 @@ k_sddmm_tile_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           const u32 dst = smem_u32(stages + s * kTlStageBytes);
           tma_load_3d_pair(dst, &mapA, bar, kc * kChunkElems, rowA, blockIdx.y);
           tma_load_3d_pair(dst + 128u * 128u, &mapB, bar, kc * kChunkElems, rowB, blockIdx.y);
+          if (kc + 1 == numChunks) SB_TP_STAMP(g / numChunks, 0);  // producer: all boxes of the quad requested
         }
         __syncwarp();
       }
@@ -1493,12 +1513,13 @@ k_sddmm_tile_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       u32 g = 0, t = 0;
       for (u32 q = pairId; q < numQuads; q += numPairs, ++t) {
         const u32 buf = t & 1u;
-        if (lane == 0 && t >= 2u) mbar_wait_cluster_bounded(&accEmpty[buf], ((t >> 1) - 1u) & 1u);
+        if (lane == 0 && t >= 2u) mbar_wait_bounded(&accEmpty[buf], ((t >> 1) - 1u) & 1u);
+        if (lane == 0) SB_TP_STAMP(t, 1);  // MMA: accumulator half free
         __syncwarp();
         for (u32 kc = 0; kc < numChunks; ++kc, ++g) {
           const u32 s = g % kTpStages;
           if (lane == 0) {
-            mbar_wait_cluster_bounded(&fullBar[s], (g / kTpStages) & 1u);
+            mbar_wait_bounded(&fullBar[s], (g / kTpStages) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const u32 base = smem_u32(stages + s * kTlStageBytes);
             const u64 dA = umma_desc_sw128(base);
@@ -1520,103 +1541,134 @@ k_sddmm_tile_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                     : "memory");
             }
             umma_commit_pair(&emptyBar[s]);
-            if (kc + 1 == numChunks) umma_commit_pair(&accFull[buf]);
+            if (kc + 1 == numChunks) {
+              umma_commit_pair(&accFull[buf]);
+              SB_TP_STAMP(t, 2);  // MMA: last chunk issued
+            }
           }
           __syncwarp();
         }
       }
     }
   } else {
-    // ---- epilogue (both CTAs, 8 warps): this CTA's 128 rows x 256 columns = the quad's tiles (rank, 0), (rank, 1).
-    // Only 8 warps per SM run it, so nothing hides a global-load round trip inside the loop: the row masks and the
-    // first kTpPrefetch CSR indices per thread of BOTH tiles are requested before the accumulator is waited for.
-    const u32 et = tid - 64u, q4 = warp & 3u, half = (warp - 2u) >> 2;  // TMEM lane quarter = warp id mod 4
+    // ---- epilogue (both CTAs, 16 warps): this CTA's 128 rows x 256 columns = the quad's tiles (rank, 0), (rank, 1).
+    // Warp (q4, cq) owns TMEM lanes 32*q4.. (rows; a warp may only touch the lane quarter of its id mod 4) and the
+    // 32-column slice cq of each tile.  Nothing hides a global-load round trip inside this loop (the other 16 warps
+    // of the SM are all here), so everything is requested a full step ahead: the next quad's tile headers at the
+    // top of a quad, and a tile's row masks and CSR indices as soon as the previous tile's registers are free.
+    const u32 et = tid - 64u, q4 = warp & 3u, cq = (warp - 2u) >> 2;
     const u32 r = q4 * 32u + lane;
+    u32 cIdx[2] = {kNull, kNull}, cBeg[2] = {0u, 0u}, cCnt[2] = {0u, 0u}, pf[2][kTpPrefetch];
+    uint2 mk[2];  // {mask word of my 32-column slice, offset of my first entry in the tile's staging order}
+    auto load_hdr = [&](u32 q, u32 (&ti)[2], u32 (&beg)[2], u32 (&cnt)[2]) {
+#pragma unroll
+      for (u32 sub = 0; sub < 2; ++sub) {
+        ti[sub] = q < numQuads ? __ldg(quadTiles + q * 4u + rank * 2u + sub) : kNull;
+        beg[sub] = cnt[sub] = 0u;
+        if (ti[sub] != kNull) {
+          const uint4 tile = __ldg(tiles + ti[sub]);
+          beg[sub] = tile.z;
+          cnt[sub] = tile.w;
+        }
+      }
+    };
+    auto request = [&](u32 sub) {  // row masks + offset of my row, my first kTpPrefetch CSR indices
+      if (cIdx[sub] != kNull) {
+        mk[sub] = __ldg(rowMetaT + ((size_t)cIdx[sub] * 4u + cq) * 128u + r);
+#pragma unroll
+        for (u32 j = 0; j < kTpPrefetch; ++j) {
+          const u32 e = et + j * kTpEpiThreads;
+          pf[sub][j] = e < cCnt[sub] ? __ldg(entIdx + cBeg[sub] + e) : 0u;
+        }
+      }
+    };
+    load_hdr(pairId, cIdx, cBeg, cCnt);
+    request(0);
+    request(1);
     u32 t = 0;
     for (u32 q = pairId; q < numQuads; q += numPairs, ++t) {
       const u32 buf = t & 1u;
-      u32 tIdx[2], tBeg[2] = {0u, 0u}, tCnt[2] = {0u, 0u}, mk[2][5], pf[2][kTpPrefetch];
-#pragma unroll
-      for (u32 sub = 0; sub < 2; ++sub) {
-        tIdx[sub] = quadTiles[q * 4u + rank * 2u + sub];
-        if (tIdx[sub] != kNull) {
-          const uint4 tile = tiles[tIdx[sub]];
-          tBeg[sub] = tile.z;
-          tCnt[sub] = tile.w;
-          const u32* meta = rowMeta + (size_t)tIdx[sub] * 640u + r * 5u;
-#pragma unroll
-          for (u32 i = 0; i < 5; ++i) mk[sub][i] = __ldg(meta + i);
-#pragma unroll
-          for (u32 j = 0; j < kTpPrefetch; ++j) {
-            const u32 e = et + j * 256u;
-            pf[sub][j] = e < tCnt[sub] ? __ldg(entIdx + tBeg[sub] + e) : 0u;
-          }
-        }
-      }
-      const u32 arriveAt = tIdx[1] != kNull ? 1u : 0u;  // ONE accEmpty arrive per warp and quad, after its last TMEM read
-      mbar_wait_cluster_bounded(&accFull[buf], (t >> 1) & 1u);
+      u32 nIdx[2], nBeg[2], nCnt[2];
+      load_hdr(q + numPairs, nIdx, nBeg, nCnt);
+      const u32 arriveAt = cIdx[1] != kNull ? 1u : 0u;  // ONE accEmpty arrive per warp and quad, after its last TMEM read
+      if (et == 0) SB_TP_STAMP(t, 3);  // epilogue: waiting for the accumulator
+      mbar_wait_bounded(&accFull[buf], (t >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (et == 0) SB_TP_STAMP(t, 4);  // epilogue: accumulator ready
 #pragma unroll
       for (u32 sub = 0; sub < 2; ++sub) {
-        if (tIdx[sub] != kNull) {
-          u32 off = mk[sub][4] - tBeg[sub];
-          if (half) off += __popc(mk[sub][0]) + __popc(mk[sub][1]);
+        if (cIdx[sub] != kNull) {
+          const u32 off = mk[sub].y, mw = mk[sub].x;
+          u32 acc[32];
+          const u32 taddr = tmem + ((q4 * 32u) << 16) + buf * 256u + sub * 128u + cq * 32u;
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]),
+                "=r"(acc[7]), "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]),
+                "=r"(acc[14]), "=r"(acc[15]), "=r"(acc[16]), "=r"(acc[17]), "=r"(acc[18]), "=r"(acc[19]),
+                "=r"(acc[20]), "=r"(acc[21]), "=r"(acc[22]), "=r"(acc[23]), "=r"(acc[24]), "=r"(acc[25]),
+                "=r"(acc[26]), "=r"(acc[27]), "=r"(acc[28]), "=r"(acc[29]), "=r"(acc[30]), "=r"(acc[31])
+              : "r"(taddr)
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          // two independent offset chains (low / high 16 columns) instead of one of 32
+          u32 offLo = off, offHi = off + __popc(mw & 0xFFFFu);
 #pragma unroll
-          for (u32 qq = 0; qq < 2; ++qq) {
-            const u32 qd = half * 2u + qq;
-            u32 acc[32];
-            const u32 taddr = tmem + ((q4 * 32u) << 16) + buf * 256u + sub * 128u + qd * 32u;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]),
-                  "=r"(acc[7]), "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]),
-                  "=r"(acc[14]), "=r"(acc[15]), "=r"(acc[16]), "=r"(acc[17]), "=r"(acc[18]), "=r"(acc[19]),
-                  "=r"(acc[20]), "=r"(acc[21]), "=r"(acc[22]), "=r"(acc[23]), "=r"(acc[24]), "=r"(acc[25]),
-                  "=r"(acc[26]), "=r"(acc[27]), "=r"(acc[28]), "=r"(acc[29]), "=r"(acc[30]), "=r"(acc[31])
-                : "r"(taddr)
-                : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const u32 mw = qd == 0 ? mk[sub][0] : qd == 1 ? mk[sub][1] : qd == 2 ? mk[sub][2] : mk[sub][3];
-#pragma unroll
-            for (u32 b = 0; b < 32; ++b) {
-              if ((mw >> b) & 1u) {
-                sOut[off] = __uint_as_float(acc[b]);
-                ++off;
-              }
+          for (u32 b = 0; b < 16; ++b) {
+            if ((mw >> b) & 1u) {
+              sOut[offLo] = __uint_as_float(acc[b]);
+              ++offLo;
+            }
+            if ((mw >> (b + 16u)) & 1u) {
+              sOut[offHi] = __uint_as_float(acc[b + 16u]);
+              ++offHi;
             }
           }
         }
         if (sub == arriveAt) {  // the accumulator half is free for the quad after next
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive_remote(&accEmpty[buf], 0u);
+          if (lane == 0) mbar_arrive_cluster_relaxed(&accEmpty[buf], 0u);
         }
-        if (tIdx[sub] != kNull) {
-          asm volatile("bar.sync 1, 256;" ::: "memory");  // the tile's values are staged
-          const u32 cnt = tCnt[sub];
+        if (cIdx[sub] != kNull) {
+          asm volatile("bar.sync 1, 512;" ::: "memory");  // the tile's values are staged
+          if (et == 0) SB_TP_STAMP(t, 5 + sub);  // epilogue: tile `sub` compacted
+          const u32 cnt = cCnt[sub];
+          float v[kTpPrefetch];
 #pragma unroll
           for (u32 j = 0; j < kTpPrefetch; ++j) {
-            const u32 e = et + j * 256u;
-            if (e < cnt) P[pf[sub][j]] = sOut[e];
+            const u32 e = et + j * kTpEpiThreads;
+            v[j] = e < cnt ? sOut[e] : 0.f;
           }
-          if (cnt > kTpPrefetch * 256u) {  // denser than the prefetch depth covers: the rest with loads in the loop
-            const u32* __restrict__ idx = entIdx + tBeg[sub];
-            u32 e = et + kTpPrefetch * 256u;
-            for (; e + 768u < cnt; e += 1024u) {
-              const u32 i0 = __ldg(idx + e), i1 = __ldg(idx + e + 256u), i2 = __ldg(idx + e + 512u),
-                        i3 = __ldg(idx + e + 768u);
+#pragma unroll
+          for (u32 j = 0; j < kTpPrefetch; ++j) {
+            const u32 e = et + j * kTpEpiThreads;
+            if (e < cnt) P[pf[sub][j]] = v[j];
+          }
+          if (cnt > kTpPrefetch * kTpEpiThreads) {  // denser than the prefetch depth covers: the rest with loads here
+            const u32* __restrict__ idx = entIdx + cBeg[sub];
+            u32 e = et + kTpPrefetch * kTpEpiThreads;
+            for (; e + 3u * kTpEpiThreads < cnt; e += 4u * kTpEpiThreads) {
+              const u32 i0 = __ldg(idx + e), i1 = __ldg(idx + e + kTpEpiThreads), i2 = __ldg(idx + e + 2u * kTpEpiThreads),
+                        i3 = __ldg(idx + e + 3u * kTpEpiThreads);
               P[i0] = sOut[e];
-              P[i1] = sOut[e + 256u];
-              P[i2] = sOut[e + 512u];
-              P[i3] = sOut[e + 768u];
+              P[i1] = sOut[e + kTpEpiThreads];
+              P[i2] = sOut[e + 2u * kTpEpiThreads];
+              P[i3] = sOut[e + 3u * kTpEpiThreads];
             }
-            for (; e < cnt; e += 256u) P[__ldg(idx + e)] = sOut[e];
+            for (; e < cnt; e += kTpEpiThreads) P[__ldg(idx + e)] = sOut[e];
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");  // staging area free again
+          asm volatile("bar.sync 1, 512;" ::: "memory");  // staging area free again
         }
+        // this tile's registers are free: request the same tile of the NEXT quad
+        cIdx[sub] = nIdx[sub];
+        cBeg[sub] = nBeg[sub];
+        cCnt[sub] = nCnt[sub];
+        request(sub);
       }
+      if (et == 0) SB_TP_STAMP(t, 7);  // epilogue: quad done
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -2208,12 +2260,25 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
       u32 perBatch = std::max<u32>(1u, (u32)maxPairs / numBatch);
       if (const char* e = getenv("SDDMM_B200_PAIR_GRID")) { const int v = atoi(e); if (v >= 1) perBatch = std::min<u32>(perBatch, (u32)v); }
       cfg.gridDim = dim3(2u * std::min<u32>(L->tl->numQuads, perBatch), numBatch);
+      const u32 dbgOn = [] { const char* e = getenv("SDDMM_B200_PAIR_DEBUG"); return e && atoi(e) ? 1u : 0u; }();
       SB_CUDA(cudaLaunchKernelEx(&cfg, kp, *reinterpret_cast<const CUtensorMap*>(t->mapA),
                                  *reinterpret_cast<const CUtensorMap*>(t->mapB), K, (u32)L->tl->numQuads,
                                  (const uint2*)L->tl->quads.get(), (const u32*)L->tl->quadTiles.get(),
-                                 (const uint4*)L->tl->tiles.get(), (const u32*)L->tl->rowMeta.get(),
-                                 (const u32*)L->tl->idx.get(), dP, bst.p));
+                                 (const uint4*)L->tl->tiles.get(), (const uint2*)L->tl->rowMetaT.get(),
+                                 (const u32*)L->tl->idx.get(), dP, bst.p, dbgOn));
       SB_LAUNCH_CHECK();
+      if (dbgOn && !is_capturing(denseStream)) {
+        unsigned long long h[2][8][8];
+        SB_CUDA(cudaStreamSynchronize(denseStream));
+        SB_CUDA(cudaMemcpyFromSymbol(h, g_tpDbg, sizeof h));
+        for (int c = 0; c < 2; ++c)
+          for (int t = 0; t < 8; ++t) {
+            if (!h[c][t][7]) continue;
+            fprintf(stderr, "[pair dbg] cta %d quad %d:", c, t);
+            for (int e = 0; e < 8; ++e) fprintf(stderr, " %lld", (long long)(h[c][t][e] ? h[c][t][e] - h[c][0][3] : 0));
+            fprintf(stderr, "\n");
+          }
+      }
     } else if (p.tile == SDDMM_TILE_TMA_CLUSTER) {
       auto kq = p.tileStages == 2 ? k_sddmm_tile_tma4<2> : p.tileStages == 3 ? k_sddmm_tile_tma4<3> : k_sddmm_tile_tma4<4>;
       set_smem(kq, smem);
@@ -2335,8 +2400,13 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
         // measured on R-MAT scale 22: gather mode 2.07 -> 1.17 ms at K=32 and 2.46 -> 2.03 ms at K=64, but 3.58 -> 4.00
         // ms at K=128 and worse above (there one row per 8 lanes already keeps 64 KB per SM in flight and the L2
         // fabric, ~8.5 TB/s of gathered rows, is the limit), hence K <= 64.  With fp16 B^T rows a row is half as long
-        // and gather mode wins at every K (K = 64 / 256 / 512: 2.65 -> 1.78, 6.89 -> 5.41, 10.9 -> 10.6 ms)
-        const bool gather = gatherCfg >= 0 ? gatherCfg != 0 : ((halfB || K <= 64u) && (double)sp->numEntries < 1.5 * (double)sp->numRuns);
+        // and gather mode wins at every K (K = 64 / 256 / 512: 2.65 -> 1.78, 6.89 -> 5.41, 10.9 -> 10.6 ms).
+        // Threshold: 2.5 entries per run -- the REORDERED graph averages a little over 1.5 (its hub runs are long, most
+        // runs are still singletons) and gathers faster too (K=32: 2.01 -> 1.38 ms, K=64: 2.43 -> 2.13 ms, fp16 K=256:
+        // 6.33 -> 4.94 ms); the uniform 1 % matrix (3.8 entries per run, 7.7 with the fp16 tile) keeps reuse mode.
+        // A third form, two independent streams per group with a B^T register set each (two rows in flight AND run
+        // reuse), measured 7.44 vs 7.27 ms at K=256: at that row length bandwidth, not the round trip, is the limit.
+        const bool gather = gatherCfg >= 0 ? gatherCfg != 0 : ((halfB || K <= 64u) && (double)sp->numEntries < 2.5 * (double)sp->numRuns);
 #define SB_SP_CASE2(NBv, THRv, Uv, HALFv)                                                         \
   do {                                                                                            \
     if (gather) { if (hints) launch(k_sddmm_residual_sp<NBv, THRv, true, Uv, HALFv>, THRv);       \

@@ -193,13 +193,14 @@ def test_prepare_then_graph_capture(torch_mod):
         assert O.check_data(O.sddmm_cpu(S, A, B), P.cpu().numpy()) == 0
 
 
-def test_two_streams_share_one_layout(torch_mod):
-    """tile-TMA plan, one layout, two streams: the shared rounded workspace is serialised by the layout's event."""
+@pytest.mark.parametrize("tile", ["tma", "tma_pair"])
+def test_two_streams_share_one_layout(tile, torch_mod):
+    """tile-TMA plans, one layout, two streams: the shared rounded workspace is serialised by the layout's event."""
     torch = torch_mod
     S = MATS["blocks"]
     K = 128
     lay = _layout("blocks", 0.3)
-    plan = pkg.make_plan(plan="tile", tile="tma")
+    plan = pkg.make_plan(plan="tile", tile=tile)
     pkg.sddmm_prepare(lay, K, 1, plan)
     ops = [gen.dense_operands(S.M, S.N, K, seed_a=50 + i, seed_b=60 + i) for i in range(4)]
     dev = [(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()) for a, b in ops]

@@ -34,10 +34,18 @@ def main():
     ap.add_argument("--operands", default="exact")
     ap.add_argument("--host-gen", action="store_true", help="R-MAT from the host generator (tests' matrices)")
     ap.add_argument("--graph", action="store_true", help="forced plans: time replays of ONE CUDA graph per pass")
+    ap.add_argument("--persist-mb", type=int, default=-1, help="experiment: cudaLimitPersistingL2CacheSize in MB")
     a = ap.parse_args()
     import torch
     pkg = load_package()
     gen = pkg.generators
+    if a.persist_mb >= 0:
+        import ctypes
+        torch.cuda.init(); torch.zeros(1, device="cuda")
+        rt = ctypes.CDLL("libcudart.so")
+        rc = rt.cudaDeviceSetLimit(6, ctypes.c_size_t(a.persist_mb << 20))  # cudaLimitPersistingL2CacheSize
+        v = ctypes.c_size_t(0); rt.cudaDeviceGetLimit(ctypes.byref(v), 6)
+        print(f"persisting L2 limit: rc={rc} now {v.value >> 20} MB", flush=True)
     if a.workload == "uniform100k":
         S = gen.uniform_random(100_000, 100_000, 0.01, 2)
     elif a.workload == "uniform20k":
