@@ -515,6 +515,10 @@ def record_rmat(ctx, w, headline=True, scale=None, K=None, reorder=True, steps=N
             e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
             assert np.array_equal(nPs[0], nPs[1]), "pipelined slots disagree"
             api = "sddmm_run_host_async, 2 slots (H2D / kernels / D2H of consecutive steps overlap)"
+            moved = pkg.host_traffic(lay)  # what the entry point really moved (referenced rows only when it can)
+            hPt = torch.from_numpy(nPs[(e2e_steps - 1) & 1]).cuda()
+            fp64_row_check(torch, ro_host, ci, dA, dB, hPt, pick)
+            del hPt
         else:
             # N GPUs: sddmm_mgpu_run_host -- every rank copies 1/N of A and of B over its own PCIe link, the slices are
             # all-gathered over NVLink, P is summed onto rank 0, which copies it to the host: the job reads the host
@@ -556,14 +560,20 @@ def record_rmat(ctx, w, headline=True, scale=None, K=None, reorder=True, steps=N
         ceil_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
         ctx.barrier()
         e2e_ms_max, ceil_ms_max = ctx.max_over_ranks([e2e_ms, ceil_ms])
+        full_in = int(4 * K * (M + N))
+        h2d_b, d2h_b = (moved if W == 1 else (full_in, int(4 * nnz)))
         e2e_rec = dict(value=2.0 * nnz * K / (e2e_ms_max * 1e-3) / 1e9, unit=UNIT, ms_per_step=e2e_ms_max,
-                       steps=e2e_steps, h2d_bytes_per_step=int(4 * K * (M + N)), d2h_bytes_per_step=int(4 * nnz),
+                       steps=e2e_steps, h2d_bytes_per_step=int(h2d_b), d2h_bytes_per_step=int(d2h_b),
                        bytes_note=("whole job: A and B enter once per step (1/N per rank), P leaves once (rank 0)"
-                                   if W > 1 else "all of A and B in, all of P out, every step"),
+                                   if W > 1 else
+                                   ("the A rows and B^T rows the pass reads (non-empty rows / referenced columns of S: "
+                                    f"{h2d_b / full_in:.0%} of the arrays) gathered from the pinned host buffers, all of "
+                                    "P out, every step" if h2d_b < full_in else
+                                    "all of A and B in, all of P out, every step")),
                        api=api,
                        host_copy_ceiling=dict(ms_per_step=ceil_ms_max, value=2.0 * nnz * K / (ceil_ms_max * 1e-3) / 1e9,
-                                              note="same host bytes per step by bare pinned cudaMemcpyAsync on two "
-                                                   "streams, all ranks concurrently, no kernels, no NVLink"))
+                                              note="ALL of A and B in and P out per step by bare pinned cudaMemcpyAsync "
+                                                   "on two streams, all ranks concurrently, no kernels, no NVLink"))
         del hA, hB, hP, ha, hb
 
     cpu_rec = None
@@ -687,8 +697,9 @@ def record_single(ctx, name, w, K=None, steps=None, warmup=None, e2e=True, cpu=T
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
         assert np.array_equal(nPs[0], nPs[1]), "pipelined slots disagree"
+        h2d_b, d2h_b = pkg.host_traffic(lay)
         e2e_rec = dict(value=2.0 * S.nnz * K / (e2e_ms * 1e-3) / 1e9, unit=UNIT, ms_per_step=e2e_ms,
-                       h2d_bytes_per_step=int(4 * K * (S.M + S.N)), d2h_bytes_per_step=int(4 * S.nnz),
+                       h2d_bytes_per_step=int(h2d_b), d2h_bytes_per_step=int(d2h_b),
                        api="sddmm_run_host_async, 2 slots (H2D / kernels / D2H of consecutive steps overlap)",
                        sync_api_ms_per_step=sync_ms, sync_api_value=2.0 * S.nnz * K / (sync_ms * 1e-3) / 1e9)
     cpu_rec = None

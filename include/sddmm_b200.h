@@ -286,6 +286,12 @@ int sddmm_run_host(const bsmr_layout*, uint32_t K, const float* h_A, const float
  * (The reference's host overload, src/sddmmKernel.cu:2518-2537, is synchronous; this is its streaming twin.) */
 int sddmm_run_host_async(const bsmr_layout*, uint32_t K, const float* h_A, const float* h_B, float* h_P, int slot);
 int sddmm_host_sync(const bsmr_layout*);
+/* Host <-> device bytes of the most recent sddmm_run_host / _async call on this layout.  Both host entry points move
+ * only what the pass reads when they can: if h_A and h_B are page-locked and the layout references at most 85 % of
+ * the rows of A plus the columns of S (graphs leave many empty), a gather kernel reads just the referenced A rows
+ * (reorderedRows) and B^T rows through the mapped host pointers instead of copying the whole arrays
+ * (SDDMM_B200_H2D = auto | full | gather).  (The reference copies whole arrays, src/sddmmKernel.cu:2518-2537.) */
+int sddmm_host_traffic(const bsmr_layout*, uint64_t* h2dBytes, uint64_t* d2hBytes);
 
 /* ---- whole path on host buffers ----------------------------------------------------------------
  * replaces sddmm(options, A, B, P, logger)                src/sddmm.cu:10-39

@@ -9,9 +9,9 @@ from ._lib import SddmmError, declared_symbols, lib  # noqa: F401
 from .host import (BSMR, RPHM, Layout, calculateBlockSize, dispersion_dev, launch_count,  # noqa: F401
                    layout_build_dev, row_reorder_dev, sddmm, sddmm_gpu, sddmm_gpu_async, sddmm_gpu_batch, sddmm_gpu_sync,
                    sddmm_gpu_timed, shard_plan, evaluationReordering, make_plan, make_reorder_opts, plan_resolve,
-                   sddmm_prepare)
+                   sddmm_prepare, host_traffic)
 
 __all__ = ["generators", "lib", "declared_symbols", "SddmmError", "BSMR", "RPHM", "Layout", "calculateBlockSize",
            "sddmm", "sddmm_gpu", "sddmm_gpu_async", "sddmm_gpu_batch", "sddmm_gpu_sync", "sddmm_gpu_timed", "row_reorder_dev", "layout_build_dev", "dispersion_dev",
            "shard_plan", "launch_count", "evaluationReordering", "make_plan", "make_reorder_opts", "plan_resolve",
-           "sddmm_prepare"]
+           "sddmm_prepare", "host_traffic"]

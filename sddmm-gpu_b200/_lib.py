@@ -122,6 +122,7 @@ def lib():
     L.sddmm_run_host.argtypes = [vp, u32, vp, vp, vp, pf32]
     L.sddmm_run_host_async.argtypes = [vp, u32, vp, vp, vp, C.c_int]
     L.sddmm_host_sync.argtypes = [vp]
+    L.sddmm_host_traffic.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.sddmm_host.argtypes = [vp, vp, u32, u32, u32, u32, vp, vp, f32, f32, u32, vp, C.POINTER(Stats), C.POINTER(vp)]
     L.bsmr_shard_plan.argtypes = [vp, vp, u32, u32, vp]
     L.sddmm_coo_to_csr.argtypes = [vp, vp, vp, u32, u32, u32, vp, vp, vp, C.POINTER(C.c_int)]

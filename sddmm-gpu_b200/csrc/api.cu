@@ -2,6 +2,7 @@
 // forms, exception -> error code translation.  No CPU compute path exists behind any entry point.
 #include <algorithm>
 #include <chrono>
+#include <cstring>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -487,6 +488,90 @@ int sddmm_run_timed_dev(const bsmr_layout* L, uint32_t K, const float* d_A, cons
   API_END
 }
 
+}  // extern "C"
+
+namespace sb_hostcopy {
+using namespace sb;
+// Host -> device copy of the operands of one pass.  Whole arrays by cudaMemcpyAsync, or -- when both host buffers are
+// page-locked (device-accessible through UVA) and the layout references clearly fewer rows than the arrays hold (an
+// R-MAT graph leaves half of its rows and columns empty) -- a gather kernel that reads ONLY the referenced A rows
+// (reorderedRows) and B^T rows (ensure_host_refs) through the mapped pointers: PCIe carries what the pass reads.
+// Unreferenced rows of the staging buffers keep their (zeroed) contents; no kernel result depends on them.
+static __global__ void __launch_bounds__(256) k_gather_rows_h2d(const u32* __restrict__ listA, u32 nA, const u32* __restrict__ listB,
+                                                         u32 nB, u32 limA, u32 limB, u32 K4, const float4* hA,
+                                                         const float4* hB, float4* __restrict__ dA,
+                                                         float4* __restrict__ dB) {
+  const u32 lane = threadIdx.x & 31u;
+  const u32 warps = (gridDim.x * blockDim.x) >> 5, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  for (u32 i = gw; i < nA + nB; i += warps) {
+    const bool isA = i < nA;
+    const u32 row = isA ? listA[i] : listB[i - nA];
+    if (row >= (isA ? limA : limB)) continue;
+    const float4* src = (isA ? hA : hB) + (size_t)row * K4;
+    float4* dst = (isA ? dA : dB) + (size_t)row * K4;
+    for (u32 c0 = 0; c0 < K4; c0 += 128u) {  // up to 4 x 16 bytes in flight per lane
+      float4 v[4];
+#pragma unroll
+      for (u32 u = 0; u < 4; ++u) {
+        const u32 c = c0 + u * 32u + lane;
+        if (c < K4) v[u] = src[c];
+      }
+#pragma unroll
+      for (u32 u = 0; u < 4; ++u) {
+        const u32 c = c0 + u * 32u + lane;
+        if (c < K4) dst[c] = v[u];
+      }
+    }
+  }
+}
+
+static int h2d_mode() {  // SDDMM_B200_H2D = auto | full | gather
+  const char* e = getenv("SDDMM_B200_H2D");
+  if (!e) return 0;
+  return !strcmp(e, "full") ? 1 : !strcmp(e, "gather") ? 2 : 0;
+}
+static bool pinned_host(const void* p, const void** dev) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+  *dev = at.devicePointer;
+  return true;
+}
+static size_t h2d_operands(const bsmr_layout* L, u32 K, const float* hA, const float* hB, float* dA, float* dB, cudaStream_t s) {
+  const bsmr_layout_info& I = L->info;
+  const size_t nA = (size_t)I.M * K, nB = (size_t)I.N * K;
+  const int mode = h2d_mode();
+  const void *mA = nullptr, *mB = nullptr;
+  if (mode != 1 && !(K & 3u) && pinned_host(hA, &mA) && pinned_host(hB, &mB)) {
+    const bsmr_layout::HostRefs* hr = ensure_host_refs(L, s);
+    const size_t refRows = (size_t)I.numRows + hr->numCols;
+    if (mode == 2 || refRows * 100 <= ((size_t)I.M + I.N) * 85) {
+      // few CTAs: the kernel waits on PCIe, it must not crowd the SDDMM pass of the other slot off the SMs
+      k_gather_rows_h2d<<<128, 256, 0, s>>>(L->arr[BSMR_REORDERED_ROWS].get(), I.numRows, hr->cols.get(), hr->numCols,
+                                            I.M, I.N, K / 4, static_cast<const float4*>(mA),
+                                            static_cast<const float4*>(mB), reinterpret_cast<float4*>(dA),
+                                            reinterpret_cast<float4*>(dB));
+      SB_LAUNCH_CHECK();
+      return refRows * K * 4;
+    }
+  }
+  SB_CUDA(cudaMemcpyAsync(dA, hA, nA * 4, cudaMemcpyHostToDevice, s));
+  SB_CUDA(cudaMemcpyAsync(dB, hB, nB * 4, cudaMemcpyHostToDevice, s));
+  return (nA + nB) * 4;
+}
+}  // namespace sb_hostcopy
+using sb_hostcopy::h2d_operands;
+
+extern "C" {
+
+int sddmm_host_traffic(const bsmr_layout* L, uint64_t* h2dBytes, uint64_t* d2hBytes) {
+  API_BEGIN
+  require(L, "null layout");
+  if (h2dBytes) *h2dBytes = L->lastH2DBytes;
+  if (d2hBytes) *d2hBytes = L->lastD2HBytes;
+  API_END
+}
+
 int sddmm_run_host(const bsmr_layout* L, uint32_t K, const float* h_A, const float* h_B, float* h_P, float* msTotal) {
   API_BEGIN
   require_device();
@@ -497,15 +582,15 @@ int sddmm_run_host(const bsmr_layout* L, uint32_t K, const float* h_A, const flo
   Timer t(s);
   t.start();
   const size_t nA = (size_t)I.M * K, nB = (size_t)I.N * K, nP = I.nnz ? I.nnz : 1;
-  if (L->wsA.size() < nA) L->wsA.alloc(nA, true);
-  if (L->wsB.size() < nB) L->wsB.alloc(nB, true);
+  if (L->wsA.size() < nA) { L->wsA.alloc(nA, true); SB_CUDA(cudaMemsetAsync(L->wsA.get(), 0, nA * 4, s)); }
+  if (L->wsB.size() < nB) { L->wsB.alloc(nB, true); SB_CUDA(cudaMemsetAsync(L->wsB.get(), 0, nB * 4, s)); }
   if (L->wsP.size() < nP) {
     L->wsP.alloc(nP, true);
     SB_CUDA(cudaMemsetAsync(L->wsP.get(), 0, nP * 4, s));
   }
   float *dA = L->wsA.get(), *dB = L->wsB.get(), *dP = L->wsP.get();
-  SB_CUDA(cudaMemcpyAsync(dA, h_A, nA * 4, cudaMemcpyHostToDevice, s));
-  SB_CUDA(cudaMemcpyAsync(dB, h_B, nB * 4, cudaMemcpyHostToDevice, s));
+  L->lastH2DBytes = h2d_operands(L, K, h_A, h_B, dA, dB, s);
+  L->lastD2HBytes = (unsigned long long)I.nnz * 4;
   // (the reference zero-fills P, sddmmKernel.cu:2525; every entry this layout covers is overwritten by the pass --
   //  the NaN-canary test proves it -- so a full layout needs no memset; a row-panel shard leaves foreign entries
   //  as they were, hence the one-time zeroing when the staging buffer is created)
@@ -538,8 +623,8 @@ int sddmm_run_host_async(const bsmr_layout* L, uint32_t K, const float* h_A, con
   const size_t nA = (size_t)I.M * K, nB = (size_t)I.N * K, nP = I.nnz ? I.nnz : 1;
   if (P.A[slot].size() < nA || P.B[slot].size() < nB || P.P[slot].size() < nP) {
     SB_CUDA(cudaDeviceSynchronize());  // growing a slot: nothing may still be using it
-    if (P.A[slot].size() < nA) P.A[slot].alloc(nA, true);
-    if (P.B[slot].size() < nB) P.B[slot].alloc(nB, true);
+    if (P.A[slot].size() < nA) { P.A[slot].alloc(nA, true); SB_CUDA(cudaMemset(P.A[slot].get(), 0, nA * 4)); }
+    if (P.B[slot].size() < nB) { P.B[slot].alloc(nB, true); SB_CUDA(cudaMemset(P.B[slot].get(), 0, nB * 4)); }
     if (P.P[slot].size() < nP) {
       P.P[slot].alloc(nP, true);
       SB_CUDA(cudaMemset(P.P[slot].get(), 0, nP * 4));  // once; see sddmm_run_host
@@ -547,8 +632,8 @@ int sddmm_run_host_async(const bsmr_layout* L, uint32_t K, const float* h_A, con
   }
   // H2D of this batch may start once the previous pass on this slot has consumed A/B
   SB_CUDA(cudaStreamWaitEvent(P.h2d, P.evComp[slot], 0));
-  SB_CUDA(cudaMemcpyAsync(P.A[slot].get(), h_A, nA * 4, cudaMemcpyHostToDevice, P.h2d));
-  SB_CUDA(cudaMemcpyAsync(P.B[slot].get(), h_B, nB * 4, cudaMemcpyHostToDevice, P.h2d));
+  L->lastH2DBytes = h2d_operands(L, K, h_A, h_B, P.A[slot].get(), P.B[slot].get(), P.h2d);
+  L->lastD2HBytes = (unsigned long long)I.nnz * 4;
   SB_CUDA(cudaEventRecord(P.evH2D[slot], P.h2d));
   // the pass needs the operands and a P buffer whose previous contents have left for the host
   SB_CUDA(cudaStreamWaitEvent(P.comp, P.evH2D[slot], 0));

@@ -831,6 +831,37 @@ const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, u32 hubB
   return (L->sp[key] = std::move(sp)).get();
 }
 
+// ---- columns referenced by the layout (dense-block columns + residual columns), ascending
+namespace {
+__global__ void k_flag_cols(const u32* __restrict__ cols, size_t n, u32 N, u32* __restrict__ flag) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const u32 c = cols[i];
+    if (c < N) flag[c] = 1u;  // denseCols pads with N
+  }
+}
+}  // namespace
+
+const bsmr_layout::HostRefs* ensure_host_refs(const bsmr_layout* L, cudaStream_t s) {
+  if (L->hostRefs) return L->hostRefs.get();
+  TempScope tempScope(s);
+  const bsmr_layout_info& I = L->info;
+  auto h = std::make_unique<bsmr_layout::HostRefs>();
+  const u32 N = I.N ? I.N : 1u;
+  DevBuf<u32> flag(N), ex((size_t)N + 1);
+  SB_CUDA(cudaMemsetAsync(flag.get(), 0, (size_t)N * 4, s));
+  const size_t nd = L->arr[BSMR_DENSE_COLS].size(), ns = I.numSparseValues;
+  if (nd) k_flag_cols<<<grid_for(nd), 256, 0, s>>>(L->arr[BSMR_DENSE_COLS].get(), nd, I.N, flag.get());
+  if (ns) k_flag_cols<<<grid_for(ns), 256, 0, s>>>(L->arr[RPHM_SPARSE_COL_INDICES].get(), ns, I.N, flag.get());
+  SB_LAUNCH_CHECK();
+  scan_counts(flag.get(), ex.get(), N, s);
+  h->numCols = read_u32(ex.get() + N, s);
+  h->cols.alloc(h->numCols ? h->numCols : 1u, true);
+  k_compact_flagged<<<grid_for(N), 256, 0, s>>>(flag.get(), ex.get(), N, h->cols.get());
+  SB_LAUNCH_CHECK();
+  SB_CUDA(cudaStreamSynchronize(s));
+  return (L->hostRefs = std::move(h)).get();
+}
+
 // ---- row-stream residual layout (K7c): residual entries sorted by (reordered row position, column)
 namespace {
 __global__ void __launch_bounds__(256) k_st_keys(const u32* __restrict__ vOff, const u32* __restrict__ sCols,

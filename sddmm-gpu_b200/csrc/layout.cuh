@@ -135,6 +135,14 @@ struct bsmr_layout {
     }
   };
   mutable std::unique_ptr<HostPipe> pipe;
+  // host-buffer entry points: the distinct columns this layout references (dense blocks + residual), ascending, so
+  // that a pass moves only the B^T rows it reads over PCIe (the A rows it reads are `reorderedRows`); built on first use
+  struct HostRefs {
+    sb::u32 numCols = 0;
+    sb::DevBuf<sb::u32> cols;
+  };
+  mutable std::unique_ptr<HostRefs> hostRefs;
+  mutable unsigned long long lastH2DBytes = 0, lastD2HBytes = 0;  // of the most recent host-buffer pass
 };
 
 namespace sb {
@@ -152,6 +160,8 @@ bsmr_layout* layout_load(const char* path);
 // builds (once, then cached) the super-panel layout for G panels per super-panel; returns it
 // hubBudget: number of B^T rows that may be kept L2-resident (0 = no residency classes)
 const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, u32 hubBudget, cudaStream_t s);
+// builds (once) the list of columns the layout references (host-buffer passes copy only those B^T rows)
+const bsmr_layout::HostRefs* ensure_host_refs(const bsmr_layout* L, cudaStream_t s);
 // builds (once) the row-ordered residual layout of the row-stream kernel
 const StreamLayout* ensure_stream(const bsmr_layout* L, cudaStream_t s);
 

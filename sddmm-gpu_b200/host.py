@@ -266,6 +266,13 @@ def sddmm_gpu_async(A, B, layout, P, slot):
     check(_lib.lib().sddmm_run_host_async(lay.handle, A.shape[1], A.ctypes.data, B.ctypes.data, P.ctypes.data, int(slot)))
 
 
+def host_traffic(lay):
+    """(h2d_bytes, d2h_bytes) of the most recent host-buffer pass on this layout (sddmm_host_traffic)."""
+    a, b = C.c_uint64(0), C.c_uint64(0)
+    check(_lib.lib().sddmm_host_traffic(lay.handle, C.byref(a), C.byref(b)))
+    return int(a.value), int(b.value)
+
+
 def sddmm_gpu_sync(layout):
     lay = layout.layout() if hasattr(layout, "layout") else layout
     check(_lib.lib().sddmm_host_sync(lay.handle))

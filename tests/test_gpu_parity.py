@@ -368,6 +368,45 @@ def test_pipelined_host_api_equals_synchronous(torch_mod):
     assert np.array_equal(bufs[1].numpy(), refs[3]) and np.array_equal(bufs[0].numpy(), refs[4])
 
 
+@pytest.mark.parametrize("plan_kind", ["bsmr", "tile"])
+def test_host_passes_copy_only_referenced_rows(plan_kind, torch_mod, monkeypatch):
+    """Host entry points with page-locked A / B: the referenced-rows gather (A rows of reorderedRows, B^T rows of the
+    referenced columns, read through the mapped pointers) gives bit-identical results to whole-array copies and
+    moves fewer bytes; pageable buffers fall back to whole-array copies.  Operands change between passes."""
+    torch = torch_mod
+    S = gen.with_empty_rows(gen.rmat(11, 8, 4), every=3)   # many empty rows AND columns
+    K = 64
+    b = pkg.BSMR().rowReordering(0.3, S, block_size=16)
+    b.colReordering(0.3, S, tiles="always" if plan_kind == "tile" else "never")
+    lay = b.layout()
+    used_cols = int(np.unique(S.col_idx).size)
+    used_rows = int((np.diff(S.row_off.astype(np.int64)) > 0).sum())
+    assert used_cols + used_rows < 0.85 * (S.M + S.N)
+    if plan_kind == "tile":
+        monkeypatch.setenv("SDDMM_B200_PLAN", "full")
+    out = torch.zeros(S.nnz, dtype=torch.float32).pin_memory()
+    for it in range(3):
+        A, B = gen.dense_operands(S.M, S.N, K, seed_a=300 + it, seed_b=400 + it)
+        ref = O.sddmm_cpu(S, A, B)
+        pa, pb = torch.from_numpy(A).pin_memory(), torch.from_numpy(B).pin_memory()
+        results = {}
+        for mode in ("full", "auto"):
+            monkeypatch.setenv("SDDMM_B200_H2D", mode)
+            P, _ = pkg.sddmm_gpu(pa.numpy(), pb.numpy(), lay)
+            results[mode] = (P.copy(), pkg.host_traffic(lay))
+            assert O.check_data(ref, P) == 0, (mode, it)
+            pkg.sddmm_gpu_async(pa.numpy(), pb.numpy(), lay, out.numpy(), it & 1)
+            pkg.sddmm_gpu_sync(lay)
+            assert np.array_equal(out.numpy(), P), (mode, it, "async")
+        assert np.array_equal(results["full"][0], results["auto"][0])
+        assert results["full"][1] == (4 * K * (S.M + S.N), 4 * S.nnz)
+        assert results["auto"][1] == (4 * K * (used_rows + used_cols), 4 * S.nnz)
+        monkeypatch.setenv("SDDMM_B200_H2D", "auto")
+        P2, _ = pkg.sddmm_gpu(A, B, lay)  # pageable numpy buffers: whole-array copies
+        assert pkg.host_traffic(lay)[0] == 4 * K * (S.M + S.N)
+        assert np.array_equal(P2, results["full"][0])
+
+
 def test_batched_sddmm_matches_per_batch_calls(torch_mod):
     """sddmm_gpu_batch (src/sddmmKernel.cu:2764-2850): numBatch (A, B, P) triples back to back, one layout."""
     torch = torch_mod
