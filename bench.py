@@ -531,8 +531,9 @@ def record_rmat(ctx, w, headline=True, scale=None, K=None, reorder=True, steps=N
                 ctx.mg.run_host(lay, nA, nB, nPs[i & 1] if ctx.rank == 0 else None, 0)
             torch.cuda.synchronize()
             e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-            api = ("sddmm_mgpu_run_host: 1/N slices of A and B per rank over PCIe, all-gather over NVLink, P reduced "
-                   "to rank 0 and copied out")
+            api = ("sddmm_mgpu_run_host: 1/N of the referenced rows of A and B per rank over PCIe (gathered through the "
+                   "mapped pinned buffers), all-gather over NVLink, P reduced to rank 0 and copied out")
+            moved = (int(ctx.sum_over_ranks([float(ctx.mg.host_traffic())])[0]), int(4 * nnz))
             if ctx.rank == 0:  # the merged result on the host against fp64, rows from every shard
                 pick_all = Rh[np.linspace(0, Rh.size - 1, 24).astype(np.int64)]
                 hPt = torch.from_numpy(nPs[(e2e_steps - 1) & 1]).cuda()
@@ -561,11 +562,11 @@ def record_rmat(ctx, w, headline=True, scale=None, K=None, reorder=True, steps=N
         ctx.barrier()
         e2e_ms_max, ceil_ms_max = ctx.max_over_ranks([e2e_ms, ceil_ms])
         full_in = int(4 * K * (M + N))
-        h2d_b, d2h_b = (moved if W == 1 else (full_in, int(4 * nnz)))
+        h2d_b, d2h_b = moved
         e2e_rec = dict(value=2.0 * nnz * K / (e2e_ms_max * 1e-3) / 1e9, unit=UNIT, ms_per_step=e2e_ms_max,
                        steps=e2e_steps, h2d_bytes_per_step=int(h2d_b), d2h_bytes_per_step=int(d2h_b),
-                       bytes_note=("whole job: A and B enter once per step (1/N per rank), P leaves once (rank 0)"
-                                   if W > 1 else
+                       bytes_note=((f"whole job: the referenced rows of A and B ({h2d_b / full_in:.0%} of the arrays) "
+                                    "enter once per step (1/N per rank), P leaves once (rank 0)") if W > 1 else
                                    ("the A rows and B^T rows the pass reads (non-empty rows / referenced columns of S: "
                                     f"{h2d_b / full_in:.0%} of the arrays) gathered from the pinned host buffers, all of "
                                     "P out, every step" if h2d_b < full_in else

@@ -369,9 +369,14 @@ int sddmm_mgpu_gather(sddmm_mgpu*, float* d_P, size_t count, void* stream);
  * holds the same host A (M x K) and B (N x K) but copies only its 1/world slice of each over its own PCIe link;
  * the slices are all-gathered over NVLink (so the host is read ONCE per job step, not once per rank), every rank
  * computes its panel range, the disjoint pieces of P are summed onto `root`, and root copies the whole P to h_P
- * (h_P may be NULL elsewhere).  msTotal (optional) = this rank's device time for the whole call. */
+ * (h_P may be NULL elsewhere).  msTotal (optional) = this rank's device time for the whole call.
+ * With page-locked h_A / h_B and a matrix that leaves at least 15 % of its rows + columns unreferenced, a rank reads
+ * only 1/world of the REFERENCED rows (non-empty rows of S, referenced columns; lists kept by sddmm_mgpu_shard)
+ * through the mapped pointers into a packed buffer; the packed buffers are all-gathered and unpacked on the device. */
 int sddmm_mgpu_run_host(sddmm_mgpu*, const bsmr_layout*, uint32_t K, const float* h_A, const float* h_B, float* h_P,
                         int root, float* msTotal);
+/* host -> device bytes THIS rank moved in its most recent sddmm_mgpu_run_host call */
+int sddmm_mgpu_host_traffic(const sddmm_mgpu*, uint64_t* h2dBytes);
 
 #ifdef __cplusplus
 }

@@ -138,6 +138,7 @@ def lib():
     L.sddmm_mgpu_run.argtypes = [vp, vp, u32, vp, vp, vp, vp]
     L.sddmm_mgpu_gather.argtypes = [vp, vp, C.c_size_t, vp]
     L.sddmm_mgpu_run_host.argtypes = [vp, vp, u32, vp, vp, vp, C.c_int, pf32]
+    L.sddmm_mgpu_host_traffic.argtypes = [vp, C.POINTER(u64)]
     L.bsmr_layout_eval.argtypes = [vp, f32, C.POINTER(Eval)]
     L.bsmr_original_block_stats_dev.argtypes = [vp, vp, u32, u32, u32, f32, vp, vp, vp]
     L.bsmr_original_block_stats.argtypes = [vp, vp, u32, u32, u32, f32, vp, vp]

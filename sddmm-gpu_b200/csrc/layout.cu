@@ -841,24 +841,30 @@ __global__ void k_flag_cols(const u32* __restrict__ cols, size_t n, u32 N, u32* 
 }
 }  // namespace
 
-const bsmr_layout::HostRefs* ensure_host_refs(const bsmr_layout* L, cudaStream_t s) {
-  if (L->hostRefs) return L->hostRefs.get();
+// the distinct values < N of up to two u32 lists, ascending, into `out`; returns their number
+u32 distinct_values_dev(const u32* a, size_t na, const u32* b, size_t nb, u32 N, DevBuf<u32>& out, cudaStream_t s) {
   TempScope tempScope(s);
-  const bsmr_layout_info& I = L->info;
-  auto h = std::make_unique<bsmr_layout::HostRefs>();
-  const u32 N = I.N ? I.N : 1u;
-  DevBuf<u32> flag(N), ex((size_t)N + 1);
-  SB_CUDA(cudaMemsetAsync(flag.get(), 0, (size_t)N * 4, s));
-  const size_t nd = L->arr[BSMR_DENSE_COLS].size(), ns = I.numSparseValues;
-  if (nd) k_flag_cols<<<grid_for(nd), 256, 0, s>>>(L->arr[BSMR_DENSE_COLS].get(), nd, I.N, flag.get());
-  if (ns) k_flag_cols<<<grid_for(ns), 256, 0, s>>>(L->arr[RPHM_SPARSE_COL_INDICES].get(), ns, I.N, flag.get());
+  const u32 n = N ? N : 1u;
+  DevBuf<u32> flag(n), ex((size_t)n + 1);
+  SB_CUDA(cudaMemsetAsync(flag.get(), 0, (size_t)n * 4, s));
+  if (na) k_flag_cols<<<grid_for(na), 256, 0, s>>>(a, na, N, flag.get());
+  if (nb) k_flag_cols<<<grid_for(nb), 256, 0, s>>>(b, nb, N, flag.get());
   SB_LAUNCH_CHECK();
-  scan_counts(flag.get(), ex.get(), N, s);
-  h->numCols = read_u32(ex.get() + N, s);
-  h->cols.alloc(h->numCols ? h->numCols : 1u, true);
-  k_compact_flagged<<<grid_for(N), 256, 0, s>>>(flag.get(), ex.get(), N, h->cols.get());
+  scan_counts(flag.get(), ex.get(), n, s);
+  const u32 cnt = read_u32(ex.get() + n, s);
+  out.alloc(cnt ? cnt : 1u, true);
+  k_compact_flagged<<<grid_for(n), 256, 0, s>>>(flag.get(), ex.get(), n, out.get());
   SB_LAUNCH_CHECK();
   SB_CUDA(cudaStreamSynchronize(s));
+  return cnt;
+}
+
+const bsmr_layout::HostRefs* ensure_host_refs(const bsmr_layout* L, cudaStream_t s) {
+  if (L->hostRefs) return L->hostRefs.get();
+  const bsmr_layout_info& I = L->info;
+  auto h = std::make_unique<bsmr_layout::HostRefs>();
+  h->numCols = distinct_values_dev(L->arr[BSMR_DENSE_COLS].get(), L->arr[BSMR_DENSE_COLS].size(),
+                                   L->arr[RPHM_SPARSE_COL_INDICES].get(), I.numSparseValues, I.N, h->cols, s);
   return (L->hostRefs = std::move(h)).get();
 }
 

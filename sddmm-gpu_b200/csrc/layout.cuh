@@ -160,6 +160,8 @@ bsmr_layout* layout_load(const char* path);
 // builds (once, then cached) the super-panel layout for G panels per super-panel; returns it
 // hubBudget: number of B^T rows that may be kept L2-resident (0 = no residency classes)
 const SuperPanelLayout* ensure_superpanels(const bsmr_layout* L, u32 G, u32 hubBudget, cudaStream_t s);
+// the distinct values < N of up to two u32 device lists, ascending, into `out`; returns their number
+u32 distinct_values_dev(const u32* a, size_t na, const u32* b, size_t nb, u32 N, DevBuf<u32>& out, cudaStream_t s);
 // builds (once) the list of columns the layout references (host-buffer passes copy only those B^T rows)
 const bsmr_layout::HostRefs* ensure_host_refs(const bsmr_layout* L, cudaStream_t s);
 // builds (once) the row-ordered residual layout of the row-stream kernel

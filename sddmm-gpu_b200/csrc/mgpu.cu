@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cstring>
 
 #include <vector>
 
@@ -162,6 +163,13 @@ struct sddmm_mgpu {
   std::vector<u64> pre;  // prefix sum of per-panel non-zero counts of the reordered matrix (kept for rebalancing)
   // sddmm_mgpu_run_host: device staging (grown on demand), two streams and their events
   DevBuf<float> wsA, wsB, wsP, wsPfull;
+  // the rows of A (non-empty rows of S) and of B^T (referenced columns) the WHOLE job reads: with page-locked host
+  // buffers every rank gathers 1/world of each list over its PCIe link into a packed buffer, the packed buffers are
+  // all-gathered over NVLink and unpacked on the device -- PCIe and NVLink carry only rows some rank reads
+  DevBuf<u32> refRows, refCols;
+  u32 nRefRows = 0, nRefCols = 0;
+  DevBuf<float> packA, packB;
+  unsigned long long lastH2DBytes = 0;
   cudaStream_t sCopy = nullptr, sWork = nullptr;
   cudaEvent_t evA = nullptr, evB = nullptr, evDone = nullptr, evT0 = nullptr, evT1 = nullptr;
   ~sddmm_mgpu() {
@@ -170,6 +178,48 @@ struct sddmm_mgpu {
     if (sWork) cudaStreamDestroy(sWork);
   }
 };
+
+// rows list[beg..end) of a page-locked host array (read through its mapped pointer) into the packed buffer at the
+// same list positions; and the inverse on the device after the all-gather
+static __global__ void __launch_bounds__(256) k_pack_rows_h2d(const u32* __restrict__ list, u32 beg, u32 end, u32 K4,
+                                                              const float4* hsrc, float4* __restrict__ packed) {
+  const u32 lane = threadIdx.x & 31u;
+  const u32 warps = (gridDim.x * blockDim.x) >> 5, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  for (u32 i = beg + gw; i < end; i += warps) {
+    const float4* src = hsrc + (size_t)list[i] * K4;
+    float4* dst = packed + (size_t)i * K4;
+    for (u32 c0 = 0; c0 < K4; c0 += 128u) {
+      float4 v[4];
+#pragma unroll
+      for (u32 u = 0; u < 4; ++u) {
+        const u32 c = c0 + u * 32u + lane;
+        if (c < K4) v[u] = src[c];
+      }
+#pragma unroll
+      for (u32 u = 0; u < 4; ++u) {
+        const u32 c = c0 + u * 32u + lane;
+        if (c < K4) dst[c] = v[u];
+      }
+    }
+  }
+}
+static __global__ void __launch_bounds__(256) k_unpack_rows(const u32* __restrict__ list, u32 n, u32 K4,
+                                                            const float4* __restrict__ packed, float4* __restrict__ dst) {
+  const u32 lane = threadIdx.x & 31u;
+  const u32 warps = (gridDim.x * blockDim.x) >> 5, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  for (u32 i = gw; i < n; i += warps) {
+    const float4* src = packed + (size_t)i * K4;
+    float4* d = dst + (size_t)list[i] * K4;
+    for (u32 c = lane; c < K4; c += 32u) d[c] = src[c];
+  }
+}
+static bool host_mapped(const void* p, const void** dev) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+  *dev = at.devicePointer;
+  return true;
+}
 
 #define API_BEGIN try {
 #define API_END                                   \
@@ -247,6 +297,11 @@ int sddmm_mgpu_shard(sddmm_mgpu* g, const uint32_t* d_rowOff, const uint32_t* d_
       nccl_check(nccl().Broadcast(d_reorderedRows, d_reorderedRows, (size_t)*numRows * 4, kNcclUint8, 0, g->comm, s),
                  "ncclBroadcast(reorderedRows)");
   }
+  g->nRefRows = *numRows;
+  g->refRows.alloc(*numRows ? *numRows : 1u, true);
+  if (*numRows)
+    SB_CUDA(cudaMemcpyAsync(g->refRows.get(), d_reorderedRows, (size_t)*numRows * 4, cudaMemcpyDeviceToDevice, s));
+  g->nRefCols = distinct_values_dev(d_colIdx, nnz, nullptr, 0, N, g->refCols, s);
   g->cuts.assign((size_t)g->world + 1, 0);
   shard_plan_dev(d_rowOff, d_reorderedRows, *numRows, (u32)g->world, g->cuts.data(), s, &g->pre);
   if (h_cuts) std::memcpy(h_cuts, g->cuts.data(), g->cuts.size() * 4);
@@ -309,8 +364,8 @@ int sddmm_mgpu_run_host(sddmm_mgpu* g, const bsmr_layout* L, uint32_t K, const f
     SB_CUDA(cudaEventCreate(&g->evT0));
     SB_CUDA(cudaEventCreate(&g->evT1));
   }
-  if (g->wsA.size() < cA * W) g->wsA.alloc(cA * W, true);
-  if (g->wsB.size() < cB * W) g->wsB.alloc(cB * W, true);
+  if (g->wsA.size() < cA * W) { g->wsA.alloc(cA * W, true); SB_CUDA(cudaMemset(g->wsA.get(), 0, cA * W * 4)); }
+  if (g->wsB.size() < cB * W) { g->wsB.alloc(cB * W, true); SB_CUDA(cudaMemset(g->wsB.get(), 0, cB * W * 4)); }
   if (g->wsP.size() < nP) {  // zeroed once: a shard's pass never writes foreign entries, so the sum below IS the merge
     g->wsP.alloc(nP, true);
     SB_CUDA(cudaMemset(g->wsP.get(), 0, nP * 4));
@@ -323,6 +378,45 @@ int sddmm_mgpu_run_host(sddmm_mgpu* g, const bsmr_layout* L, uint32_t K, const f
     if (end > beg) SB_CUDA(cudaMemcpyAsync(d + beg, h + beg, (end - beg) * 4, cudaMemcpyHostToDevice, g->sCopy));
   };
   SB_CUDA(cudaEventRecord(g->evT0, g->sCopy));
+  // referenced rows only, when both host buffers are page-locked and the lists are clearly shorter than the arrays
+  const void *mA = nullptr, *mB = nullptr;
+  const char* h2dEnv = getenv("SDDMM_B200_H2D");
+  const bool forceFull = h2dEnv && !strcmp(h2dEnv, "full"), forceGather = h2dEnv && !strcmp(h2dEnv, "gather");
+  const bool refsKnown = g->world > 1 && (g->nRefRows || g->nRefCols) && !(K & 3u) && !forceFull;
+  const bool sparseRefs = forceGather || ((size_t)g->nRefRows + g->nRefCols) * 100 <= ((size_t)I.M + I.N) * 85;
+  if (refsKnown && sparseRefs && host_mapped(h_A, &mA) && host_mapped(h_B, &mB)) {
+    const u32 K4 = K / 4;
+    const size_t perA = (g->nRefRows + W - 1) / W, perB = (g->nRefCols + W - 1) / W;
+    if (g->packA.size() < perA * W * K) g->packA.alloc(perA * W * K, true);
+    if (g->packB.size() < perB * W * K) g->packB.alloc(perB * W * K, true);
+    auto pack = [&](const u32* list, u32 n, size_t per, const void* hsrc, float* packed) {
+      const u32 beg = (u32)std::min<size_t>(n, r * per), end = (u32)std::min<size_t>(n, (r + 1) * per);
+      if (end > beg)
+        k_pack_rows_h2d<<<128, 256, 0, g->sCopy>>>(list, beg, end, K4, static_cast<const float4*>(hsrc),
+                                                   reinterpret_cast<float4*>(packed));
+      SB_LAUNCH_CHECK();
+    };
+    auto unpack = [&](const u32* list, u32 n, const float* packed, float* dst) {
+      if (n) k_unpack_rows<<<grid_for((size_t)n * 32), 256, 0, g->sWork>>>(list, n, K4,
+                                                                          reinterpret_cast<const float4*>(packed),
+                                                                          reinterpret_cast<float4*>(dst));
+      SB_LAUNCH_CHECK();
+    };
+    pack(g->refRows.get(), g->nRefRows, perA, mA, g->packA.get());
+    SB_CUDA(cudaEventRecord(g->evA, g->sCopy));
+    pack(g->refCols.get(), g->nRefCols, perB, mB, g->packB.get());
+    SB_CUDA(cudaEventRecord(g->evB, g->sCopy));
+    SB_CUDA(cudaStreamWaitEvent(g->sWork, g->evA, 0));
+    nccl_check(nccl().AllGather(g->packA.get() + r * perA * K, g->packA.get(), perA * K, kNcclFloat32, g->comm, g->sWork),
+               "ncclAllGather(A rows)");
+    unpack(g->refRows.get(), g->nRefRows, g->packA.get(), dA);
+    SB_CUDA(cudaStreamWaitEvent(g->sWork, g->evB, 0));
+    nccl_check(nccl().AllGather(g->packB.get() + r * perB * K, g->packB.get(), perB * K, kNcclFloat32, g->comm, g->sWork),
+               "ncclAllGather(B rows)");
+    unpack(g->refCols.get(), g->nRefCols, g->packB.get(), dB);
+    g->lastH2DBytes = (unsigned long long)(std::min<size_t>(g->nRefRows, (r + 1) * perA) - std::min<size_t>(g->nRefRows, r * perA) +
+                                           std::min<size_t>(g->nRefCols, (r + 1) * perB) - std::min<size_t>(g->nRefCols, r * perB)) * K * 4;
+  } else {
   h2d_slice(dA, h_A, nA, cA);
   SB_CUDA(cudaEventRecord(g->evA, g->sCopy));
   h2d_slice(dB, h_B, nB, cB);
@@ -331,6 +425,9 @@ int sddmm_mgpu_run_host(sddmm_mgpu* g, const bsmr_layout* L, uint32_t K, const f
   if (g->world > 1) nccl_check(nccl().AllGather(dA + r * cA, dA, cA, kNcclFloat32, g->comm, g->sWork), "ncclAllGather(A)");
   SB_CUDA(cudaStreamWaitEvent(g->sWork, g->evB, 0));
   if (g->world > 1) nccl_check(nccl().AllGather(dB + r * cB, dB, cB, kNcclFloat32, g->comm, g->sWork), "ncclAllGather(B)");
+    g->lastH2DBytes = (unsigned long long)((std::min(nA, (r + 1) * cA) - std::min(nA, r * cA)) +
+                                           (std::min(nB, (r + 1) * cB) - std::min(nB, r * cB))) * 4;
+  }
   {
     const int rc = sddmm_run_dev(L, K, dA, dB, dP, g->sWork);
     if (rc) return rc;
@@ -346,6 +443,13 @@ int sddmm_mgpu_run_host(sddmm_mgpu* g, const bsmr_layout* L, uint32_t K, const f
   SB_CUDA(cudaEventRecord(g->evT1, g->sCopy));
   SB_CUDA(cudaEventSynchronize(g->evT1));
   if (msTotal) SB_CUDA(cudaEventElapsedTime(msTotal, g->evT0, g->evT1));
+  API_END
+}
+
+int sddmm_mgpu_host_traffic(const sddmm_mgpu* g, uint64_t* h2dBytes) {
+  API_BEGIN
+  need(g && h2dBytes, "arguments");
+  *h2dBytes = g->lastH2DBytes;
   API_END
 }
 

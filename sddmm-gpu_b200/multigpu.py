@@ -135,6 +135,12 @@ class MultiGpu:
                                              P.ctypes.data if P is not None else None, int(root), C.byref(ms)))
         return ms.value
 
+    def host_traffic(self):
+        """host -> device bytes this rank moved in its most recent run_host call (sddmm_mgpu_host_traffic)."""
+        b = C.c_uint64(0)
+        check(_lib.lib().sddmm_mgpu_host_traffic(self._h, C.byref(b)))
+        return int(b.value)
+
     def gather(self, P):
         """sddmm_mgpu_gather: disjoint pieces (zeros elsewhere) -> the full P on every rank."""
         import torch

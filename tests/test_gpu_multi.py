@@ -111,6 +111,16 @@ def _worker(rank, world, port, q):
             g.run_host(sh.layout, A, B, hP, 0)
         if rank == 0:
             ok = ok and O.check_data(Pref, hP) == 0
+        # the same with page-locked buffers: every rank reads only its share of the REFERENCED rows (half of an R-MAT
+        # graph's rows and columns are empty) through the mapped pointers; packed all-gather, unpack on the device
+        full_bytes = g.host_traffic()
+        pA, pB = torch.from_numpy(A).pin_memory(), torch.from_numpy(B).pin_memory()
+        hP2 = np.full(S.nnz, np.nan, np.float32) if rank == 0 else None
+        for _ in range(2):
+            g.run_host(sh.layout, pA.numpy(), pB.numpy(), hP2, 0)
+        ok = ok and 0 < g.host_traffic() < 0.8 * full_bytes
+        if rank == 0:
+            ok = ok and O.check_data(Pref, hP2) == 0
         # cost calibration: the cuts may move, the union must still cover every non-zero exactly once
         sh.calibrate(dA, dB, P, rounds=2, passes=2)
         P.zero_()
