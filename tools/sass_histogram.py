@@ -1,5 +1,5 @@
 """Per-kernel SASS opcode histogram of libsddmm_b200.so (evidence that the hot kernels are Blackwell-native:
-UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG = TMA, UTCBAR = tcgen05.commit; B200_PROFILING.md table).
+UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG = TMA, UTCBAR = tcgen05.commit, .2CTA = the cta_group::2 forms, FHFMA = fma.rn.f32.f16; B200_PROFILING.md table).
 
     python tools/sass_histogram.py > profiles/sass_r02.txt
 """
@@ -11,8 +11,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "sddmm-gpu_b200", "libsddmm_b200.so")
-KEYS = ["UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMALDG.2D.GATHER4", "MULTICAST", "SYNCS", "HMMA", "FFMA", "LDG", "LDS", "STS",
-        "STG", "SHFL", "POPC", "REDUX", "ATOM"]
+KEYS = ["UTCHMMA", "2CTA", "UTCBAR", "LDTM", "UTMALDG", "UTMALDG.2D.GATHER4", "MULTICAST", "SYNCS", "HMMA", "FFMA", "FHFMA",
+        "LDG", "LDS", "STS", "STG", "SHFL", "POPC", "REDUX", "ATOM"]
 
 
 def main():
@@ -31,7 +31,7 @@ def main():
             op = m.group(1)
             hist[cur]["total"] += 1
             for k in KEYS:
-                if op.startswith(k) or (k == "MULTICAST" and "MULTICAST" in op) or (k == "UTMALDG.2D.GATHER4" and "GATHER4" in op):
+                if op.startswith(k) or (k == "MULTICAST" and "MULTICAST" in op) or (k == "2CTA" and ".2CTA" in op) or (k == "UTMALDG.2D.GATHER4" and "GATHER4" in op):
                     hist[cur][k] += 1
     print(f"# SASS opcode counts per kernel, {os.path.relpath(LIB, ROOT)} (cuobjdump -sass, sm_100a)")
     print("# " + " ".join(f"{k:>8}" for k in ["total"] + KEYS) + "  kernel")
