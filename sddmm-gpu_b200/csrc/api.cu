@@ -547,7 +547,8 @@ static size_t h2d_operands(const bsmr_layout* L, u32 K, const float* hA, const f
     const size_t refRows = (size_t)I.numRows + hr->numCols;
     if (mode == 2 || refRows * 100 <= ((size_t)I.M + I.N) * 85) {
       // few CTAs: the kernel waits on PCIe, it must not crowd the SDDMM pass of the other slot off the SMs
-      k_gather_rows_h2d<<<128, 256, 0, s>>>(L->arr[BSMR_REORDERED_ROWS].get(), I.numRows, hr->cols.get(), hr->numCols,
+      static const int ctas = [] { const char* e = getenv("SDDMM_B200_H2D_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 128; }();
+      k_gather_rows_h2d<<<ctas, 256, 0, s>>>(L->arr[BSMR_REORDERED_ROWS].get(), I.numRows, hr->cols.get(), hr->numCols,
                                             I.M, I.N, K / 4, static_cast<const float4*>(mA),
                                             static_cast<const float4*>(mB), reinterpret_cast<float4*>(dA),
                                             reinterpret_cast<float4*>(dB));
