@@ -958,6 +958,9 @@ static __global__ void __launch_bounds__(256) k_round_operands(u32 M, u32 N, u32
                                                                const u32* __restrict__ R, u32 nR,
                                                                float4* __restrict__ Ar, float4* __restrict__ Br,
                                                                BatchStrides bs) {
+  // programmatic dependent launch: the tile kernel behind this pass may be scheduled now; it waits
+  // (griddepcontrol.wait) before its first read of the rounded copies
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   A += (bs.a >> 2) * blockIdx.y;
   B += (bs.b >> 2) * blockIdx.y;
   Ar += (size_t)nR * K4 * blockIdx.y;
@@ -984,6 +987,9 @@ static __global__ void __launch_bounds__(256) k_round_operands_half(u32 M, u32 N
                                                                     const u32* __restrict__ R, u32 nR,
                                                                     uint2* __restrict__ Ar, uint2* __restrict__ Br,
                                                                     BatchStrides bs) {
+  // programmatic dependent launch: the tile kernel behind this pass may be scheduled now; it waits
+  // (griddepcontrol.wait) before its first read of the rounded copies
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   A += (bs.a >> 2) * blockIdx.y;
   B += (bs.b >> 2) * blockIdx.y;
   Ar += (size_t)nR * K4 * blockIdx.y;
@@ -1403,9 +1409,9 @@ constexpr u32 kTpEpiThreads = 512;
 constexpr u32 kTpStages = 4;
 constexpr u32 kTpStagingBytes = 128u * 128u * 4u;  // one 128x128 tile's stored entries at most
 constexpr u32 kTpPrefetch = 12;  // CSR indices per epilogue thread and tile requested ahead (covers 6144 entries)
-// AUTO's choice between K9 and K10 for K >= 128, from measurements (4096^2 masks, one CUDA graph per pass incl. the
+// AUTO's choice between K9 and K10 for K >= 64, from measurements (4096^2 masks, one CUDA graph per pass incl. the
 // rounding pre-pass, K=256, K9 / K10): 70 % sparse 35.1 / 30.7 us, 90 % 33.0 / 29.0, 50 % 40.7 / 40.5; fp16 operands
-// 27.0 / 24.9 us.  K = 64: 22.5 / 22.7 us (and 23.9 for the register-staged K8, which stays the choice below 128).
+// 27.0 / 24.9 us.  K = 64: 22.5 / 22.7 us (and 23.9 for the register-staged K8, which stays the choice below 64).
 constexpr bool kPairDefault = true;
 
 __device__ __forceinline__ u32 mapa_u32(u32 smemAddr, u32 rank) {
@@ -1486,6 +1492,9 @@ k_sddmm_tile_pair(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 
   if (warp == 0) {
     // ---- producer (both CTAs): A rows of this CTA's tile row, B^T rows of this CTA's half of the 256 columns
+    // (launched with programmatic stream serialization: everything above overlapped the rounding pass; its copies
+    //  are complete and visible after this wait -- nothing else in the kernel reads what that pass writes)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     u32 g = 0;
     for (u32 q = pairId; q < numQuads; q += numPairs) {
       const uint2 qrc = quads[q];
@@ -2106,14 +2115,14 @@ void plan_resolve(const bsmr_layout* L, u32 K, u32 numBatch, const sddmm_plan* i
     }
   }
   if (p.plan == SDDMM_PLAN_TILE) {
-    // REG: register-staged tiles; TMA: one CTA per tile fed by TMA (default for K >= 128; below that the rounding
-    // pre-pass costs more than it saves); TMA_CLUSTER: 2x2 clusters with multicast (opt-in: measured slower)
+    // REG: register-staged tiles (K < 64: the rounding pre-pass of the TMA forms costs more than it saves there);
+    // TMA: one CTA per tile fed by TMA; TMA_PAIR: persistent CTA pairs (AUTO for K >= 64); TMA_CLUSTER: 2x2 clusters with multicast (opt-in: measured slower)
     if (p.operands == SDDMM_OPERANDS_FP16) {
       if (p.tile == SDDMM_TILE_REG || p.tile == SDDMM_TILE_TMA_CLUSTER)
         fail(SDDMM_E_UNSUPPORTED, "SDDMM_OPERANDS_FP16 is implemented by the TMA tile kernels only (tile = SDDMM_TILE_TMA / _TMA_PAIR)");
       if (p.tile == SDDMM_TILE_AUTO) p.tile = pair_default() ? SDDMM_TILE_TMA_PAIR : SDDMM_TILE_TMA;
     }
-    if (p.tile == SDDMM_TILE_AUTO) p.tile = K >= 128 ? (pair_default() ? SDDMM_TILE_TMA_PAIR : SDDMM_TILE_TMA) : SDDMM_TILE_REG;
+    if (p.tile == SDDMM_TILE_AUTO) p.tile = K >= 64 ? (pair_default() ? SDDMM_TILE_TMA_PAIR : SDDMM_TILE_TMA) : SDDMM_TILE_REG;
     if ((p.tile == SDDMM_TILE_TMA_CLUSTER || p.tile == SDDMM_TILE_TMA_PAIR) && !L->tl->numQuads) p.tile = SDDMM_TILE_TMA;
     if (p.tile == SDDMM_TILE_TMA_PAIR) p.tileStages = kTpStages;  // fixed ring depth
     if (!p.tileStages) p.tileStages = 2;
@@ -2234,11 +2243,14 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
       cfg.blockDim = dim3(kTpThreads);
       cfg.dynamicSmemBytes = psmem;
       cfg.stream = denseStream;
-      cudaLaunchAttribute at[1];
+      cudaLaunchAttribute at[2];
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // prologue under the rounding pass's tail
+      at[1].val.programmaticStreamSerializationAllowed = 1;
+      static const bool pdl = [] { const char* e = getenv("SDDMM_B200_PAIR_PDL"); return !e || atoi(e) != 0; }();
       cfg.attrs = at;
-      cfg.numAttrs = 1;
+      cfg.numAttrs = pdl ? 2 : 1;
       // persistent: as many CTA pairs as can be resident at once (a static round-robin schedule must not queue pairs)
       cfg.gridDim = dim3((unsigned)device_sm_count() & ~1u, 1);
       static std::mutex occMu;
