@@ -458,6 +458,14 @@ __device__ __forceinline__ bool cb_sig_may_join(float sh, float exRep, float nRe
   return !(ub * (1.0002f + thr) < thr * (Sa + Sb));
 }
 
+// ---- norm bound (no memory access beyond the meta record) ------------------------------------------------------
+// sum_i min(a_i, b_i) <= min(S_a, S_b) and sum_i max(a_i, b_i) = S_a + S_b - sum_i min >= max(S_a, S_b), with
+// S = (sum of counts) / |.|, so sim <= min(S_a, S_b) / max(S_a, S_b): a hub row (S ~ sqrt(#blocks)) can never join a
+// cluster of short rows and vice versa.  Same margin and safety factor as the signature bound.
+__device__ __forceinline__ bool cb_norm_may_join(float Sa, float Sb, float thr) {
+  return !(fminf(Sa, Sb) * 1.0002f < thr * fmaxf(Sa, Sb));
+}
+
 // block 0 only: the next (up to G) unclustered positions at or after `from`, in order
 __device__ void cb_find_seeds(const ClusterBatchArgs& a, u32 from, u32* sCount) {
   __shared__ u32 warpCnt[kCbWarps];
@@ -540,6 +548,14 @@ __device__ __forceinline__ u32 cb_eval_row_warp(const ClusterBatchArgs& a, const
   const uint2* ent = a.enc + m.x;
   const u32 ssCmp = m.z;
   const float nCmpInv = ssCmp ? 1.0f / sqrtf((float)ssCmp) : 0.f;
+  if (a.sigThr > 0.f && ssCmp) {  // norm bound: decided from the meta record alone
+    const float Sb = (float)m.w * nCmpInv;
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < TG; ++k)
+      if ((u32)k < kmax) any = any || sSs[k] == 0 || cb_norm_may_join(Sa[k], Sb, a.sigThr);
+    if (!any) return kNull;
+  }
   if (a.W && ssCmp && m.y * 2u > a.W) {  // reading the signature is cheaper than reading the entries
     u32 sh[TG], popB = 0;
 #pragma unroll
@@ -653,6 +669,14 @@ __device__ __forceinline__ u32 cb_eval_row_lane(const ClusterBatchArgs& a, const
   const u32 ssCmp = m.z;
   const float nCmpInv = ssCmp ? 1.0f / sqrtf((float)ssCmp) : 0.f;
   *again = false;
+  if (a.sigThr > 0.f && ssCmp) {  // norm bound: decided from the meta record alone
+    const float Sb = (float)m.w * nCmpInv;
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < TG; ++k)
+      if ((u32)k < kmax) any = any || sSs[k] == 0 || cb_norm_may_join(Sa[k], Sb, a.sigThr);
+    if (!any) return kNull;
+  }
   if (a.W && ssCmp && (m.y * 2u > a.W || m.y > a.laneRows)) {
     u32 sh[TG], popB = 0;
 #pragma unroll
@@ -1073,7 +1097,12 @@ void row_reorder_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32
       if (sigCfg != 0 && a.sigThr > 0.f && totalEnt) {
         const double avgEnt = (double)totalEnt / (double)(M - zeroRows);
         u32 bits = 64;
-        while (bits < (a.laneRows ? 4.0 : 8.0) * avgEnt && bits < (1u << 16)) bits <<= 1;
+        // signature bits per average kept entry.  Lane regime (graphs): 16 -- R-MAT scale 22, whole row reorder at
+        // 4 / 8 / 16 / 32 bits per entry: 37.6 / 29.5 / 26.6 / 28.9 s (fewer entry-list walks by single lanes vs
+        // more signature bytes per candidate); the permutation is the same whatever the width.
+        double perEnt = a.laneRows ? 16.0 : 8.0;
+        if (const char* e = getenv("SDDMM_B200_CLUSTER_SIGBITS")) { const double v = atof(e); if (v >= 1.0 && v <= 64.0) perEnt = v; }
+        while (bits < perEnt * avgEnt && bits < (1u << 16)) bits <<= 1;
         if (bits >= nbpr) { a.W = (nbpr + 31u) / 32u; a.sigMask = 0xFFFFFFFFu; }
         else { a.W = bits / 32u; a.sigMask = bits - 1u; }
         sigBuf.alloc((size_t)M * a.W);
