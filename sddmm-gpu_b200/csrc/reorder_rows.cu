@@ -1114,6 +1114,10 @@ void row_reorder_dev(const u32* d_rowOff, const u32* d_colIdx, u32 M, u32 N, u32
     }
     u32 G = (u32)((200u * 1024u) / (((size_t)nbpr + a.W + 1) * 4));
     if (o.batch && o.batch < G) G = o.batch;
+    // lane regime: 4 clusters per batch unless asked otherwise (a lane's work and its chance of having to walk an
+    // entry list both grow with the batch: R-MAT scale 20 / 22 at G = 8 vs 4: 5.8 vs 4.8 s, 26.6 vs 25.1 s); the warp
+    // regime wants the widest batch (uniform 100k^2: 0.90 s at 8, 2.15 s at 4)
+    if (a.laneRows && !o.batch && G > 4) G = 4;
     G = G >= 8 ? 8u : G >= 4 ? 4u : G >= 2 ? 2u : 1u;  // template instances
     a.G = G;
     SB_CUDA(cudaMemsetAsync(slots.get(), 0xFF, 4 * 8, s));
