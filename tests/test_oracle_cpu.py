@@ -166,6 +166,17 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
     assert L.sddmm_b200_abi_version() == 2
 
 
+def test_host_traffic_entry_points_check_their_arguments():
+    """sddmm_host_traffic / sddmm_mgpu_host_traffic (the bytes a host-buffer pass moved): present in the ABI and
+    strict about null handles -- an argument error, never a crash; no device is touched."""
+    import ctypes as C
+    L = pkg.lib()
+    a, b = C.c_uint64(7), C.c_uint64(7)
+    assert L.sddmm_host_traffic(None, C.byref(a), C.byref(b)) == 1      # SDDMM_E_ARG
+    assert L.sddmm_mgpu_host_traffic(None, C.byref(a)) == 1
+    assert b"null" in L.sddmm_last_error().lower() or b"argument" in L.sddmm_last_error().lower()
+
+
 def test_product_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
