@@ -2070,6 +2070,26 @@ static u32 env_choice(const char* name, std::initializer_list<std::pair<const ch
   return 0u;
 }
 
+// The super-panel layout a pass uses and whether it runs in gather mode.  Gather mode (several B^T rows in flight per
+// 8 lanes, no column-run reuse) when a (super-panel, column) run averages fewer than 2.5 entries -- graphs -- and the
+// rows are short: K <= 64, or any K with fp16 B^T rows.  Gather mode has nothing to gain from tall super-panels (their
+// only purpose is run reuse) and runs on half-height ones: 96 KB A tiles, shorter tile-load phases, more CTAs in
+// flight (R-MAT scale 22, 192 -> 96 KB: K=64 2.06 -> 1.90 ms, fp16 K=64 1.67 -> 1.49 ms, fp16 K=256 4.92 -> 4.47 ms;
+// reuse mode at K=256 loses: 7.40 -> 7.57 ms and keeps the full height).
+struct SpChoice {
+  const SuperPanelLayout* sp;
+  bool gather;
+};
+static SpChoice choose_superpanels(const bsmr_layout* L, u32 K, bool halfA, bool halfB, cudaStream_t s) {
+  const int gatherCfg = [] { const char* e = getenv("SDDMM_B200_SP_GATHER"); return e ? atoi(e) : -1; }();
+  const u32 G = superpanel_G(K, halfA), hub = hub_budget(L, K, halfB);
+  const SuperPanelLayout* sp = ensure_superpanels(L, G, hub, s);
+  const bool gather = gatherCfg >= 0 ? gatherCfg != 0
+                                     : ((halfB || K <= 64u) && (double)sp->numEntries < 2.5 * (double)sp->numRuns);
+  if (gather && G >= 2u && !getenv("SDDMM_B200_SP_SMEM_KB")) sp = ensure_superpanels(L, G / 2u, hub, s);
+  return {sp, gather};
+}
+
 // whether AUTO picks the CTA-pair tile kernel (K10) over the one-tile-per-CTA TMA kernel (K9)
 static bool pair_default() {
   static const bool v = [] { const char* e = getenv("SDDMM_B200_TILE_PAIR"); return e ? atoi(e) != 0 : kPairDefault; }();
@@ -2167,7 +2187,7 @@ void plan_prepare(const bsmr_layout* L, u32 K, u32 numBatch, const sddmm_plan& p
   if (p.dense == SDDMM_DENSE_TMA) ensure_dense_tma(L, K, numBatch, s);
   if (p.residual == SDDMM_RESIDUAL_SUPERPANEL) {
     const bool halfA = p.operands == SDDMM_OPERANDS_FP16, halfB = halfA && sp_half_b(K);
-    ensure_superpanels(L, superpanel_G(K, halfA), hub_budget(L, K, halfB), s);
+    choose_superpanels(L, K, halfA, halfB, s);
     if (halfB) ensure_half_b(L, K, numBatch);
   }
   if (p.residual == SDDMM_RESIDUAL_STREAM) ensure_stream(L, s);
@@ -2378,8 +2398,8 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
       }
     } else if (p.residual == SDDMM_RESIDUAL_SUPERPANEL) {
       const bool halfA = p.operands == SDDMM_OPERANDS_FP16, halfB = halfA && sp_half_b(K);
-      const SuperPanelLayout* sp =
-          ensure_superpanels(L, superpanel_G(K, halfA), hub_budget(L, K, halfB), sparseStream);
+      const SpChoice spc = choose_superpanels(L, K, halfA, halfB, sparseStream);
+      const SuperPanelLayout* sp = spc.sp;
       if (sp->numWork) {
         const size_t smem = (size_t)sp->rows * K * (halfA ? 2 : 4);
         const float* bSrc = dB;
@@ -2407,7 +2427,6 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
         // eviction hints when B (N x K floats) cannot live in the 126 MB L2 next to A and the layout; gather mode
         // (several B^T rows in flight, no column-run reuse) when a run averages fewer than 1.5 entries
         const int hintCfg = l2_hint_cfg();
-        const int gatherCfg = [] { const char* e = getenv("SDDMM_B200_SP_GATHER"); return e ? atoi(e) : -1; }();
         const bool hints = hintCfg >= 0 ? hintCfg != 0 : l2_hints_wanted(L, K);
         // measured on R-MAT scale 22: gather mode 2.07 -> 1.17 ms at K=32 and 2.46 -> 2.03 ms at K=64, but 3.58 -> 4.00
         // ms at K=128 and worse above (there one row per 8 lanes already keeps 64 KB per SM in flight and the L2
@@ -2418,7 +2437,7 @@ void sddmm_launch(const bsmr_layout* L, u32 K, const float* dA, const float* dB,
         // 6.33 -> 4.94 ms); the uniform 1 % matrix (3.8 entries per run, 7.7 with the fp16 tile) keeps reuse mode.
         // A third form, two independent streams per group with a B^T register set each (two rows in flight AND run
         // reuse), measured 7.44 vs 7.27 ms at K=256: at that row length bandwidth, not the round trip, is the limit.
-        const bool gather = gatherCfg >= 0 ? gatherCfg != 0 : ((halfB || K <= 64u) && (double)sp->numEntries < 2.5 * (double)sp->numRuns);
+        const bool gather = spc.gather;  // choose_superpanels
 #define SB_SP_CASE2(NBv, THRv, Uv, HALFv)                                                         \
   do {                                                                                            \
     if (gather) { if (hints) launch(k_sddmm_residual_sp<NBv, THRv, true, Uv, HALFv>, THRv);       \
