@@ -60,6 +60,14 @@ def exchange_unique_id(make_id=unique_id, src=0, device="cpu") -> bytes:
     return bytes(t.cpu().numpy().tobytes())
 
 
+def packed_share(n: int, rank: int, world: int):
+    """The slice [beg, end) of an n-entry referenced-row list that `rank` brings over its own PCIe link in
+    sddmm_mgpu_run_host (csrc/mgpu.cu): ceil(n / world) consecutive list positions per rank, the tail clipped.  The
+    packed buffers of all ranks are all-gathered and row i of the list is unpacked to row list[i] of the operand."""
+    per = -(-n // world) if world > 0 else n
+    return min(n, rank * per), min(n, (rank + 1) * per)
+
+
 class MultiGpu:
     """Owns a `sddmm_mgpu*`: this process's rank of the library's NCCL communicator on the current CUDA device."""
 

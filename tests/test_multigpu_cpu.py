@@ -1,6 +1,7 @@
 """world_size-2 gloo tests (CPU) of the multi-GPU host logic: the out-of-band exchange of the library's NCCL
 communicator id (multigpu.exchange_unique_id), nnz-balanced panel shards (bsmr_shard_plan: the rule
-sddmm_mgpu_shard applies on the device), and the disjoint-merge property sddmm_mgpu_gather relies on.  Each rank's
+sddmm_mgpu_shard applies on the device), the disjoint-merge property sddmm_mgpu_gather relies on, and the
+packed referenced-rows exchange of sddmm_mgpu_run_host.  Each rank's
 share of P is produced by the oracle here (test infrastructure); the product kernels and the NCCL calls themselves
 run in the -m gpu tests and under bench.py --gpus N."""
 import os
@@ -75,6 +76,23 @@ def _worker(rank, world, port, q):
         Pt = torch.from_numpy(mine)
         dist.all_reduce(Pt)  # disjoint pieces, zeros elsewhere: the sum IS the merge (sddmm_mgpu_gather)
         ok = np.array_equal(Pt.numpy(), Pfull)
+        # host pass of the whole job (sddmm_mgpu_run_host): every rank packs ITS share of the referenced rows of A
+        # (the non-empty rows of S, in R's order), the packed buffers are all-gathered, row i of the list is unpacked
+        # to row R[i]: every referenced row arrives exactly once, nothing else is touched
+        per = -(-len(R) // world)
+        beg, end = mg.packed_share(len(R), rank, world)
+        packed = torch.zeros((per, K))
+        packed[: end - beg] = torch.from_numpy(A[R[beg:end].astype(np.int64)])
+        parts = [torch.zeros((per, K)) for _ in range(world)]
+        dist.all_gather(parts, packed)
+        allp = torch.cat(parts)[: len(R)].numpy()
+        dA = np.zeros_like(A)
+        dA[R.astype(np.int64)] = allp
+        ref_rows = np.zeros(S.M, bool)
+        ref_rows[R.astype(np.int64)] = True
+        ok = ok and np.array_equal(dA[ref_rows], A[ref_rows]) and not dA[~ref_rows].any()
+        shares = [mg.packed_share(len(R), r, world) for r in range(world)]
+        ok = ok and shares[0][0] == 0 and shares[-1][1] == len(R) and all(shares[i][1] == shares[i + 1][0] for i in range(world - 1))
         q.put((rank, ok, nnz_mine, S.nnz, [int(c) for c in cuts]))
     finally:
         dist.destroy_process_group()
